@@ -1,0 +1,154 @@
+/*
+ * msha_b200 -- C-ABI of the B200-native (sm_100a) graph-attention + link-scoring hot path of MSHA-GNN.
+ *
+ * The reference (Sienna12321/MSHA--GNN) has no FFI: its boundary is the torch nn.Module surface
+ * (GAT.py:7,20,39,53; Ours.py:30,54,145,160; Ablation.py; HGANE.py:12,37; LLP.py:87,104; model.py:16,34).
+ * The Python package msha_gnn_b200 mirrors that surface and calls the entry points below through ctypes;
+ * every entry cites the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated; fp32 data, int32 CSR indices, int64 at the pair/COO surface
+ *   - the caller owns every buffer (outputs and workspaces); the library never allocates or frees device memory
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered, re-entrant, and never synchronise
+ *   - return value: 0 ok, < 0 invalid argument, > 0 cudaError_t; message via msha_last_error() (thread local)
+ *   - feature tensors are row-major [rows, H, D] (C = H*D contiguous channels per row)
+ *   - attention CSR: a column index c < 0 denotes a "masked" edge to column ~c (rows without neighbours attend
+ *     uniformly to all M columns: softmax of an all -9e15 row, GAT.py:29-31)
+ *   - dropout: Philox4x32-10, element i of stream s is kept iff word_i >= floor(p*2^32); p == 0 disables
+ */
+#ifndef MSHA_B200_H
+#define MSHA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* activation codes */
+#define MSHA_ACT_NONE 0
+#define MSHA_ACT_ELU 1
+#define MSHA_ACT_RELU 2
+#define MSHA_ACT_SIGMOID_RELU 3 /* sigmoid(relu(x)): LinkPredictor, LLP.py:108-115 */
+#define MSHA_ACT_LRELU 4
+#define MSHA_ACT_SIGMOID 5
+
+/* ---- library ---- */
+const char* msha_last_error(void);
+int msha_abi_version(void);
+int msha_check_device(void); /* 0 iff the current device is sm_100 */
+uint64_t msha_launch_count(void); /* kernels launched by this library so far (bench.py gpu_launches) */
+
+/* ---- K-1 graph build: replaces dataset.py:279-296 (inter_adjacent), dataset.py:260-277 (intra_adjacent),
+ *      the dense `adj > 0` masks of GAT.py:30 / Ours.py:67,81-82 and model.py:95-100 (column normalisation) ---- */
+size_t msha_scan_workspace_bytes(int64_t n);
+int msha_scan_exclusive_i32(const int32_t* in, int64_t n_in, int32_t* out, int64_t n_out, void* ws, size_t ws_bytes,
+                            void* stream);
+size_t msha_radix_sort_workspace_bytes(int64_t n);
+int msha_radix_sort_u64(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, int64_t n,
+                        int begin_bit, int end_bit, void* ws, size_t ws_bytes, void* stream);
+size_t msha_csr_from_coo_workspace_bytes(int64_t n, int64_t n_rows, int64_t n_cols);
+int msha_csr_from_coo(const int64_t* src, const int64_t* dst, int64_t n, int64_t n_rows, int64_t n_cols,
+                      int32_t* rowptr, int32_t* col, float* val, int32_t* status, void* ws, size_t ws_bytes,
+                      void* stream);
+size_t msha_csr_from_dense_workspace_bytes(int64_t n_rows);
+int msha_csr_from_dense_rowptr(const float* adj, int64_t n_rows, int64_t n_cols, int64_t ld, int32_t* rowptr, void* ws,
+                               size_t ws_bytes, void* stream);
+int msha_csr_from_dense_fill(const float* adj, int64_t n_rows, int64_t n_cols, int64_t ld, const int32_t* rowptr,
+                             int32_t* col, float* val, void* stream);
+int msha_csr_augment_rowptr(const int32_t* rowptr, int64_t n_rows, int64_t n_cols, int32_t* rowptr_aug, void* ws,
+                            size_t ws_bytes, void* stream);
+int msha_csr_augment_fill(const int32_t* rowptr, const int32_t* col, int64_t n_rows, int64_t n_cols,
+                          const int32_t* rowptr_aug, int32_t* col_aug, void* stream);
+size_t msha_csc_from_csr_workspace_bytes(int64_t nnz, int64_t n_cols);
+int msha_csc_from_csr(const int32_t* rowptr, const int32_t* col, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                      int32_t* colptr, int32_t* rowidx, int32_t* perm, void* ws, size_t ws_bytes, void* stream);
+int msha_csr_normalize_columns(const int32_t* col, const float* val, int64_t nnz, int64_t n_cols, float* colsum,
+                               float* out, void* stream);
+
+/* ---- K-2/K-3 fused logit + segmented softmax + aggregation: replaces Ours.py:64-69,98 / Ablation.py:265-271,274 /
+ *      HGANE.py:46-47,66-68.  alpha_in != NULL -> plain weighted SpMM (K-3 only). ---- */
+int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr, const float* s_self,
+                 const float* feat, int H, int D, float slope, const float* alpha_in, float* alpha_out, float* out,
+                 int act, float drop_p, uint64_t drop_seed, void* stream);
+/* backward row pass (autograd of the lines above): d alpha, softmax and LeakyReLU backward, d s_self */
+int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
+                      const float* s_self, float slope, const float* alpha, const float* feat, const float* dout,
+                      const float* out, int act, float* dz_out, const float* dT, const float* fT,
+                      const float* dalpha_extra, int H, int D, float* dlogit, float* ds_self, float drop_p,
+                      uint64_t drop_seed, void* stream);
+/* ---- K-4 transposed SpMM over CSC: replaces `attention_inter.t() @ h2` Ours.py:100 and the d feat pass ---- */
+int msha_spmm_csc(const int32_t* colptr, const int32_t* rowidx, const int32_t* perm, int64_t n_cols, const float* w,
+                  const float* feat, int H, int D, float* out, int accumulate, const float* esum_in, float* esum_out,
+                  float drop_p, uint64_t drop_seed, void* stream);
+/* node-level pieces of the logit: s = Wh . a (Ours.py:64: matmul(inter_input, a)) and its backward */
+int msha_node_scores(const float* feat, int64_t n, int H, int D, const float* a1, float* s1, const float* a2,
+                     float* s2, void* stream);
+int msha_node_outer_add(float* out, int64_t n, int H, int D, const float* s1, const float* a1, const float* s2,
+                        const float* a2, int accumulate, void* stream);
+size_t msha_colreduce_workspace_bytes(int C);
+int msha_colreduce(const float* x, const float* y, const float* s, int64_t n, int C, int D, float* out, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/* ---- K-7 feature transform Wh = X @ W (GAT.py:21, Ours.py:57-58) and K-8 u @ v.T + ELU (Ours.py:108-109) ---- */
+int msha_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                  int64_t ldc, int transA, int transB, const float* bias, float beta, int act, float slope,
+                  void* stream);
+
+/* ---- a-1 GraphAttentionLayer epilogue: replaces GAT.py:24-35 (uniform masked softmax, elu(att*h)) ---- */
+int msha_gal_fwd(const float* h, const int32_t* rowptr, const int32_t* col, int64_t n_rows, int H, int64_t M,
+                 float* out, float drop_p, uint64_t drop_seed, void* stream);
+int msha_gal_bwd(const float* dout, const float* y, const int32_t* rowptr, const int32_t* col, int64_t n_rows, int H,
+                 int64_t M, float* dh, float drop_p, uint64_t drop_seed, void* stream);
+/* feature dropout F.dropout(x) (Ours.py:161-162,165; GAT.py:54,56); the same call is its backward */
+int msha_dropout_apply(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t stream_id, void* stream);
+
+/* ---- K-5 intra-scale (city / province) block: replaces Ours.py:71-90,99 without the (B,N)/(N,N) dense tensors ---- */
+int msha_rowsum_exp(const int32_t* rowptr, const float* alpha, int H, const int64_t* src, int64_t B, int64_t n_cols,
+                    float* T, float drop_p, uint64_t drop_seed, void* stream);
+int msha_rowsum_exp_bwd(const int32_t* rowptr, const float* alpha, int H, const int64_t* src, int64_t B,
+                        const float* dT, float* dalpha, float drop_p, uint64_t drop_seed, void* stream);
+int msha_group_scatter_add(const int32_t* rowptr, const int32_t* col, const int32_t* row_map, const int64_t* src,
+                           int64_t B, int64_t n_nodes, const float* coef, const float* feat, int H, int D, float* out,
+                           float drop_p, uint64_t drop_seed, uint32_t drop_stream, void* stream);
+int msha_group_gather_sum(const int32_t* rowptr, const int32_t* col, const int32_t* row_map, const int64_t* src,
+                          int64_t B, int64_t n_nodes, const float* dout, int H, int D, float* G, float drop_p,
+                          uint64_t drop_seed, uint32_t drop_stream, void* stream);
+
+/* ---- activations (F.elu / F.leaky_relu / relu / sigmoid call sites) ---- */
+int msha_act_fwd(const float* x, float* y, int64_t n, int act, float slope, void* stream);
+int msha_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, float slope, void* stream);
+
+/* ---- K-6 BatchNorm1d over the node axis + LeakyReLU: replaces leakyrelu(bn(.)) Ours.py:100-101 ---- */
+size_t msha_bn_workspace_bytes(int C);
+int msha_bn_lrelu_fwd(const float* x, int64_t n, int C, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, int training, float momentum, float eps, float slope, float* y,
+                      float* save_mean, float* save_invstd, void* ws, size_t ws_bytes, void* stream);
+int msha_bn_lrelu_bwd(const float* dy, const float* y, const float* x, int64_t n, int C, const float* gamma,
+                      const float* save_mean, const float* save_invstd, int training, float slope, float* dx,
+                      float* xhat, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- read-out: log_softmax(elu(x)) rows, Ours.py:166-167 / GAT.py:57-58 ---- */
+int msha_log_softmax_fwd(const float* x, int64_t n, int64_t M, int pre_elu, float* y, void* stream);
+int msha_log_softmax_bwd(const float* dy, const float* y, const float* x, int64_t n, int64_t M, int pre_elu, float* dx,
+                         void* stream);
+
+/* ---- K-9 link scorer: replaces LinkPredictor.forward LLP.py:104-115 (x_i*x_j, Linear, ReLU, sigmoid) ---- */
+int msha_pair_gather_mul(const float* hi, const float* hj, const int64_t* src, const int64_t* dst, int64_t P, int64_t C,
+                         float* z, void* stream);
+int msha_pair_scatter_mul_add(const float* dz, const float* hi, const float* hj, const int64_t* src,
+                              const int64_t* dst, int64_t P, int64_t C, float* dhi, float* dhj, void* stream);
+int msha_pair_dot(const float* hi, const float* hj, const int64_t* src, const int64_t* dst, int64_t P, int64_t C,
+                  int act, float* out, void* stream);
+int msha_pair_dot_bwd(const float* dout, const float* out, const float* hi, const float* hj, const int64_t* src,
+                      const int64_t* dst, int64_t P, int64_t C, int act, float* dhi, float* dhj, void* stream);
+/* builder-defined sampler (the reference's --ns_rate flags are dead code, LLP.py:26-29) */
+int msha_negative_sample(uint64_t seed, int64_t P, int64_t n_src, int64_t n_dst, int64_t* src, int64_t* dst,
+                         void* stream);
+int msha_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* keep, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSHA_B200_H */

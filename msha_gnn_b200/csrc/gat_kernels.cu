@@ -1,0 +1,603 @@
+// K-2/K-3/K-4: edge kernels of the graph-attention hot path (all fp32, int32 CSR).
+//
+//   gat_fwd        per destination row: SDDMM logit  e_ij = lrelu(s_nbr[j] + s_self[i])   (Ours.py:64-65)
+//                  + masked row softmax (Ours.py:66-68) + dropout (Ours.py:69)
+//                  + weighted aggregation out_i = sum_j alpha_ij feat[j]                    (Ours.py:98)
+//                  for H heads at once (feat is [n, H, D]); optional fused ELU.
+//   gat_bwd_rows   per row: d alpha = dOut_i . feat_j (+ dT_j . fT_i), softmax/LeakyReLU backward,
+//                  d s_self, writes d logit per edge.
+//   spmm_csc       per column (CSC + perm): out_j = sum_i w_ij feat[i]  (alpha.T @ h2, Ours.py:100, and the
+//                  d feat pass of the backward), optional per-column sums of a second edge array.
+//
+// Mapping: one warp per row/column; lanes tile the C = H*D channels in VW-wide vectors (VW = 4 -> 128-bit
+// loads), VPL vectors per lane.  Per-edge weights of the current 32-edge chunk are staged in shared memory.
+// Masked edges (col < 0, j = ~col) are the reference's isolated-row semantics: logit = -9e15, no gradient.
+#include "common.cuh"
+
+#define NEG_MASK_F (-9e15f)
+
+constexpr int GAT_WARPS = 8;
+constexpr int GAT_THREADS = GAT_WARPS * 32;
+
+template <int VW> struct VecT;
+template <> struct VecT<4> {
+    static __device__ __forceinline__ void load(const float* p, float (&r)[4]) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&r)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+};
+template <> struct VecT<1> {
+    static __device__ __forceinline__ void load(const float* p, float (&r)[1]) { r[0] = __ldg(p); }
+    static __device__ __forceinline__ void store(float* p, const float (&r)[1]) { *p = r[0]; }
+};
+
+__device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+struct DropArgs {
+    uint32_t thr;       // keep iff philox word >= thr ; 0 -> dropout inactive
+    float inv_keep;     // 1/(1-p)
+    uint64_t seed;
+    uint32_t stream;
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int VW, int VPL>
+__global__ void __launch_bounds__(GAT_THREADS)
+gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_rows,
+               const float* __restrict__ s_nbr, const float* __restrict__ s_self,
+               const float* __restrict__ feat, int H, int D, float slope,
+               const float* __restrict__ alpha_in, float* __restrict__ alpha_out,
+               float* __restrict__ out, int act, DropArgs drop) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * GAT_WARPS + warp;
+    if (row >= n_rows) return;
+    float* sm_w = smem + warp * 32 * H;
+    const int C = H * D;
+    const int nvec = C / VW;
+    const int beg = rowptr[row], end = rowptr[row + 1];
+
+    int head_of[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        int v = lane + 32 * k;
+        head_of[k] = (v < nvec) ? (v * VW) / D : 0;
+    }
+
+    // ---- softmax statistics: lane h keeps (max, sum) of head h
+    float m_stat = 0.f, l_stat = 1.f;
+    if (alpha_in == nullptr) {
+        for (int h = 0; h < H; ++h) {
+            const float ss = s_self[(int64_t)row * H + h];
+            float mx = -INFINITY;
+            for (int e = beg + lane; e < end; e += 32) {
+                int c = col[e];
+                float lg = c < 0 ? NEG_MASK_F : lrelu(__ldg(s_nbr + (int64_t)c * H + h) + ss, slope);
+                mx = fmaxf(mx, lg);
+            }
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int e = beg + lane; e < end; e += 32) {
+                int c = col[e];
+                float lg = c < 0 ? NEG_MASK_F : lrelu(__ldg(s_nbr + (int64_t)c * H + h) + ss, slope);
+                sum += expf(lg - mx);
+            }
+            sum = warp_sum(sum);
+            if (lane == h) { m_stat = mx; l_stat = sum; }
+        }
+    }
+
+    float acc[VPL][VW];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int q = 0; q < VW; ++q) acc[k][q] = 0.f;
+
+    for (int e0 = beg; e0 < end; e0 += 32) {
+        const int e = e0 + lane;
+        const bool valid = e < end;
+        const int c = valid ? col[e] : 0;
+        const bool masked = c < 0;
+        const int j = masked ? ~c : c;
+        for (int h = 0; h < H; ++h) {
+            const float mh = __shfl_sync(FULL_MASK, m_stat, h);
+            const float lh = __shfl_sync(FULL_MASK, l_stat, h);
+            float a = 0.f;
+            if (valid) {
+                if (alpha_in != nullptr) {
+                    a = alpha_in[(int64_t)e * H + h];
+                } else {
+                    float lg = masked ? NEG_MASK_F
+                                      : lrelu(__ldg(s_nbr + (int64_t)j * H + h) + s_self[(int64_t)row * H + h], slope);
+                    a = expf(lg - mh) / lh;
+                    if (alpha_out) alpha_out[(int64_t)e * H + h] = a;
+                }
+                if (drop.thr) a *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + h, drop.thr, drop.inv_keep);
+            }
+            sm_w[lane * H + h] = a;
+        }
+        __syncwarp();
+        const int cnt = min(32, end - e0);
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+            const int jt = __shfl_sync(FULL_MASK, j, t);
+            const float* f = feat + (int64_t)jt * C;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                const int v = lane + 32 * k;
+                if (v < nvec) {
+                    float x[VW];
+                    VecT<VW>::load(f + v * VW, x);
+                    const float w = sm_w[t * H + head_of[k]];
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) acc[k][q] = fmaf(w, x[q], acc[k][q]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int v = lane + 32 * k;
+        if (v < nvec) {
+            if (act == 1) {
+#pragma unroll
+                for (int q = 0; q < VW; ++q) acc[k][q] = elu1(acc[k][q]);
+            }
+            VecT<VW>::store(out + (int64_t)row * C + v * VW, acc[k]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, row pass
+// ---------------------------------------------------------------------------------------------
+template <int VW, int VPL>
+__global__ void __launch_bounds__(GAT_THREADS)
+gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_rows,
+                    const float* __restrict__ s_nbr, const float* __restrict__ s_self, float slope,
+                    const float* __restrict__ alpha, const float* __restrict__ feat,
+                    const float* __restrict__ dout, const float* __restrict__ outp, int act,
+                    float* __restrict__ dz_out,
+                    const float* __restrict__ dT, const float* __restrict__ fT,
+                    const float* __restrict__ dalpha_extra,
+                    int H, int D, float* __restrict__ dlogit, float* __restrict__ ds_self, DropArgs drop) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * GAT_WARPS + warp;
+    if (row >= n_rows) return;
+    float* sm_d = smem + warp * (32 * H + 2 * H);
+    float* sm_r = sm_d + 32 * H;
+    float* sm_ds = sm_r + H;
+    const int C = H * D;
+    const int nvec = C / VW;
+    const int LPH = D / VW;                        // lanes (vectors) per head
+    const bool pow2 = (LPH & (LPH - 1)) == 0;
+    const int beg = rowptr[row], end = rowptr[row + 1];
+    const bool softmax_mode = (s_nbr != nullptr);
+
+    float dz[VPL][VW], ft[VPL][VW];
+    int head_of[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int v = lane + 32 * k;
+        head_of[k] = (v < nvec) ? (v * VW) / D : 0;
+#pragma unroll
+        for (int q = 0; q < VW; ++q) { dz[k][q] = 0.f; ft[k][q] = 0.f; }
+        if (v < nvec) {
+            VecT<VW>::load(dout + (int64_t)row * C + v * VW, dz[k]);
+            if (act == 1) {
+                float o[VW];
+                VecT<VW>::load(outp + (int64_t)row * C + v * VW, o);
+#pragma unroll
+                for (int q = 0; q < VW; ++q) dz[k][q] = o[q] > 0.f ? dz[k][q] : dz[k][q] * (o[q] + 1.f);
+            }
+            if (dz_out) VecT<VW>::store(dz_out + (int64_t)row * C + v * VW, dz[k]);
+            if (fT) VecT<VW>::load(fT + (int64_t)row * C + v * VW, ft[k]);
+        }
+    }
+    for (int h = lane; h < 2 * H; h += 32) sm_r[h] = 0.f;   // sm_r and sm_ds are contiguous
+    __syncwarp();
+
+    // ---- phase 1: d alpha per edge (-> dlogit as scratch), r_h = sum alpha * dalpha
+    for (int e0 = beg; e0 < end; e0 += 32) {
+        const int e = e0 + lane;
+        const bool valid = e < end;
+        const int c = valid ? col[e] : 0;
+        const int j = c < 0 ? ~c : c;
+        for (int q = lane; q < 32 * H; q += 32) sm_d[q] = 0.f;
+        __syncwarp();
+        const int cnt = min(32, end - e0);
+#pragma unroll 2
+        for (int t = 0; t < cnt; ++t) {
+            const int jt = __shfl_sync(FULL_MASK, j, t);
+            const float* f = feat + (int64_t)jt * C;
+            const float* g = dT ? dT + (int64_t)jt * C : nullptr;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                const int v = lane + 32 * k;
+                float p = 0.f;
+                if (v < nvec) {
+                    float x[VW];
+                    VecT<VW>::load(f + v * VW, x);
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) p = fmaf(x[q], dz[k][q], p);
+                    if (g) {
+                        float y[VW];
+                        VecT<VW>::load(g + v * VW, y);
+#pragma unroll
+                        for (int q = 0; q < VW; ++q) p = fmaf(y[q], ft[k][q], p);
+                    }
+                }
+                if (pow2) {
+                    if (LPH >= 32) {
+                        p = warp_sum(p);
+                        if (lane == 0 && (32 * k) < nvec) sm_d[t * H + head_of[k]] += p;
+                    } else {
+                        for (int o = LPH >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(FULL_MASK, p, o);
+                        if ((lane & (LPH - 1)) == 0 && v < nvec) sm_d[t * H + head_of[k]] += p;
+                    }
+                } else if (v < nvec) {
+                    atomicAdd(&sm_d[t * H + head_of[k]], p);
+                }
+            }
+        }
+        __syncwarp();
+        for (int h = 0; h < H; ++h) {
+            float da = 0.f, a = 0.f;
+            if (valid) {
+                da = sm_d[lane * H + h];
+                if (drop.thr) da *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + h, drop.thr, drop.inv_keep);
+                if (dalpha_extra) da += dalpha_extra[(int64_t)e * H + h];   // grad w.r.t. the pre-dropout alpha
+                if (softmax_mode) a = alpha[(int64_t)e * H + h];
+                dlogit[(int64_t)e * H + h] = da;
+            }
+            if (softmax_mode) {
+                float s = warp_sum(a * da);
+                if (lane == 0) sm_r[h] += s;
+            }
+        }
+        __syncwarp();
+    }
+    if (!softmax_mode) return;
+
+    // ---- phase 2: softmax + LeakyReLU backward
+    for (int e0 = beg; e0 < end; e0 += 32) {
+        const int e = e0 + lane;
+        const bool valid = e < end;
+        const int c = valid ? col[e] : 0;
+        const bool masked = c < 0;
+        const int j = masked ? ~c : c;
+        for (int h = 0; h < H; ++h) {
+            float dl = 0.f;
+            if (valid) {
+                const float a = alpha[(int64_t)e * H + h];
+                const float da = dlogit[(int64_t)e * H + h];
+                const float de = a * (da - sm_r[h]);
+                const float pre = __ldg(s_nbr + (int64_t)j * H + h) + s_self[(int64_t)row * H + h];
+                dl = masked ? 0.f : (pre > 0.f ? de : de * slope);
+                dlogit[(int64_t)e * H + h] = dl;
+            }
+            float s = warp_sum(dl);
+            if (lane == 0) sm_ds[h] += s;
+        }
+    }
+    __syncwarp();
+    if (ds_self)
+        for (int h = lane; h < H; h += 32) ds_self[(int64_t)row * H + h] = sm_ds[h];
+}
+
+// ---------------------------------------------------------------------------------------------
+// column pass (CSC + perm)
+// ---------------------------------------------------------------------------------------------
+template <int VW, int VPL>
+__global__ void __launch_bounds__(GAT_THREADS)
+spmm_csc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowidx,
+                const int32_t* __restrict__ perm, int n_cols,
+                const float* __restrict__ w, const float* __restrict__ feat, int H, int D,
+                float* __restrict__ out, int accumulate,
+                const float* __restrict__ esum_in, float* __restrict__ esum_out, DropArgs drop) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cidx = blockIdx.x * GAT_WARPS + warp;
+    if (cidx >= n_cols) return;
+    float* sm_w = smem + warp * (32 * H + H);
+    float* sm_s = sm_w + 32 * H;
+    const int C = H * D;
+    const int nvec = C / VW;
+    const int beg = colptr[cidx], end = colptr[cidx + 1];
+
+    int head_of[VPL];
+    float acc[VPL][VW];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int v = lane + 32 * k;
+        head_of[k] = (v < nvec) ? (v * VW) / D : 0;
+#pragma unroll
+        for (int q = 0; q < VW; ++q) acc[k][q] = 0.f;
+    }
+    for (int h = lane; h < H; h += 32) sm_s[h] = 0.f;
+    __syncwarp();
+
+    for (int k0 = beg; k0 < end; k0 += 32) {
+        const int kk = k0 + lane;
+        const bool valid = kk < end;
+        const int i = valid ? rowidx[kk] : 0;
+        const int e = valid ? perm[kk] : 0;
+        for (int h = 0; h < H; ++h) {
+            float a = 0.f, s = 0.f;
+            if (valid) {
+                a = w ? w[(int64_t)e * H + h] : 0.f;
+                if (drop.thr) a *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + h, drop.thr, drop.inv_keep);
+                if (esum_in) s = esum_in[(int64_t)e * H + h];
+            }
+            sm_w[lane * H + h] = a;
+            if (esum_in) {
+                s = warp_sum(s);
+                if (lane == 0) sm_s[h] += s;
+            }
+        }
+        __syncwarp();
+        if (w) {
+            const int cnt = min(32, end - k0);
+#pragma unroll 4
+            for (int t = 0; t < cnt; ++t) {
+                const int it = __shfl_sync(FULL_MASK, i, t);
+                const float* f = feat + (int64_t)it * C;
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    const int v = lane + 32 * k;
+                    if (v < nvec) {
+                        float x[VW];
+                        VecT<VW>::load(f + v * VW, x);
+                        const float ww = sm_w[t * H + head_of[k]];
+#pragma unroll
+                        for (int q = 0; q < VW; ++q) acc[k][q] = fmaf(ww, x[q], acc[k][q]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (w) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int v = lane + 32 * k;
+            if (v < nvec) {
+                float* o = out + (int64_t)cidx * C + v * VW;
+                if (accumulate) {
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) acc[k][q] += o[q];
+                }
+                VecT<VW>::store(o, acc[k]);
+            }
+        }
+    }
+    if (esum_out)
+        for (int h = lane; h < H; h += 32) esum_out[(int64_t)cidx * H + h] = sm_s[h];
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+static int pick_layout(int H, int D, int* vw, int* vpl) {
+    const int C = H * D;
+    if (D % 4 == 0) {
+        int nvec = C / 4;
+        *vw = 4;
+        *vpl = nvec <= 32 ? 1 : (nvec <= 64 ? 2 : (nvec <= 128 ? 4 : 0));
+        if (*vpl) return 0;
+    }
+    *vw = 1;
+    *vpl = C <= 32 ? 1 : (C <= 64 ? 2 : (C <= 128 ? 4 : (C <= 256 ? 8 : 0)));
+    return *vpl ? 0 : -1;
+}
+
+static DropArgs make_drop(float p, uint64_t seed, uint32_t stream) {
+    DropArgs d;
+    d.thr = 0; d.inv_keep = 1.f; d.seed = seed; d.stream = stream;
+    if (p > 0.f) {
+        double t = (double)p * 4294967296.0;
+        d.thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+        if (d.thr == 0) d.thr = 1;                      // p tiny but > 0
+        d.inv_keep = 1.f / (1.f - p);
+    }
+    return d;
+}
+
+#define DISPATCH_LAYOUT(VWv, VPLv, CALL)                        \
+    if (VWv == 4 && VPLv == 1) { CALL(4, 1); }                  \
+    else if (VWv == 4 && VPLv == 2) { CALL(4, 2); }             \
+    else if (VWv == 4 && VPLv == 4) { CALL(4, 4); }             \
+    else if (VWv == 1 && VPLv == 1) { CALL(1, 1); }             \
+    else if (VWv == 1 && VPLv == 2) { CALL(1, 2); }             \
+    else if (VWv == 1 && VPLv == 4) { CALL(1, 4); }             \
+    else { CALL(1, 8); }
+
+// alpha_in == NULL: compute softmax attention from (s_nbr, s_self) and optionally store it in alpha_out.
+// alpha_in != NULL: plain weighted SpMM with the given per-edge, per-head weights.
+MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
+                          const float* s_self, const float* feat, int H, int D, float slope, const float* alpha_in,
+                          float* alpha_out, float* out, int act, float drop_p, uint64_t drop_seed, void* stream) {
+    MSHA_REQUIRE(H >= 1 && H <= 32 && D >= 1, "gat_fwd: need 1 <= H <= 32, D >= 1");
+    MSHA_REQUIRE(alpha_in != nullptr || (s_nbr != nullptr && s_self != nullptr), "gat_fwd: scores or alpha required");
+    MSHA_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), "gat_fwd: bad n_rows");
+    int vw, vpl;
+    MSHA_REQUIRE(pick_layout(H, D, &vw, &vpl) == 0, "gat_fwd: unsupported channel count H*D=%d", H * D);
+    if (n_rows == 0) return 0;
+    DropArgs drop = make_drop(drop_p, drop_seed, 2u);
+    const unsigned grid = (unsigned)msha_cdiv(n_rows, GAT_WARPS);
+    const size_t smem = (size_t)GAT_WARPS * 32 * H * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(A, B)                                                                                             \
+    gat_fwd_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, feat, H, D, \
+                                                          slope, alpha_in, alpha_out, out, act, drop)
+    DISPATCH_LAYOUT(vw, vpl, CALL)
+#undef CALL
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+// Row pass of the backward.  s_nbr == NULL -> no softmax: dlogit receives d(weights).
+MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
+                               const float* s_self, float slope, const float* alpha, const float* feat,
+                               const float* dout, const float* out, int act, float* dz_out, const float* dT,
+                               const float* fT, const float* dalpha_extra, int H, int D, float* dlogit,
+                               float* ds_self, float drop_p, uint64_t drop_seed, void* stream) {
+    MSHA_REQUIRE(H >= 1 && H <= 32 && D >= 1, "gat_bwd_rows: need 1 <= H <= 32, D >= 1");
+    MSHA_REQUIRE((dT == nullptr) == (fT == nullptr), "gat_bwd_rows: dT and fT go together");
+    MSHA_REQUIRE(act == 0 || out != nullptr, "gat_bwd_rows: activated output needed for ELU backward");
+    MSHA_REQUIRE(s_nbr == nullptr || (s_self != nullptr && alpha != nullptr), "gat_bwd_rows: softmax mode needs s_self, alpha");
+    int vw, vpl;
+    MSHA_REQUIRE(pick_layout(H, D, &vw, &vpl) == 0, "gat_bwd_rows: unsupported channel count H*D=%d", H * D);
+    if (n_rows == 0) return 0;
+    DropArgs drop = make_drop(drop_p, drop_seed, 2u);
+    const unsigned grid = (unsigned)msha_cdiv(n_rows, GAT_WARPS);
+    const size_t smem = (size_t)GAT_WARPS * (32 * H + 2 * H) * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(A, B)                                                                                              \
+    gat_bwd_rows_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, slope,  \
+                                                               alpha, feat, dout, out, act, dz_out, dT, fT,     \
+                                                               dalpha_extra, H, D, dlogit, ds_self, drop)
+    DISPATCH_LAYOUT(vw, vpl, CALL)
+#undef CALL
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+// out[j] (+)= sum_{i in col j} w[perm]*feat[i];  esum_out[j,h] = sum esum_in[perm,h].   w may be NULL (sums only).
+MSHA_API int msha_spmm_csc(const int32_t* colptr, const int32_t* rowidx, const int32_t* perm, int64_t n_cols,
+                           const float* w, const float* feat, int H, int D, float* out, int accumulate,
+                           const float* esum_in, float* esum_out, float drop_p, uint64_t drop_seed, void* stream) {
+    MSHA_REQUIRE(H >= 1 && H <= 32 && D >= 1, "spmm_csc: need 1 <= H <= 32, D >= 1");
+    MSHA_REQUIRE(w == nullptr || (feat != nullptr && out != nullptr), "spmm_csc: feat/out required with weights");
+    MSHA_REQUIRE((esum_in == nullptr) == (esum_out == nullptr), "spmm_csc: esum_in/esum_out go together");
+    int vw, vpl;
+    MSHA_REQUIRE(pick_layout(H, D, &vw, &vpl) == 0, "spmm_csc: unsupported channel count H*D=%d", H * D);
+    if (n_cols == 0) return 0;
+    DropArgs drop = make_drop(drop_p, drop_seed, 2u);
+    const unsigned grid = (unsigned)msha_cdiv(n_cols, GAT_WARPS);
+    const size_t smem = (size_t)GAT_WARPS * (32 * H + H) * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(A, B)                                                                                             \
+    spmm_csc_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(colptr, rowidx, perm, (int)n_cols, w, feat, H, D,   \
+                                                           out, accumulate, esum_in, esum_out, drop)
+    DISPATCH_LAYOUT(vw, vpl, CALL)
+#undef CALL
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// node-level helpers
+// ---------------------------------------------------------------------------------------------
+// s1[n,h] = sum_d feat[n,h,d]*a1[h,d] ; s2 likewise (a2/s2 optional)
+__global__ void node_scores_kernel(const float* __restrict__ feat, int64_t n, int H, int D,
+                                   const float* __restrict__ a1, float* __restrict__ s1,
+                                   const float* __restrict__ a2, float* __restrict__ s2) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float* f = feat + row * (int64_t)H * D;
+    for (int h = 0; h < H; ++h) {
+        float p1 = 0.f, p2 = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            float x = f[h * D + d];
+            p1 = fmaf(x, a1[h * D + d], p1);
+            if (a2) p2 = fmaf(x, a2[h * D + d], p2);
+        }
+        p1 = warp_sum(p1);
+        if (a2) p2 = warp_sum(p2);
+        if (lane == 0) {
+            s1[row * H + h] = p1;
+            if (a2) s2[row * H + h] = p2;
+        }
+    }
+}
+
+MSHA_API int msha_node_scores(const float* feat, int64_t n, int H, int D, const float* a1, float* s1,
+                              const float* a2, float* s2, void* stream) {
+    MSHA_REQUIRE(H >= 1 && D >= 1 && n >= 0, "node_scores: bad shape");
+    if (n == 0) return 0;
+    node_scores_kernel<<<(unsigned)msha_cdiv(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(feat, n, H, D, a1, s1, a2, s2);
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+// out[n,h,d] (+)= s1[n,h]*a1[h,d] + s2[n,h]*a2[h,d]
+__global__ void node_outer_kernel(float* __restrict__ out, int64_t n, int H, int D, const float* __restrict__ s1,
+                                  const float* __restrict__ a1, const float* __restrict__ s2,
+                                  const float* __restrict__ a2, int accumulate) {
+    const int C = H * D;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * C) return;
+    const int64_t row = idx / C;
+    const int ch = (int)(idx - row * C);
+    const int h = ch / D;
+    float v = s1[row * H + h] * a1[ch];
+    if (s2) v = fmaf(s2[row * H + h], a2[ch], v);
+    out[idx] = accumulate ? out[idx] + v : v;
+}
+
+MSHA_API int msha_node_outer_add(float* out, int64_t n, int H, int D, const float* s1, const float* a1,
+                                 const float* s2, const float* a2, int accumulate, void* stream) {
+    MSHA_REQUIRE(H >= 1 && D >= 1 && n >= 0, "node_outer_add: bad shape");
+    MSHA_REQUIRE((s2 == nullptr) == (a2 == nullptr), "node_outer_add: s2/a2 go together");
+    if (n == 0) return 0;
+    node_outer_kernel<<<(unsigned)msha_cdiv(n * H * D, 256), 256, 0, (cudaStream_t)stream>>>(out, n, H, D, s1, a1, s2, a2,
+                                                                                          accumulate);
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+// Column reduction over nodes:  out[c] = sum_n x[n,c] * (y ? y[n,c] : 1) * (s ? s[n, c/D] : 1)
+// two stages through `partial` ([COLRED_BLOCKS, C] doubles) for a deterministic result.
+constexpr int COLRED_BLOCKS = 296;
+__global__ void colreduce_stage1(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ s,
+                                 int64_t n, int C, int D, double* __restrict__ partial) {
+    const int64_t rows_per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = blockIdx.x * rows_per;
+    const int64_t r1 = r0 + rows_per < n ? r0 + rows_per : n;
+    const int H = C / D;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double acc = 0.0;
+        const int h = c / D;
+        for (int64_t r = r0; r < r1; ++r) {
+            float v = x[r * C + c];
+            if (y) v *= y[r * C + c];
+            if (s) v *= s[r * H + h];
+            acc += (double)v;
+        }
+        partial[(int64_t)blockIdx.x * C + c] = acc;
+    }
+}
+__global__ void colreduce_stage2(const double* __restrict__ partial, int nblocks, int C, float* __restrict__ out,
+                                 double* __restrict__ out_d) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * C + c];
+    if (out) out[c] = (float)acc;
+    if (out_d) out_d[c] = acc;
+}
+
+MSHA_API size_t msha_colreduce_workspace_bytes(int C) { return (size_t)COLRED_BLOCKS * C * sizeof(double); }
+
+MSHA_API int msha_colreduce(const float* x, const float* y, const float* s, int64_t n, int C, int D, float* out,
+                            void* ws, size_t ws_bytes, void* stream) {
+    MSHA_REQUIRE(C >= 1 && D >= 1 && C % D == 0 && n >= 0, "colreduce: bad shape");
+    MSHA_REQUIRE(ws_bytes >= msha_colreduce_workspace_bytes(C), "colreduce: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int nb = (int)(n < COLRED_BLOCKS ? (n > 0 ? n : 1) : COLRED_BLOCKS);
+    colreduce_stage1<<<nb, 256, 0, st>>>(x, y, s, n, C, D, (double*)ws);
+    MSHA_LAUNCH_OK();
+    colreduce_stage2<<<(unsigned)msha_cdiv(C, 128), 128, 0, st>>>((const double*)ws, nb, C, out, nullptr);
+    MSHA_LAUNCH_OK();
+    return 0;
+}

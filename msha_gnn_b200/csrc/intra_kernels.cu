@@ -1,0 +1,162 @@
+// K-5: intra-scale (city / province) block of OursLayer (Ours.py:71-90,99) without the (B,N) / (N,N) dense
+// tensors.  The logit of a batch row is a row constant, so att3[b, n] = coef3[b] for every member n of the
+// batch row's group: the (B,N)@(B,d') products collapse into segment broadcasts / segment sums.
+//
+//   rowsum_exp        T[b,h] = sum_{j<M} exp(alpha_drop[src_b, j, h])        third term of SUM_county, Ours.py:86
+//                     (non-edges contribute e^0 = 1; duplicates in src handled row by row)
+//   group_scatter_add out[n] += coef[b,h] * drop * feat[b,h,:]  for n in list(src_b)   att3.t() @ h2_  Ours.py:99
+//   group_gather_sum  G[b]   = sum_{n in list(src_b)} drop * dout[n]                    its backward
+//
+// list(r) = col[rowptr[k] .. rowptr[k+1]) with k = row_map ? row_map[r] : r  (generic CSR of a dense (N,N)
+// adjacency, or group-member lists when the adjacency is a group-equality block structure).
+#include "common.cuh"
+
+struct DropI { uint32_t thr; float inv_keep; uint64_t seed; uint32_t stream; };
+static DropI make_drop_i(float p, uint64_t seed, uint32_t stream) {
+    DropI d; d.thr = 0; d.inv_keep = 1.f; d.seed = seed; d.stream = stream;
+    if (p > 0.f) {
+        double t = (double)p * 4294967296.0;
+        d.thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+        if (d.thr == 0) d.thr = 1;
+        d.inv_keep = 1.f / (1.f - p);
+    }
+    return d;
+}
+
+// one warp per batch entry
+__global__ void rowsum_exp_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ alpha, int H,
+                                  const int64_t* __restrict__ src, int64_t B, int n_cols, float* __restrict__ T,
+                                  DropI drop) {
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int64_t r = src[b];
+    const int beg = rowptr[r], end = rowptr[r + 1];
+    for (int h = 0; h < H; ++h) {
+        float s = 0.f;
+        for (int e = beg + lane; e < end; e += 32) {
+            float a = alpha[(int64_t)e * H + h];
+            if (drop.thr) a *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + h, drop.thr, drop.inv_keep);
+            s += expf(a);
+        }
+        s = warp_sum(s);
+        if (lane == 0) T[b * H + h] = s + (float)(n_cols - (end - beg));
+    }
+}
+// dalpha[e,h] += dT[b,h] * exp(alpha*k) * k      (dalpha zero-initialised by the caller)
+__global__ void rowsum_exp_bwd_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ alpha, int H,
+                                      const int64_t* __restrict__ src, int64_t B, const float* __restrict__ dT,
+                                      float* __restrict__ dalpha, DropI drop) {
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int64_t r = src[b];
+    const int beg = rowptr[r], end = rowptr[r + 1];
+    for (int h = 0; h < H; ++h) {
+        const float g = dT[b * H + h];
+        for (int e = beg + lane; e < end; e += 32) {
+            float k = 1.f;
+            if (drop.thr) k = dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + h, drop.thr, drop.inv_keep);
+            const float a = alpha[(int64_t)e * H + h] * k;
+            atomicAdd(&dalpha[(int64_t)e * H + h], g * expf(a) * k);
+        }
+    }
+}
+
+MSHA_API int msha_rowsum_exp(const int32_t* rowptr, const float* alpha, int H, const int64_t* src, int64_t B,
+                             int64_t n_cols, float* T, float drop_p, uint64_t drop_seed, void* stream) {
+    MSHA_REQUIRE(H >= 1 && B >= 0 && n_cols >= 0, "rowsum_exp: bad shape");
+    if (B == 0) return 0;
+    rowsum_exp_kernel<<<(unsigned)msha_cdiv(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        rowptr, alpha, H, src, B, (int)n_cols, T, make_drop_i(drop_p, drop_seed, 2u));
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+MSHA_API int msha_rowsum_exp_bwd(const int32_t* rowptr, const float* alpha, int H, const int64_t* src, int64_t B,
+                                 const float* dT, float* dalpha, float drop_p, uint64_t drop_seed, void* stream) {
+    MSHA_REQUIRE(H >= 1 && B >= 0, "rowsum_exp_bwd: bad shape");
+    if (B == 0) return 0;
+    rowsum_exp_bwd_kernel<<<(unsigned)msha_cdiv(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        rowptr, alpha, H, src, B, dT, dalpha, make_drop_i(drop_p, drop_seed, 2u));
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+// grid = (B, chunks); each warp of a block handles a strided share of the member list.
+// dropout element index: ((h*B + b) * n_nodes + n)  -- the dense (B,N) attention3 of head h (Ours.py:88).
+__global__ void group_scatter_add_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                         const int32_t* __restrict__ row_map, const int64_t* __restrict__ src, int64_t B,
+                                         int64_t n_nodes, const float* __restrict__ coef, const float* __restrict__ feat,
+                                         int H, int D, float* __restrict__ out, DropI drop) {
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int64_t r = src[b];
+    const int64_t k = row_map ? row_map[r] : r;
+    const int beg = rowptr[k], end = rowptr[k + 1];
+    const int C = H * D;
+    for (int m = beg + blockIdx.y * nwarp + warp; m < end; m += gridDim.y * nwarp) {
+        int n = col[m];
+        n = n < 0 ? ~n : n;
+        for (int c = lane; c < C; c += 32) {
+            const int h = c / D;
+            float w = coef[(int64_t)b * H + h];
+            if (drop.thr)
+                w *= dropout_scale(drop.seed, drop.stream, ((uint64_t)h * B + b) * n_nodes + n, drop.thr, drop.inv_keep);
+            atomicAdd(&out[(int64_t)n * C + c], w * feat[(int64_t)b * C + c]);
+        }
+    }
+}
+// G[b,c] = sum_n drop * dout[n,c]   (atomics across the chunks of one batch entry; G zero-initialised)
+__global__ void group_gather_sum_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                        const int32_t* __restrict__ row_map, const int64_t* __restrict__ src, int64_t B,
+                                        int64_t n_nodes, const float* __restrict__ dout, int H, int D,
+                                        float* __restrict__ G, DropI drop) {
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int64_t r = src[b];
+    const int64_t k = row_map ? row_map[r] : r;
+    const int beg = rowptr[k], end = rowptr[k + 1];
+    const int C = H * D;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        const int h = c < C ? c / D : 0;
+        float acc = 0.f;
+        for (int m = beg + blockIdx.y * nwarp + warp; m < end; m += gridDim.y * nwarp) {
+            int n = col[m];
+            n = n < 0 ? ~n : n;
+            if (c < C) {
+                float w = 1.f;
+                if (drop.thr)
+                    w = dropout_scale(drop.seed, drop.stream, ((uint64_t)h * B + b) * n_nodes + n, drop.thr, drop.inv_keep);
+                acc = fmaf(w, dout[(int64_t)n * C + c], acc);
+            }
+        }
+        if (c < C && acc != 0.f) atomicAdd(&G[(int64_t)b * C + c], acc);
+    }
+}
+
+// out [n_nodes, H*D] must hold the running value (accumulated with atomics).
+MSHA_API int msha_group_scatter_add(const int32_t* rowptr, const int32_t* col, const int32_t* row_map,
+                                    const int64_t* src, int64_t B, int64_t n_nodes, const float* coef, const float* feat,
+                                    int H, int D, float* out, float drop_p, uint64_t drop_seed, uint32_t drop_stream,
+                                    void* stream) {
+    MSHA_REQUIRE(H >= 1 && D >= 1 && B >= 0 && B < ((int64_t)1 << 31), "group_scatter_add: bad shape");
+    if (B == 0) return 0;
+    dim3 grid((unsigned)B, 16);
+    group_scatter_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, row_map, src, B, n_nodes, coef, feat, H, D,
+                                                                   out, make_drop_i(drop_p, drop_seed, drop_stream));
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+// G [B, H*D] must be zero-initialised.
+MSHA_API int msha_group_gather_sum(const int32_t* rowptr, const int32_t* col, const int32_t* row_map, const int64_t* src,
+                                   int64_t B, int64_t n_nodes, const float* dout, int H, int D, float* G, float drop_p,
+                                   uint64_t drop_seed, uint32_t drop_stream, void* stream) {
+    MSHA_REQUIRE(H >= 1 && D >= 1 && B >= 0 && B < ((int64_t)1 << 31), "group_gather_sum: bad shape");
+    if (B == 0) return 0;
+    dim3 grid((unsigned)B, 16);
+    group_gather_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, row_map, src, B, n_nodes, dout, H, D, G,
+                                                                  make_drop_i(drop_p, drop_seed, drop_stream));
+    MSHA_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,487 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels (forward + hand-written backward).
+
+Each Function cites the reference arithmetic it replaces.  Tensors are fp32, contiguous, CUDA;
+outputs and workspaces are allocated through PyTorch's caching allocator and handed to the
+library as raw pointers on the current stream.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .graph import Graph
+from .ops import (ACT_ELU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SIGMOID_RELU, LRELU_SLOPE, call, ptr,
+                  workspace, _stream)
+
+I32 = torch.int32
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear: y = x @ W   (torch.mm(input, self.W) GAT.py:21, Ours.py:57-58)
+# ------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W):
+        x, W = _c(x), _c(W)
+        ctx.save_for_backward(x, W)
+        return ops.gemm(x, W)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = _c(dy)
+        dx = ops.gemm(dy, W, transB=True) if ctx.needs_input_grad[0] else None
+        dW = ops.gemm(x, dy, transA=True) if ctx.needs_input_grad[1] else None
+        return dx, dW
+
+
+def linear(x, W):
+    return _Linear.apply(x, W)
+
+
+class _LinearBiasAct(torch.autograd.Function):
+    """act(x @ W.T + b) with nn.Linear weight layout [out, in]  (lin(x); F.relu; sigmoid LLP.py:107-115)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        x, W = _c(x), _c(W)
+        y = ops.gemm(x, W, transB=True, bias=b, act=act)
+        ctx.act = act
+        ctx.save_for_backward(x, W, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        dy = _c(dy)
+        g = ops.act_bwd(dy, y, ctx.act) if ctx.act != ACT_NONE else dy
+        dx = ops.gemm(g, W) if ctx.needs_input_grad[0] else None
+        dW = ops.gemm(g, x, transA=True) if ctx.needs_input_grad[1] else None
+        db = colsum(g) if ctx.needs_input_grad[2] else None
+        return dx, dW, db, None
+
+
+def linear_bias_act(x, W, b, act=ACT_NONE):
+    return _LinearBiasAct.apply(x, W, b, act)
+
+
+def colsum(x, y=None, s=None, D=None):
+    """sum over rows of x (* y) (* s broadcast over D-wide heads) -> [C]."""
+    n, C = x.shape
+    out = torch.empty(C, dtype=torch.float32, device=x.device)
+    lib = ops._lib.lib()
+    ws = workspace(lib.msha_colreduce_workspace_bytes(C), x.device)
+    call("msha_colreduce", ptr(x), ptr(y), ptr(s), n, C, D if D else C, ptr(out), ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# activations
+# ------------------------------------------------------------------------------------------------
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        y = ops.act_fwd(_c(x), act)
+        ctx.act = act
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return ops.act_bwd(_c(dy), y, ctx.act), None
+
+
+def elu(x):
+    return _Act.apply(x, ACT_ELU)
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ctx.p, ctx.seed = p, seed
+        return ops.dropout_apply(_c(x), p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout_apply(_c(dy), ctx.p, ctx.seed), None, None
+
+
+def dropout(x, p, training):
+    """F.dropout(x, p, training) with the Philox stream of this library (Ours.py:161-162,165)."""
+    if not training or p == 0.0:
+        return x
+    return _Dropout.apply(x, float(p), ops.next_seed())
+
+
+# ------------------------------------------------------------------------------------------------
+# node scores  s[n,h] = feat[n,h,:] . a[h,:]     (torch.matmul(inter_input, self.a), Ours.py:64)
+# ------------------------------------------------------------------------------------------------
+class _NodeScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, a1, a2, H, D):
+        feat, a1 = _c(feat), _c(a1)
+        n = feat.shape[0]
+        s1 = torch.empty((n, H), dtype=torch.float32, device=feat.device)
+        s2 = torch.empty((n, H), dtype=torch.float32, device=feat.device) if a2 is not None else None
+        if a2 is not None:
+            a2 = _c(a2)
+        call("msha_node_scores", ptr(feat), n, H, D, ptr(a1), ptr(s1), ptr(a2), ptr(s2), _stream())
+        ctx.H, ctx.D = H, D
+        ctx.has2 = a2 is not None
+        ctx.save_for_backward(feat, a1, a2 if a2 is not None else a1)
+        if s2 is None:
+            return s1
+        return s1, s2
+
+    @staticmethod
+    def backward(ctx, ds1, ds2=None):
+        feat, a1, a2 = ctx.saved_tensors
+        H, D = ctx.H, ctx.D
+        n = feat.shape[0]
+        ds1 = _c(ds1)
+        if ctx.has2:
+            ds2 = _c(ds2)
+        dfeat = da1 = da2 = None
+        if ctx.needs_input_grad[0]:
+            dfeat = torch.empty_like(feat)
+            call("msha_node_outer_add", ptr(dfeat), n, H, D, ptr(ds1), ptr(a1), ptr(ds2) if ctx.has2 else None,
+                 ptr(a2) if ctx.has2 else None, 0, _stream())
+        if ctx.needs_input_grad[1]:
+            da1 = colsum(feat, None, ds1, D).view(H, D)
+        if ctx.has2 and ctx.needs_input_grad[2]:
+            da2 = colsum(feat, None, ds2, D).view(H, D)
+        return dfeat, da1, da2, None, None
+
+
+def node_scores(feat, a1, a2=None, H=1, D=None):
+    """feat [n, H*D]; a1/a2 [H, D].  Returns s1 (and s2) of shape [n, H]."""
+    D = D if D is not None else feat.shape[1] // H
+    return _NodeScores.apply(feat, a1, a2, H, D)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention block: logits + masked row softmax + dropout + aggregation(s)
+#   e_ij = lrelu(s_nbr[j] + s_self[i])                              Ours.py:64-65 / Ablation.py:265-266
+#   alpha = softmax_j(where(adj>0, e, -9e15)); dropout              Ours.py:66-69
+#   out_rows[i] = sum_j alpha_ij feat_nbr[j]        (alpha @ h1)     Ours.py:98
+#   out_cols[j] = sum_i alpha_ij feat_self[i]       (alpha.T @ h2)   Ours.py:100   (optional)
+# ------------------------------------------------------------------------------------------------
+class _AttentionBlock(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s_nbr, s_self, feat_nbr, feat_self, dalpha_hook, graph: Graph, H, D, act, p, seed, want_cols):
+        s_nbr, s_self, feat_nbr = _c(s_nbr), _c(s_self), _c(feat_nbr)
+        rp, col = graph.attention_csr()
+        N, M = graph.n_rows, graph.n_cols
+        E = col.numel()
+        C = H * D
+        assert s_nbr.shape == (M, H) and s_self.shape == (N, H) and feat_nbr.shape == (M, C), \
+            (s_nbr.shape, s_self.shape, feat_nbr.shape, (N, M, H, D))
+        dev = feat_nbr.device
+        alpha = torch.empty((E, H), dtype=torch.float32, device=dev)
+        out = torch.empty((N, C), dtype=torch.float32, device=dev)
+        call("msha_gat_fwd", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr), ptr(s_self), ptr(feat_nbr), H, D, LRELU_SLOPE,
+             None, ptr(alpha), ptr(out), act, p, seed, _stream())
+        out_cols = None
+        if want_cols:
+            feat_self = _c(feat_self)
+            assert feat_self.shape == (N, C)
+            colptr, rowidx, perm = graph.attention_csc()
+            out_cols = torch.empty((M, C), dtype=torch.float32, device=dev)
+            call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(feat_self), H, D,
+                 ptr(out_cols), 0, None, None, p, seed, _stream())
+        ctx.graph, ctx.H, ctx.D, ctx.act, ctx.p, ctx.seed, ctx.want_cols = graph, H, D, act, p, seed, want_cols
+        ctx.save_for_backward(s_nbr, s_self, feat_nbr, feat_self if want_cols else None, alpha,
+                              out if act != ACT_NONE else None)
+        ctx.set_materialize_grads(False)
+        if want_cols:
+            return out, out_cols, alpha
+        return out, alpha
+
+    @staticmethod
+    def backward(ctx, d_rows, *rest):
+        s_nbr, s_self, feat_nbr, feat_self, alpha, out = ctx.saved_tensors
+        graph, H, D, act, p, seed = ctx.graph, ctx.H, ctx.D, ctx.act, ctx.p, ctx.seed
+        d_cols = rest[0] if ctx.want_cols else None
+        d_alpha = rest[1] if ctx.want_cols else rest[0]      # grad w.r.t. the pre-dropout alpha (may be None)
+        rp, col = graph.attention_csr()
+        colptr, rowidx, perm = graph.attention_csc()
+        N, M = graph.n_rows, graph.n_cols
+        C = H * D
+        dev = alpha.device
+        d_rows = torch.zeros((N, C), dtype=torch.float32, device=dev) if d_rows is None else _c(d_rows)
+        if d_cols is not None:
+            d_cols = _c(d_cols)
+        dlogit = torch.empty_like(alpha)
+        ds_self = torch.empty((N, H), dtype=torch.float32, device=dev)
+        dz = torch.empty((N, C), dtype=torch.float32, device=dev) if act != ACT_NONE else None
+        extra = _c(d_alpha) if d_alpha is not None else None
+        call("msha_gat_bwd_rows", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr), ptr(s_self), LRELU_SLOPE, ptr(alpha),
+             ptr(feat_nbr), ptr(d_rows), ptr(out), act, ptr(dz), ptr(d_cols), ptr(feat_self) if d_cols is not None else None,
+             ptr(extra), H, D, ptr(dlogit), ptr(ds_self), p, seed, _stream())
+        dzz = dz if dz is not None else d_rows
+        dfeat_nbr = torch.empty((M, C), dtype=torch.float32, device=dev)
+        ds_nbr = torch.empty((M, H), dtype=torch.float32, device=dev)
+        call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(dzz), H, D,
+             ptr(dfeat_nbr), 0, ptr(dlogit), ptr(ds_nbr), p, seed, _stream())
+        dfeat_self = None
+        if ctx.want_cols and d_cols is not None and ctx.needs_input_grad[3]:
+            dfeat_self = torch.empty((N, C), dtype=torch.float32, device=dev)
+            call("msha_gat_fwd", ptr(rp, I32), ptr(col, I32), N, None, None, ptr(d_cols), H, D, LRELU_SLOPE, ptr(alpha),
+                 None, ptr(dfeat_self), ACT_NONE, p, seed, _stream())
+        return ds_nbr, ds_self, dfeat_nbr, dfeat_self, None, None, None, None, None, None, None, None
+
+
+def attention_block(graph: Graph, s_nbr, s_self, feat_nbr, feat_self=None, heads=1, act=ACT_NONE, dropout_p=0.0,
+                    training=True, want_cols=False):
+    """Returns (out_rows, alpha) or (out_rows, out_cols, alpha); alpha is [E_att, H], the pre-dropout attention
+    over the attention CSR (differentiable: gradients flowing into it join the softmax backward)."""
+    C = feat_nbr.shape[1]
+    D = C // heads
+    p = float(dropout_p) if training else 0.0
+    seed = ops.next_seed() if p > 0 else 0
+    return _AttentionBlock.apply(s_nbr, s_self, feat_nbr, feat_self, None, graph, heads, D, act, p, seed, want_cols)
+
+
+# ------------------------------------------------------------------------------------------------
+# weighted SpMM with given (non-learned) edge weights: out[i] = sum_j w_ij feat[j]   (GraphConvolution
+# model.py:37 uses the transposed form; see spmm_t)
+# ------------------------------------------------------------------------------------------------
+class _SpmmT(torch.autograd.Function):
+    """out[j] = sum_i w[e(i,j)] * feat[i]  over the canonical CSR (adj.T @ support, model.py:37)."""
+
+    @staticmethod
+    def forward(ctx, feat, w, graph: Graph):
+        feat, w = _c(feat), _c(w)
+        colptr, rowidx, perm = graph.transpose_structure()
+        M, C = graph.n_cols, feat.shape[1]
+        out = torch.empty((M, C), dtype=torch.float32, device=feat.device)
+        call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(w), ptr(feat), 1, C, ptr(out), 0,
+             None, None, 0.0, 0, _stream())
+        ctx.graph = graph
+        ctx.save_for_backward(w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (w,) = ctx.saved_tensors
+        g = ctx.graph
+        dout = _c(dout)
+        C = dout.shape[1]
+        dfeat = torch.empty((g.n_rows, C), dtype=torch.float32, device=dout.device)
+        call("msha_gat_fwd", ptr(g.rowptr, I32), ptr(g.col, I32), g.n_rows, None, None, ptr(dout), 1, C, LRELU_SLOPE,
+             ptr(w), None, ptr(dfeat), ACT_NONE, 0.0, 0, _stream())
+        return dfeat, None, None
+
+
+def spmm_t(graph: Graph, w, feat):
+    return _SpmmT.apply(feat, w.view(-1, 1), graph)
+
+
+# ------------------------------------------------------------------------------------------------
+# a-1 GraphAttentionLayer epilogue: elu(softmax(mask(lrelu(rowconst))) * h)          GAT.py:24-35
+# ------------------------------------------------------------------------------------------------
+class _Gal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, a_dummy, graph: Graph, H, p, seed):
+        h = _c(h)
+        rp, col = graph.attention_csr()
+        N, M = graph.n_rows, graph.n_cols
+        assert h.shape == (N, H * M)
+        out = torch.empty_like(h)
+        call("msha_gal_fwd", ptr(h), ptr(rp, I32), ptr(col, I32), N, H, M, ptr(out), p, seed, _stream())
+        ctx.graph, ctx.H, ctx.p, ctx.seed = graph, H, p, seed
+        ctx.a_shape = None if a_dummy is None else a_dummy.shape
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        g = ctx.graph
+        rp, col = g.attention_csr()
+        dh = torch.empty_like(out)
+        call("msha_gal_bwd", ptr(_c(dout)), ptr(out), ptr(rp, I32), ptr(col, I32), g.n_rows, ctx.H, g.n_cols, ptr(dh),
+             ctx.p, ctx.seed, _stream())
+        # d/da == 0: the logit is constant along the softmax axis
+        da = None if ctx.a_shape is None else torch.zeros(ctx.a_shape, dtype=torch.float32, device=out.device)
+        return dh, da, None, None, None, None
+
+
+def gal(h, a, graph: Graph, heads=1, dropout_p=0.0, training=True):
+    p = float(dropout_p) if training else 0.0
+    seed = ops.next_seed() if p > 0 else 0
+    return _Gal.apply(h, a, graph, heads, p, seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm1d (node axis) + LeakyReLU                      self.leakyrelu(self.bn1(.)) Ours.py:100-101
+# ------------------------------------------------------------------------------------------------
+class _BnLrelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps):
+        x = _c(x)
+        n, C = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        lib = ops._lib.lib()
+        ws = workspace(lib.msha_bn_workspace_bytes(C), x.device)
+        call("msha_bn_lrelu_fwd", ptr(x), n, C, ptr(_c(gamma)), ptr(_c(beta)), ptr(running_mean), ptr(running_var),
+             int(training), float(momentum), float(eps), LRELU_SLOPE, ptr(y), ptr(mean), ptr(invstd), ws.data_ptr(),
+             ws.numel(), _stream())
+        ctx.training = training
+        ctx.save_for_backward(x, y, gamma, mean, invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, mean, invstd = ctx.saved_tensors
+        n, C = x.shape
+        dx = torch.empty_like(x)
+        xhat = torch.empty_like(x)
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        lib = ops._lib.lib()
+        ws = workspace(lib.msha_bn_workspace_bytes(C), x.device)
+        call("msha_bn_lrelu_bwd", ptr(_c(dy)), ptr(y), ptr(x), n, C, ptr(_c(gamma)), ptr(mean), ptr(invstd),
+             int(ctx.training), LRELU_SLOPE, ptr(dx), ptr(xhat), ptr(dgamma), ptr(dbeta), ws.data_ptr(), ws.numel(),
+             _stream())
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+def bn_lrelu(x, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5):
+    if training and x.shape[0] < 2:
+        raise ValueError("Expected more than 1 value per channel when training")   # nn.BatchNorm1d behaviour
+    return _BnLrelu.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# score matrix: act(u @ v.T) per head                               F.elu(u @ v.t()) Ours.py:108-109
+# ------------------------------------------------------------------------------------------------
+class _MatmulNtAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, v, H, act):
+        """u [N, H*d], v [M, H*d] -> out [N, H*M] with out[:, h*M:(h+1)*M] = act(u_h @ v_h.T)."""
+        u, v = _c(u), _c(v)
+        N, M = u.shape[0], v.shape[0]
+        d = u.shape[1] // H
+        out = torch.empty((N, H * M), dtype=torch.float32, device=u.device)
+        for h in range(H):
+            ops.gemm(u[:, h * d:(h + 1) * d], v[:, h * d:(h + 1) * d], transB=True, act=act, out=out[:, h * M:(h + 1) * M])
+        ctx.H, ctx.act = H, act
+        ctx.save_for_backward(u, v, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        u, v, out = ctx.saved_tensors
+        H = ctx.H
+        N, M = u.shape[0], v.shape[0]
+        d = u.shape[1] // H
+        g = ops.act_bwd(_c(dout), out, ctx.act) if ctx.act != ACT_NONE else _c(dout)
+        du = torch.empty_like(u)
+        dv = torch.empty_like(v)
+        for h in range(H):
+            gh = g[:, h * M:(h + 1) * M]
+            ops.gemm(gh, v[:, h * d:(h + 1) * d], out=du[:, h * d:(h + 1) * d])
+            ops.gemm(gh, u[:, h * d:(h + 1) * d], transA=True, out=dv[:, h * d:(h + 1) * d])
+        return du, dv, None, None
+
+
+def matmul_nt_act(u, v, heads=1, act=ACT_ELU):
+    return _MatmulNtAct.apply(u, v, heads, act)
+
+
+# ------------------------------------------------------------------------------------------------
+# read-out: log_softmax(elu(x), dim=1)                                           Ours.py:166-167
+# ------------------------------------------------------------------------------------------------
+class _LogSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pre_elu):
+        x = _c(x)
+        y = torch.empty_like(x)
+        call("msha_log_softmax_fwd", ptr(x), x.shape[0], x.shape[1], int(pre_elu), ptr(y), _stream())
+        ctx.pre_elu = pre_elu
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("msha_log_softmax_bwd", ptr(_c(dy)), ptr(y), ptr(x), x.shape[0], x.shape[1], int(ctx.pre_elu), ptr(dx), _stream())
+        return dx, None
+
+
+def log_softmax(x, pre_elu=False):
+    return _LogSoftmax.apply(x, pre_elu)
+
+
+# ------------------------------------------------------------------------------------------------
+# link scorer pieces                                                        LLP.py:104-115
+# ------------------------------------------------------------------------------------------------
+class _PairMul(torch.autograd.Function):
+    """z[p] = h_i[src[p]] * h_j[dst[p]]  (x_i * x_j after the caller's gather, LLP.py:105,233)."""
+
+    @staticmethod
+    def forward(ctx, hi, hj, src, dst):
+        hi, hj = _c(hi), _c(hj)
+        P = src.numel() if src is not None else hi.shape[0]
+        C = hi.shape[1]
+        z = torch.empty((P, C), dtype=torch.float32, device=hi.device)
+        call("msha_pair_gather_mul", ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C, ptr(z), _stream())
+        ctx.save_for_backward(hi, hj, src, dst)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        hi, hj, src, dst = ctx.saved_tensors
+        P, C = dz.shape
+        dhi = torch.zeros_like(hi)
+        dhj = torch.zeros_like(hj)
+        call("msha_pair_scatter_mul_add", ptr(_c(dz)), ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C,
+             ptr(dhi), ptr(dhj), _stream())
+        return dhi, dhj, None, None
+
+
+def pair_mul(hi, hj, src=None, dst=None):
+    return _PairMul.apply(hi, hj, src, dst)
+
+
+class _PairDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hi, hj, src, dst, act):
+        hi, hj = _c(hi), _c(hj)
+        P = src.numel() if src is not None else hi.shape[0]
+        out = torch.empty(P, dtype=torch.float32, device=hi.device)
+        call("msha_pair_dot", ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, hi.shape[1], act, ptr(out),
+             _stream())
+        ctx.act = act
+        ctx.save_for_backward(hi, hj, src, dst, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        hi, hj, src, dst, out = ctx.saved_tensors
+        dhi = torch.zeros_like(hi)
+        dhj = torch.zeros_like(hj)
+        call("msha_pair_dot_bwd", ptr(_c(dout)), ptr(out), ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64),
+             out.numel(), hi.shape[1], ctx.act, ptr(dhi), ptr(dhj), _stream())
+        return dhi, dhj, None, None, None
+
+
+def pair_dot(hi, hj, src=None, dst=None, act=ACT_NONE):
+    return _PairDot.apply(hi, hj, src, dst, act)
+
+
+def negative_sample(seed: int, n_pairs: int, n_src: int, n_dst: int, device):
+    """Uniform negative pairs from the library's Philox stream (bit-exact with oracle.negative_sample)."""
+    src = torch.empty(n_pairs, dtype=torch.int64, device=device)
+    dst = torch.empty(n_pairs, dtype=torch.int64, device=device)
+    call("msha_negative_sample", seed, n_pairs, n_src, n_dst, ptr(src, torch.int64), ptr(dst, torch.int64), _stream())
+    return src, dst

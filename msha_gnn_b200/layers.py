@@ -1,0 +1,425 @@
+"""Drop-in ``torch.nn.Module`` surface of the reference layers, backed by the sm_100a kernels.
+
+Same constructor arguments, parameter names (``state_dict`` keys), initialisation order (a seeded
+run initialises identically) and ``forward`` outputs as the reference classes; the adjacency
+argument may be the reference's dense float ``(N, M)`` tensor, an int64 ``(2, E)`` ``edge_index``
+(with ``n_rows``), or a prebuilt :class:`msha_gnn_b200.Graph`.  CUDA only -- a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from .graph import Graph, as_graph
+from .ops import ACT_ELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SIGMOID_RELU
+
+
+def _gdp_column(gdp):
+    return torch.tensor(list(gdp.values())).view(-1, 1)
+
+
+def _split_a(a: torch.Tensor, d: int):
+    """(2d', 1) attention vector -> ([1,d'] neighbour half a[:d'], [1,d'] self half a[d':])  Ours.py:64."""
+    return a[:d, 0].reshape(1, d), a[d:, 0].reshape(1, d)
+
+
+# =================================================================================================
+# a-1  GraphAttentionLayer                                     GAT.py:6-35 (copies: Ours.py:112-141 ...)
+# =================================================================================================
+class GraphAttentionLayer(nn.Module):
+    def __init__(self, in_features, out_features, dropout):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.dropout = dropout
+        self.W = nn.Parameter(torch.zeros(size=(in_features, out_features)))
+        nn.init.xavier_uniform_(self.W.data, gain=1.414)
+        self.a = nn.Parameter(torch.zeros(size=(2 * out_features, 1)))
+        nn.init.xavier_uniform_(self.a.data, gain=1.414)
+
+    def forward(self, input, adj):
+        graph = as_graph(adj, n_rows=input.shape[0], n_cols=self.out_features)
+        if graph.n_rows != input.shape[0] or graph.n_cols != self.out_features:
+            # the reference's torch.where(adj > 0, e, zero_vec) needs adj.shape == (N, out_features) (GAT.py:30)
+            raise RuntimeError(f"adjacency shape {(graph.n_rows, graph.n_cols)} must equal "
+                               f"(N, out_features) = {(input.shape[0], self.out_features)}")
+        h = Fn.linear(input, self.W)                                            # GAT.py:21
+        return Fn.gal(h, self.a, graph, 1, self.dropout, self.training)         # GAT.py:24-35
+
+
+def _gal_heads(x, layers, graph, training):
+    """Head-batched evaluation of several GraphAttentionLayers sharing input and adjacency (GAT.py:55)."""
+    H = len(layers)
+    if H == 1:
+        return layers[0](x, graph)
+    W = torch.cat([l.W for l in layers], dim=1)                                 # (F, H*M): one GEMM for all heads
+    h = Fn.linear(x, W)
+    a = torch.cat([l.a for l in layers], dim=0)                                 # only to route the (zero) gradient
+    return Fn.gal(h, a, graph, H, layers[0].dropout, training)
+
+
+# =================================================================================================
+# a-2  GAT                                                      GAT.py:38-58, LLP.py:148-168
+# =================================================================================================
+class GAT(nn.Module):
+    def __init__(self, n_features, n_classes, n_heads, dropout, gdp, N):
+        super().__init__()
+        gdp_values = _gdp_column(gdp)
+        self.features = nn.Parameter(torch.cat((torch.rand([N, n_features])[:, :-1], gdp_values), dim=1))
+        self.n_classes = n_classes
+        self.n_heads = n_heads
+        self.dropout = dropout
+        self.attentions = [GraphAttentionLayer(n_features, n_classes, dropout=dropout) for _ in range(n_heads)]
+        for i, attention in enumerate(self.attentions):
+            self.add_module('attention_{}'.format(i), attention)
+        self.out_att = GraphAttentionLayer(n_features * n_heads, n_classes, dropout=dropout)
+
+    def forward(self, *args):
+        """``forward(adj)`` (GAT.py:53) or ``forward(input, adj)`` (LLP.py:163)."""
+        if len(args) == 1:
+            x_in, adj = self.features, args[0]
+        elif len(args) == 2:
+            x_in, adj = args
+        else:
+            raise TypeError("GAT.forward takes (adj) or (input, adj)")
+        graph = as_graph(adj, n_rows=x_in.shape[0], n_cols=self.n_classes)
+        x = Fn.dropout(x_in, self.dropout, self.training)                      # GAT.py:54
+        x = _gal_heads(x, self.attentions, graph, self.training)               # GAT.py:55
+        x = Fn.dropout(x, self.dropout, self.training)                         # GAT.py:56
+        x = self.out_att(x, graph)                                             # inner ELU GAT.py:35
+        return Fn.log_softmax(x, pre_elu=True)                                 # outer ELU + log_softmax GAT.py:57-58
+
+
+# =================================================================================================
+# a-3/a-4  MSHA layers                                          Ours.py:29-109, Ablation.py:10-277
+# =================================================================================================
+class _OursBase(nn.Module):
+    """Parameters and init order of OursLayer / OursLayer2 / OursLayer3 (identical __init__, Ours.py:30-52)."""
+    variant = 1
+
+    def __init__(self, in_features, out_features, dropout):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.alpha = 0.2
+        self.dropout = dropout
+        self.W1 = nn.Parameter(torch.zeros(size=(in_features, out_features)))
+        self.W2 = nn.Parameter(torch.zeros(size=(in_features, out_features)))
+        nn.init.xavier_uniform_(self.W1.data, gain=1.414)
+        nn.init.xavier_uniform_(self.W2.data, gain=1.414)
+        self.a = nn.Parameter(torch.zeros(size=(2 * out_features, 1)))
+        nn.init.xavier_uniform_(self.a.data, gain=1.414)
+        self.a3 = nn.Parameter(torch.zeros(size=(2 * out_features, 1)))
+        nn.init.xavier_uniform_(self.a3.data, gain=1.414)
+        self.a4 = nn.Parameter(torch.zeros(size=(2 * out_features, 1)))
+        nn.init.xavier_uniform_(self.a4.data, gain=1.414)
+        self.leakyrelu = nn.LeakyReLU(self.alpha)
+        self.bn1 = nn.BatchNorm1d(out_features)
+        self.bn2 = nn.BatchNorm1d(out_features)
+        self.bn3 = nn.BatchNorm1d(out_features)      # registered but unused, as in the reference
+
+    def forward(self, Sinput, Rinput, inter_adj, city_adj=None, province_adj=None, source_index=None, record=False,
+                Coeff12=None, Coeff3=None, Coeff4=None):
+        out = msha_heads_forward([self], Sinput, Rinput, inter_adj, city_adj, province_adj, source_index,
+                                 self.training, record=record, Coeff3=Coeff3, Coeff4=Coeff4)
+        return out
+
+
+class OursLayer(_OursBase):
+    variant = 1
+
+
+class OursLayer2(_OursBase):
+    variant = 2
+
+
+class OursLayer3(_OursBase):
+    variant = 3
+
+
+def _bn_heads(x, bns, training):
+    """BatchNorm1d + LeakyReLU over head-concatenated columns; running stats are split back per head."""
+    if len(bns) == 1:
+        bn = bns[0]
+        y = Fn.bn_lrelu(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, bn.momentum, bn.eps)
+        if training:
+            bn.num_batches_tracked += 1
+        return y
+    gamma = torch.cat([b.weight for b in bns])
+    beta = torch.cat([b.bias for b in bns])
+    rm = torch.cat([b.running_mean for b in bns])
+    rv = torch.cat([b.running_var for b in bns])
+    y = Fn.bn_lrelu(x, gamma, beta, rm, rv, training, bns[0].momentum, bns[0].eps)
+    if training:
+        d = bns[0].num_features
+        with torch.no_grad():
+            for i, b in enumerate(bns):
+                b.running_mean.copy_(rm[i * d:(i + 1) * d])
+                b.running_var.copy_(rv[i * d:(i + 1) * d])
+                b.num_batches_tracked += 1
+    return y
+
+
+last_attention = {}   # filled when record=True: the export of train.py:284-291 / Ours.py:92-96
+
+
+def msha_heads_forward(layers, Sinput, Rinput, inter_adj, city_adj, province_adj, source_index, training,
+                       record=False, Coeff3=None, Coeff4=None):
+    """Head-batched OursLayer{,2,3}.forward: returns (N, H*M) -- the per-head (N, M) outputs concatenated
+    (Ours.py:164).  One GEMM per side, one fused attention pass and one BN pass for all heads."""
+    H = len(layers)
+    variant = layers[0].variant
+    d = layers[0].out_features
+    p = layers[0].dropout
+    graph = as_graph(inter_adj, n_rows=Sinput.shape[0], n_cols=Rinput.shape[0])
+    N, M = graph.n_rows, graph.n_cols
+    if (N, M) != (Sinput.shape[0], Rinput.shape[0]):
+        raise RuntimeError(f"inter adjacency {(N, M)} does not match Sinput/Rinput rows {(Sinput.shape[0], Rinput.shape[0])}")
+    if H == 1:
+        W1, W2 = layers[0].W1, layers[0].W2
+    else:
+        W1 = torch.cat([l.W1 for l in layers], dim=1)
+        W2 = torch.cat([l.W2 for l in layers], dim=1)
+    h1 = Fn.linear(Rinput, W1)                                                  # (M, H*d')  Ours.py:57
+    h2 = Fn.linear(Sinput, W2)                                                  # (N, H*d')  Ours.py:58
+    a_nbr = torch.cat([_split_a(l.a, d)[0] for l in layers], dim=0)            # (H, d')
+    a_self = torch.cat([_split_a(l.a, d)[1] for l in layers], dim=0)
+    s_nbr = Fn.node_scores(h1, a_nbr, None, H, d)                               # a[:d'].h1[j]   Ours.py:64
+    s_self = Fn.node_scores(h2, a_self, None, H, d)                             # a[d':].h2[i]
+    u_in, v_in, alpha = Fn.attention_block(graph, s_nbr, s_self, h1, h2, heads=H, act=ACT_NONE, dropout_p=p,
+                                           training=training, want_cols=True)   # Ours.py:65-69,98,100
+    if variant != 3:
+        from .intra import intra_scales
+        if source_index is None or city_adj is None or province_adj is None:
+            raise ValueError("OursLayer / OursLayer2 need city_adj, province_adj and source_index")
+        intra_nc, coeffs = intra_scales(layers, graph, h2, alpha, city_adj, province_adj, source_index, training,
+                                        joint=(variant == 1), want_coeffs=record)
+        u_in = u_in + intra_nc                                                  # Ours.py:99,101
+        if record:
+            last_attention.update(coeffs)
+            if Coeff3 is not None:
+                Coeff3[source_index] = coeffs["Coeff3"]
+            if Coeff4 is not None:
+                Coeff4[source_index] = coeffs["Coeff4"]
+    if record:
+        last_attention["Coeff12"] = dense_attention(graph, alpha, H)
+    v = _bn_heads(v_in, [l.bn1 for l in layers], training)                      # Ours.py:100
+    u = _bn_heads(u_in, [l.bn2 for l in layers], training)                      # Ours.py:101
+    return Fn.matmul_nt_act(u, v, H, ACT_ELU)                                   # Ours.py:108-109
+
+
+def dense_attention(graph: Graph, alpha, heads=1):
+    """Dense (H, N, M) view of the per-edge attention (export path only; Ours.py:92-96)."""
+    rp, col = graph.attention_csr()
+    deg = (rp[1:] - rp[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(graph.n_rows, device=alpha.device), deg)
+    cols = torch.where(col < 0, ~col, col).long()
+    out = torch.zeros((heads, graph.n_rows, graph.n_cols), dtype=alpha.dtype, device=alpha.device)
+    out[:, rows, cols] = alpha.detach().t()
+    return out
+
+
+class _MshaModel(nn.Module):
+    """Ours / ablation2 / ablation3 (Ours.py:144-167, Ablation.py:208-231,279-301)."""
+    layer_cls = OursLayer
+
+    def __init__(self, in_features, out_features, n_classes, n_heads, dropout, gdp, Scount, Rcount):
+        super().__init__()
+        gdp_values = _gdp_column(gdp)
+        self.Sfeatures = nn.Parameter(torch.cat((torch.rand([Scount, in_features])[:, :-1], gdp_values), dim=1))
+        self.Rfeatures = nn.Parameter(torch.rand([Rcount, in_features]))
+        self.n_classes = n_classes
+        self.n_heads = n_heads
+        self.dropout = dropout
+        self.attentions = [self.layer_cls(in_features, out_features, dropout=dropout) for _ in range(n_heads)]
+        for i, attention in enumerate(self.attentions):
+            self.add_module('attention_{}'.format(i), attention)
+        self.out_att = GraphAttentionLayer(n_classes * n_heads, n_classes, dropout=dropout)
+
+    def forward(self, inter_adj, city_adj=None, province_adj=None, source_index=None, record=False, Coeff12=None,
+                Coeff3=None, Coeff4=None):
+        graph = as_graph(inter_adj, n_rows=self.Sfeatures.shape[0], n_cols=self.Rfeatures.shape[0])
+        s_input = Fn.dropout(self.Sfeatures, self.dropout, self.training)       # Ours.py:161
+        r_input = Fn.dropout(self.Rfeatures, self.dropout, self.training)       # Ours.py:162
+        x = msha_heads_forward(self.attentions, s_input, r_input, graph, city_adj, province_adj, source_index,
+                               self.training, record=record, Coeff3=Coeff3, Coeff4=Coeff4)   # Ours.py:164
+        x = Fn.dropout(x, self.dropout, self.training)                          # Ours.py:165
+        x = self.out_att(x, graph)                                              # Ours.py:166 (inner ELU)
+        return Fn.log_softmax(x, pre_elu=True)                                  # Ours.py:166-167
+
+
+class Ours(_MshaModel):
+    layer_cls = OursLayer
+
+
+class ablation2(_MshaModel):
+    layer_cls = OursLayer2
+
+
+class ablation3(_MshaModel):
+    layer_cls = OursLayer3
+
+
+class ablation1(nn.Module):
+    """Single OursLayer, no out_att (Ablation.py:118-136)."""
+
+    def __init__(self, in_features, out_features, n_classes, n_heads, dropout, gdp, Scount, Rcount):
+        super().__init__()
+        gdp_values = _gdp_column(gdp)
+        self.Sfeatures = nn.Parameter(torch.cat((torch.rand([Scount, in_features])[:, :-1], gdp_values), dim=1))
+        self.Rfeatures = nn.Parameter(torch.rand([Rcount, in_features]))
+        self.n_classes = n_classes
+        self.n_heads = n_heads
+        self.dropout = dropout
+        self.attention = OursLayer(in_features, out_features, dropout=dropout)
+
+    def forward(self, inter_adj, city_adj, province_adj, source_index):
+        s_input = Fn.dropout(self.Sfeatures, self.dropout, self.training)
+        r_input = Fn.dropout(self.Rfeatures, self.dropout, self.training)
+        x = self.attention(s_input, r_input, inter_adj, city_adj, province_adj, source_index)
+        x = Fn.dropout(x, self.dropout, self.training)
+        return Fn.log_softmax(x, pre_elu=True)                                  # Ablation.py:135-136
+
+
+# =================================================================================================
+# a-7  LinkPredictor / Teacher_LinkPredictor                                   LLP.py:86-115,170-198
+# =================================================================================================
+class LinkPredictor(nn.Module):
+    def __init__(self, predictor, in_channels, hidden_channels, out_channels, num_layers, dropout):
+        super().__init__()
+        self.predictor = predictor
+        self.lins = nn.ModuleList()
+        self.lins.append(nn.Linear(in_channels, hidden_channels))
+        for _ in range(num_layers - 2):
+            self.lins.append(nn.Linear(hidden_channels, hidden_channels))
+        self.lins.append(nn.Linear(hidden_channels, out_channels))   # allocated, never applied (LLP.py:111)
+        self.dropout = dropout
+
+    def reset_parameters(self):
+        for lin in self.lins:
+            lin.reset_parameters()
+
+    def forward(self, x_i, x_j):
+        """Reference signature: rows already gathered by the caller (``h[source_index]``, LLP.py:233)."""
+        return self._score(x_i, x_j, None, None)
+
+    def forward_pairs(self, h_i, h_j, src, dst):
+        """Fused pair-gather entry: scores pairs (src[p], dst[p]) of the embedding tables h_i / h_j."""
+        return self._score(h_i, h_j, src, dst)
+
+    def _score(self, hi, hj, src, dst):
+        if self.predictor == 'mlp':
+            x = Fn.pair_mul(hi, hj, src, dst)                                   # LLP.py:105
+            hidden = list(self.lins)[:-1]
+            for k, lin in enumerate(hidden):
+                last = k == len(hidden) - 1
+                drop = self.training and self.dropout > 0
+                if last and not drop:
+                    x = Fn.linear_bias_act(x, lin.weight, lin.bias, ACT_SIGMOID_RELU)   # relu + sigmoid fused
+                else:
+                    x = Fn.linear_bias_act(x, lin.weight, lin.bias, ACT_RELU)           # LLP.py:108-109
+                    x = Fn.dropout(x, self.dropout, self.training)                      # LLP.py:110
+                    if last:
+                        x = Fn._Act.apply(x, ACT_SIGMOID)                               # LLP.py:115
+            if not hidden:
+                x = Fn._Act.apply(x, ACT_SIGMOID)
+            return x
+        if self.predictor == 'inner':
+            return Fn.pair_dot(hi, hj, src, dst, ACT_SIGMOID)                   # LLP.py:112-115
+        # any other predictor string: the reference applies sigmoid to x_i * x_j
+        return Fn._Act.apply(Fn.pair_mul(hi, hj, src, dst), ACT_SIGMOID)
+
+
+class Teacher_LinkPredictor(LinkPredictor):
+    pass
+
+
+# =================================================================================================
+# model.GraphConvolution / GCN                                                 model.py:11-64
+# =================================================================================================
+class GraphConvolution(nn.Module):
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.weight = nn.Parameter(torch.rand([in_features, out_features]))
+        if bias:
+            self.bias = nn.Parameter(torch.tensor(out_features, dtype=torch.float32))   # 0-dim, model.py:23
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1. / math.sqrt(self.weight.size(1))
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-stdv, stdv)
+
+    def forward(self, input, adj, values=None):
+        """``adj.T @ (input @ W) + bias`` (model.py:36-39).  ``adj`` dense/Graph; its stored values weight
+        the edges (pass ``values`` to override, e.g. ``graph.normalized_values()``)."""
+        graph = as_graph(adj)
+        support = Fn.linear(input, self.weight)
+        w = graph.val if values is None else values
+        out = Fn.spmm_t(graph, w, support)
+        return out + self.bias if self.bias is not None else out
+
+    def __repr__(self):
+        return self.__class__.__name__ + ' (' + str(self.in_features) + ' -> ' + str(self.out_features) + ')'
+
+
+# =================================================================================================
+# generic multi-head GAT layer for the synthetic configs (SURVEY.md section 8a generalisation rule:
+# a-3's inter-scale block with S = R, Ablation.py:262-271 + alpha @ h1 :274)
+# =================================================================================================
+class GATConv(nn.Module):
+    def __init__(self, in_features, out_features, heads=1, concat=True, dropout=0.0, activation="elu"):
+        super().__init__()
+        self.in_features, self.out_features, self.heads, self.concat = in_features, out_features, heads, concat
+        self.dropout = dropout
+        self.activation = activation
+        self.W = nn.Parameter(torch.zeros(size=(in_features, heads * out_features)))
+        nn.init.xavier_uniform_(self.W.data, gain=1.414)
+        self.a_nbr = nn.Parameter(torch.zeros(size=(heads, out_features)))
+        self.a_self = nn.Parameter(torch.zeros(size=(heads, out_features)))
+        nn.init.xavier_uniform_(self.a_nbr.data, gain=1.414)
+        nn.init.xavier_uniform_(self.a_self.data, gain=1.414)
+
+    def forward(self, x, adj, return_alpha=False):
+        graph = as_graph(adj, n_rows=x.shape[0], n_cols=x.shape[0])
+        Wh = Fn.linear(x, self.W)
+        s_nbr, s_self = Fn.node_scores(Wh, self.a_nbr, self.a_self, self.heads, self.out_features)
+        fuse_elu = self.activation == "elu" and self.concat
+        out, alpha = Fn.attention_block(graph, s_nbr, s_self, Wh, heads=self.heads,
+                                        act=ACT_ELU if fuse_elu else ACT_NONE, dropout_p=self.dropout,
+                                        training=self.training)
+        if not self.concat:
+            out = out.view(x.shape[0], self.heads, self.out_features).mean(dim=1)
+            if self.activation == "elu":
+                out = Fn.elu(out)
+        return (out, alpha) if return_alpha else out
+
+
+class GATLinkModel(nn.Module):
+    """L-layer multi-head GAT encoder + LinkPredictor scorer (BASELINE.json configs[2]/[3])."""
+
+    def __init__(self, in_features, hidden, heads, num_layers=2, predictor_hidden=None, dropout=0.0):
+        super().__init__()
+        assert hidden % heads == 0
+        dims = [in_features] + [hidden] * num_layers
+        self.convs = nn.ModuleList(GATConv(dims[i], hidden // heads, heads, concat=True, dropout=dropout)
+                                   for i in range(num_layers))
+        self.predictor = LinkPredictor('mlp', hidden, predictor_hidden or hidden, 1, 2, dropout)
+        self.dropout = dropout
+
+    def encode(self, x, graph):
+        for conv in self.convs:
+            x = conv(x, graph)
+        return x
+
+    def forward(self, x, graph, src, dst):
+        h = self.encode(x, graph)
+        return self.predictor.forward_pairs(h, h, src, dst)
