@@ -96,6 +96,14 @@ int msha_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N
                   int64_t ldc, int transA, int transB, const float* bias, float beta, int act, float slope,
                   void* stream);
 
+/* tcgen05 / TMEM / TMA path of the same contraction (3xTF32 split, fp32-grade accuracy). transA/transB as above.
+ * splits > 1: split-K, partial sums atomically added into a caller-zeroed C (no bias / activation). */
+int msha_gemm_tf32x3_supported(const float* A, const float* B, int64_t M, int64_t N, int64_t K, int64_t lda,
+                               int64_t ldb);
+int msha_gemm_tf32x3(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                     int64_t ldb, int64_t ldc, int transA, int transB, const float* bias, int act, float slope,
+                     int splits, void* stream);
+
 /* ---- a-1 GraphAttentionLayer epilogue: replaces GAT.py:24-35 (uniform masked softmax, elu(att*h)) ---- */
 int msha_gal_fwd(const float* h, const int32_t* rowptr, const int32_t* col, int64_t n_rows, int H, int64_t M,
                  float* out, float drop_p, uint64_t drop_seed, void* stream);

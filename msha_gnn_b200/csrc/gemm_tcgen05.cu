@@ -1,0 +1,447 @@
+// K-7: fp32-accurate GEMM on the 5th-gen tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM),
+// operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) -- the dense contractions of the hot path:
+// Wh = X @ W (GAT.py:21, Ours.py:57-58), the LinkPredictor Linear layers (LLP.py:107-108) and their backward.
+//
+// fp32 accuracy (north star: rel. err <= 1e-4) via the 3xTF32 split done in shared memory by converter warps:
+//     x = hi + lo,  hi = x & 0xffffe000 (exact in tf32),  lo = x - hi
+//     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi            (error ~ 2^-21 relative)
+//
+// One persistent CTA per SM, 384 threads, warp-specialised:
+//     warp 0   TMA producer          (one elected lane)         raw fp32 tiles -> smem
+//     warp 1   MMA issuer            (one elected lane)         3 x tcgen05.mma per 8-wide k-step
+//     warp 2   TMEM allocator
+//     warps 4-7   converters         split raw -> hi (in place) / lo, fence.proxy.async
+//     warps 8-11  epilogue           tcgen05.ld -> bias/activation -> global (or atomicAdd for split-K)
+// Pipelines: smem ring (full_raw -> full_cvt -> empty), TMEM double buffer (tmem_full / tmem_empty).
+//
+// Operand layouts (row-major in global memory):
+//     K-major : stored [MN, K] (K contiguous)  -> one TMA box {32 K, rows}, UMMA K-major SW128
+//     MN-major: stored [K, MN] (MN contiguous) -> boxes {32 MN, 32 K},      UMMA MN-major SW128
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                  // 32 fp32 = 128 B = one swizzle row
+constexpr int UMMA_K = 8;                    // tf32
+constexpr int NUM_THREADS = 384;
+constexpr int CVT_THREADS = 128;
+constexpr int EPI_THREADS = 128;
+constexpr uint32_t SPIN_LIMIT = 1u << 24;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > SPIN_LIMIT) __trap();      // a dead pipeline must fault, never hang the GPU
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1.
+// K-major fp32 tiles use SWIZZLE_128B (8 rows x 128 B atoms, SBO = 1024).  MN-major 32-bit operands only exist in
+// the SWIZZLE_128B_BASE32B layout (Swizzle<2,5,2>: 4 K-rows x 128 B atoms, SBO = 512 between K atoms, LBO between
+// 32-element MN chunks) -- written by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B (K-major), 1 = SWIZZLE_128B_BASE32B (MN-major tf32)
+    return d;
+}
+// 32-bit instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4)                    // c_format = F32
+           | (2u << 7)                  // a_format = TF32
+           | (2u << 10)                 // b_format = TF32
+           | ((a_mn ? 1u : 0u) << 15)   // a_major
+           | ((b_mn ? 1u : 0u) << 16)   // b_major
+           | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float epi_act(float x, int act, float slope) {
+    switch (act) {
+        case 1: return x > 0.f ? x : expm1f(x);
+        case 2: return fmaxf(x, 0.f);
+        case 3: return 1.f / (1.f + expf(-fmaxf(x, 0.f)));
+        case 4: return x > 0.f ? x : x * slope;
+        case 5: return 1.f / (1.f + expf(-x));
+        default: return x;
+    }
+}
+
+template <int BLOCK_N>
+struct Cfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;          // 16 KB
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
+    static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);    // hi + lo of both operands
+    static constexpr int STAGES = BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 4);
+    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;   // two accumulator stages
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   float* __restrict__ Cmat, int M, int N, int K, int64_t ldc, const float* __restrict__ bias, int act,
+                   float slope, int splits, int atomic_out) {
+    using C = Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full_raw = bars;                       // [STAGES]
+    uint64_t* full_cvt = bars + C::STAGES;           // [STAGES]
+    uint64_t* empty = bars + 2 * C::STAGES;          // [STAGES]
+    uint64_t* tmem_full = bars + 3 * C::STAGES;      // [2]
+    uint64_t* tmem_empty = bars + 3 * C::STAGES + 2; // [2]
+    uint32_t* tmem_ptr = (uint32_t*)(bars + 3 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(smem_u32(&full_raw[s]), 1);
+            mbar_init(smem_u32(&full_cvt[s]), CVT_THREADS);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tmem_full[a]), 1);
+            mbar_init(smem_u32(&tmem_empty[a]), EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+    const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    const int n_work = m_tiles * n_tiles * splits;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = w % splits, t = w / splits;
+                const int n0 = (t % n_tiles) * BLOCK_N, m0 = (t / n_tiles) * BLOCK_M;
+                const int kb0 = (int)((int64_t)split * total_kb / splits), kb1 = (int)((int64_t)(split + 1) * total_kb / splits);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    uint8_t* st = smem + stage * C::STAGE_BYTES;
+                    const uint32_t a_dst = smem_u32(st), b_dst = smem_u32(st + 2 * C::A_BYTES);
+                    const uint32_t bar = smem_u32(&full_raw[stage]);
+                    mbar_arrive_expect_tx(bar, C::A_BYTES + C::B_BYTES);
+                    const int k0 = kb * BLOCK_K;
+                    if (A_MN) {
+#pragma unroll
+                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_2d(a_dst + i * 4096, &tmA, bar, m0 + 32 * i, k0);
+                    } else {
+                        tma_load_2d(a_dst, &tmA, bar, k0, m0);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int i = 0; i < BLOCK_N / 32; ++i) tma_load_2d(b_dst + i * 4096, &tmB, bar, n0 + 32 * i, k0);
+                    } else {
+                        tma_load_2d(b_dst, &tmB, bar, k0, n0);
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
+            constexpr uint32_t A_LBO = A_MN ? 4096 : 16, A_SBO = A_MN ? 512 : 1024, A_KSTEP = A_MN ? 1024 : UMMA_K * 4;
+            constexpr uint32_t B_LBO = B_MN ? 4096 : 16, B_SBO = B_MN ? 512 : 1024, B_KSTEP = B_MN ? 1024 : UMMA_K * 4;
+            constexpr uint32_t A_LT = A_MN ? 1 : 2, B_LT = B_MN ? 1 : 2;
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = w % splits;
+                const int kb0 = (int)((int64_t)split * total_kb / splits), kb1 = (int)((int64_t)(split + 1) * total_kb / splits);
+                mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(&full_cvt[stage]), phase);
+                    tcgen05_fence_after();
+                    uint8_t* st = smem + stage * C::STAGE_BYTES;
+                    const uint32_t a_hi = smem_u32(st), a_lo = a_hi + C::A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t dah = make_smem_desc(a_hi + k * A_KSTEP, A_LBO, A_SBO, A_LT);
+                        const uint64_t dal = make_smem_desc(a_lo + k * A_KSTEP, A_LBO, A_SBO, A_LT);
+                        const uint64_t dbh = make_smem_desc(b_hi + k * B_KSTEP, B_LBO, B_SBO, B_LT);
+                        const uint64_t dbl = make_smem_desc(b_lo + k * B_KSTEP, B_LBO, B_SBO, B_LT);
+                        umma_tf32(tmem_d, dal, dbh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                    }
+                    tcgen05_commit(smem_u32(&empty[stage]));          // frees the smem slot when the MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(smem_u32(&tmem_full[acc]));            // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // =============================== converters: raw -> hi / lo ===============================
+        const int tid = threadIdx.x - 128;
+        uint32_t stage = 0, phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = w % splits;
+            const int kb0 = (int)((int64_t)split * total_kb / splits), kb1 = (int)((int64_t)(split + 1) * total_kb / splits);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(smem_u32(&full_raw[stage]), phase);
+                uint8_t* st = smem + stage * C::STAGE_BYTES;
+                uint4* a_hi = (uint4*)st;
+                uint4* a_lo = (uint4*)(st + C::A_BYTES);
+                uint4* b_hi = (uint4*)(st + 2 * C::A_BYTES);
+                uint4* b_lo = (uint4*)(st + 2 * C::A_BYTES + C::B_BYTES);
+#pragma unroll 4
+                for (int c = tid; c < C::A_BYTES / 16; c += CVT_THREADS) {
+                    uint4 x = a_hi[c], h, l;
+                    h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
+                    l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+                    l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+                    l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+                    l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+                    a_hi[c] = h; a_lo[c] = l;
+                }
+#pragma unroll 4
+                for (int c = tid; c < C::B_BYTES / 16; c += CVT_THREADS) {
+                    uint4 x = b_hi[c], h, l;
+                    h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
+                    l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+                    l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+                    l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+                    l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+                    b_hi[c] = h; b_lo[c] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+                mbar_arrive(smem_u32(&full_cvt[stage]));
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 8) {
+        // =============================== epilogue ===============================
+        const int q = warp & 3;                      // TMEM lane quarter owned by this warp
+        uint32_t acc = 0, acc_phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int t = w / splits;
+            const int n0 = (t % n_tiles) * BLOCK_N, m0 = (t / n_tiles) * BLOCK_M;
+            mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+            tcgen05_fence_after();
+            const int row = m0 + q * 32 + lane;
+            float* crow = Cmat + (int64_t)row * ldc;
+            const bool vec_ok = ((ldc & 3) == 0) && ((((uintptr_t)Cmat) & 15) == 0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c0, v);
+                if (row < M) {
+                    const int nb = n0 + c0;
+                    if (!atomic_out && vec_ok && nb + 32 <= N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o;
+                            o.x = epi_act(__uint_as_float(v[j + 0]) + (bias ? bias[nb + j + 0] : 0.f), act, slope);
+                            o.y = epi_act(__uint_as_float(v[j + 1]) + (bias ? bias[nb + j + 1] : 0.f), act, slope);
+                            o.z = epi_act(__uint_as_float(v[j + 2]) + (bias ? bias[nb + j + 2] : 0.f), act, slope);
+                            o.w = epi_act(__uint_as_float(v[j + 3]) + (bias ? bias[nb + j + 3] : 0.f), act, slope);
+                            *reinterpret_cast<float4*>(crow + nb + j) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (nb + j < N) {
+                                if (atomic_out) {
+                                    atomicAdd(crow + nb + j, __uint_as_float(v[j]));
+                                } else {
+                                    crow[nb + j] = epi_act(__uint_as_float(v[j]) + (bias ? bias[nb + j] : 0.f), act, slope);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(smem_u32(&tmem_empty[acc]));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: inner dimension `inner` (contiguous), `outer` rows of stride ld floats; 128B swizzle
+static int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                    int box_outer, bool mn_major) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { msha_set_error("cuTensorMapEncodeTiled entry point unavailable"); return -2; }
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { msha_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -2; }
+    return 0;
+}
+
+template <int BN, bool AM, bool BM>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int M, int N, int K, int64_t ldc,
+                  const float* bias, int act, float slope, int splits, int atomic_out, cudaStream_t st) {
+    auto kern = gemm_tf32x3_kernel<BN, AM, BM>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
+    int64_t n_work = (int64_t)m_tiles * n_tiles * splits;
+    int grid = (int)(n_work < MSHA_NUM_SMS ? n_work : MSHA_NUM_SMS);
+    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, C, M, N, K, ldc, bias, act, slope, splits, atomic_out);
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace
+
+// 0 if the operands satisfy the TMA constraints of msha_gemm_tf32x3 (16-byte aligned base, ld % 4 == 0)
+MSHA_API int msha_gemm_tf32x3_supported(const float* A, const float* B, int64_t M, int64_t N, int64_t K, int64_t lda,
+                                        int64_t ldb) {
+    if (M <= 0 || N <= 0 || K <= 0) return -1;
+    if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 3) || (ldb & 3)) return -1;
+    if (M >= ((int64_t)1 << 31) || N >= ((int64_t)1 << 31) || K >= ((int64_t)1 << 31)) return -1;
+    return 0;
+}
+
+// C[M,N] = act( opA(A) * opB(B) + bias )   (splits == 1)
+// C[M,N] += opA(A) * opB(B)                (splits  > 1: split-K partial sums are atomically added; the caller zeroes C;
+//                                           bias / act must be none)
+// transA == 0: A stored [M,K] (K-major); transA == 1: A stored [K,M].  transB == 0: B stored [K,N]; transB == 1: [N,K].
+MSHA_API int msha_gemm_tf32x3(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                              int64_t ldb, int64_t ldc, int transA, int transB, const float* bias, int act, float slope,
+                              int splits, void* stream) {
+    MSHA_REQUIRE(msha_gemm_tf32x3_supported(A, B, M, N, K, lda, ldb) == 0,
+                 "gemm_tf32x3: operands must be 16-byte aligned with ld %% 4 == 0 and positive sizes");
+    MSHA_REQUIRE(splits >= 1, "gemm_tf32x3: splits >= 1");
+    MSHA_REQUIRE(splits == 1 || (bias == nullptr && act == 0), "gemm_tf32x3: split-K excludes bias/activation");
+    const int total_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
+    if (splits > total_kb) splits = total_kb;
+    const bool a_mn = transA != 0;      // A stored [K, M]  -> MN-major
+    const bool b_mn = transB == 0;      // B stored [K, N]  -> MN-major
+    const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    CUtensorMap ta, tb;
+    int rc;
+    if (a_mn) rc = make_map(&ta, A, M, K, lda, 32, 32, true); else rc = make_map(&ta, A, K, M, lda, 32, BLOCK_M, false);
+    if (rc) return rc;
+    if (b_mn) rc = make_map(&tb, B, N, K, ldb, 32, 32, true); else rc = make_map(&tb, B, K, N, ldb, 32, BN, false);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int atomic_out = splits > 1 ? 1 : 0;
+#define GO(BNv, AMv, BMv) return launch<BNv, AMv, BMv>(ta, tb, C, (int)M, (int)N, (int)K, ldc, bias, act, slope, splits, atomic_out, st)
+#define GO_N(AMv, BMv) if (BN == 256) { GO(256, AMv, BMv); } else if (BN == 128) { GO(128, AMv, BMv); } else { GO(64, AMv, BMv); }
+    if (!a_mn && !b_mn) { GO_N(false, false) }
+    else if (!a_mn && b_mn) { GO_N(false, true) }
+    else if (a_mn && !b_mn) { GO_N(true, false) }
+    else { GO_N(true, true) }
+#undef GO_N
+#undef GO
+}

@@ -13,6 +13,8 @@ The (B, H)-sized coefficient algebra is plain tensor arithmetic; the edge / segm
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import functional as Fn
@@ -68,11 +70,13 @@ _gl_cache: dict = {}
 def _group_cache(t):
     key = (t.data_ptr(), t._version, t.numel())
     hit = _gl_cache.get(key)
-    if hit is None:
-        if len(_gl_cache) > 16:
-            _gl_cache.clear()
-        hit = _gl_cache[key] = GroupLists(t)
-    return hit
+    if hit is not None and hit[0]() is t:          # the weakref guards against address reuse by a new tensor
+        return hit[1]
+    if len(_gl_cache) > 16:
+        _gl_cache.clear()
+    gl = GroupLists(t)
+    _gl_cache[key] = (weakref.ref(t), gl)
+    return gl
 
 
 class _RowsumExp(torch.autograd.Function):

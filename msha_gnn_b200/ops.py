@@ -3,6 +3,7 @@ current CUDA stream.  PyTorch is used only for device memory (caching allocator)
 from __future__ import annotations
 
 import itertools
+import os
 
 import torch
 
@@ -10,6 +11,9 @@ from . import _lib
 
 ACT_NONE, ACT_ELU, ACT_RELU, ACT_SIGMOID_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3, 4, 5
 LRELU_SLOPE = 0.2   # Ours.py:33 / GAT.py:27
+
+GEMM_BACKEND = os.environ.get("MSHA_GEMM", "tcgen05")   # "tcgen05" (3xTF32 tensor cores) | "simt" (fp32 FMA validation path)
+TC_MIN_WORK = 1 << 18                                    # below this many MACs the SIMT kernel's latency wins
 
 launch_count = 0    # number of C-ABI compute calls issued (bench.py reports kernel launches from it)
 
@@ -31,8 +35,9 @@ def ptr(t, dtype=torch.float32, name="tensor"):
     if not t.is_contiguous():
         raise RuntimeError(f"{name}: tensor must be contiguous")
     p = t.data_ptr()
-    if t.numel() and p % 16:
-        raise RuntimeError(f"{name}: device pointer must be 16-byte aligned")
+    align = 16 if dtype == torch.float32 else t.element_size()     # float rows are read with 128-bit loads
+    if t.numel() and p % align:
+        raise RuntimeError(f"{name}: device pointer must be {align}-byte aligned")
     return p
 
 
@@ -73,8 +78,21 @@ def gemm(A, B, transA=False, transB=False, bias=None, act=ACT_NONE, out=None, be
     lda = A.stride(0) if A.shape[0] > 1 else A.shape[1]
     ldb = B.stride(0) if B.shape[0] > 1 else B.shape[1]
     ldc = out.stride(0) if M > 1 else N
-    call("msha_gemm_f32", A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc, int(transA), int(transB),
-         ptr(bias, name="bias"), float(beta), int(act), float(slope), _stream())
+    lib = _lib.lib()
+    use_tc = (GEMM_BACKEND == "tcgen05" and beta == 0.0 and M * N * K >= TC_MIN_WORK
+              and lib.msha_gemm_tf32x3_supported(A.data_ptr(), B.data_ptr(), M, N, K, lda, ldb) == 0)
+    if use_tc:
+        tiles = -(-M // 128) * -(-N // (256 if N > 128 else (128 if N > 64 else 64)))
+        splits = 1
+        if bias is None and act == ACT_NONE and K >= 4096 and tiles < 74:
+            splits = max(1, min(148 // tiles, K // 1024))
+        if splits > 1:
+            out.zero_()
+        call("msha_gemm_tf32x3", A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc, int(transA),
+             int(transB), ptr(bias, name="bias"), int(act), float(slope), splits, _stream())
+    else:
+        call("msha_gemm_f32", A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc, int(transA), int(transB),
+             ptr(bias, name="bias"), float(beta), int(act), float(slope), _stream())
     return out
 
 
