@@ -11,23 +11,26 @@
 //     warp 1   MMA issuer            (one elected lane)         3 x tcgen05.mma per 8-wide k-step
 //     warp 2   TMEM allocator
 //     warps 4-7   converters         split raw -> hi (in place) / lo, fence.proxy.async
-//     warps 8-11  epilogue           tcgen05.ld -> bias/activation -> global (or atomicAdd for split-K)
+//     warps 8-15  epilogue           tcgen05.ld -> bias/activation -> smem transpose -> coalesced global stores
+//                                    (or atomicAdd for split-K)
 // Pipelines: smem ring (full_raw -> full_cvt -> empty), TMEM double buffer (tmem_full / tmem_empty).
 //
 // Operand layouts (row-major in global memory):
-//     K-major : stored [MN, K] (K contiguous)  -> one TMA box {32 K, rows}, UMMA K-major SW128
-//     MN-major: stored [K, MN] (MN contiguous) -> boxes {32 MN, 32 K},      UMMA MN-major SW128
+//     K-major : stored [MN, K] (K contiguous)  -> one TMA box {16 K, rows},  UMMA K-major SWIZZLE_64B
+//     MN-major: stored [K, MN] (MN contiguous) -> boxes {32 MN, 16 K},       UMMA MN-major SWIZZLE_128B_BASE32B
 #include "common.cuh"
 #include <cuda.h>
 
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;                  // 32 fp32 = 128 B = one swizzle row
+constexpr int BLOCK_K = 16;                  // 16 fp32 = 64 B rows (SWIZZLE_64B); fine-grained stages keep 4+ in flight
 constexpr int UMMA_K = 8;                    // tf32
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 512;
 constexpr int CVT_THREADS = 128;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4; // per epilogue warp: 32x32 fp32 transpose buffer
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -89,7 +92,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1.
-// K-major fp32 tiles use SWIZZLE_128B (8 rows x 128 B atoms, SBO = 1024).  MN-major 32-bit operands only exist in
+// K-major fp32 tiles use SWIZZLE_64B (8 rows x 64 B atoms, SBO = 512).  MN-major 32-bit operands only exist in
 // the SWIZZLE_128B_BASE32B layout (Swizzle<2,5,2>: 4 K-rows x 128 B atoms, SBO = 512 between K atoms, LBO between
 // 32-element MN chunks) -- written by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -99,7 +102,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-    d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B (K-major), 1 = SWIZZLE_128B_BASE32B (MN-major tf32)
+    d |= (uint64_t)layout_type << 61;  // 4 = SWIZZLE_64B (K-major), 1 = SWIZZLE_128B_BASE32B (MN-major tf32)
     return d;
 }
 // 32-bit instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate
@@ -125,12 +128,14 @@ __device__ __forceinline__ float epi_act(float x, int act, float slope) {
 
 template <int BLOCK_N>
 struct Cfg {
-    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;          // 16 KB
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;          // 8 KB
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);    // hi + lo of both operands
-    static constexpr int STAGES = BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 4);
+    static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;   // two accumulator stages
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -141,7 +146,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     using C = Cfg<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* bars = (uint64_t*)(smem + C::BAR_OFF);
     uint64_t* full_raw = bars;                       // [STAGES]
     uint64_t* full_cvt = bars + C::STAGES;           // [STAGES]
     uint64_t* empty = bars + 2 * C::STAGES;          // [STAGES]
@@ -200,13 +205,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const int k0 = kb * BLOCK_K;
                     if (A_MN) {
 #pragma unroll
-                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_2d(a_dst + i * 4096, &tmA, bar, m0 + 32 * i, k0);
+                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_2d(a_dst + i * (128 * BLOCK_K), &tmA, bar, m0 + 32 * i, k0);
                     } else {
                         tma_load_2d(a_dst, &tmA, bar, k0, m0);
                     }
                     if (B_MN) {
 #pragma unroll
-                        for (int i = 0; i < BLOCK_N / 32; ++i) tma_load_2d(b_dst + i * 4096, &tmB, bar, n0 + 32 * i, k0);
+                        for (int i = 0; i < BLOCK_N / 32; ++i) tma_load_2d(b_dst + i * (128 * BLOCK_K), &tmB, bar, n0 + 32 * i, k0);
                     } else {
                         tma_load_2d(b_dst, &tmB, bar, k0, n0);
                     }
@@ -218,9 +223,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
-            constexpr uint32_t A_LBO = A_MN ? 4096 : 16, A_SBO = A_MN ? 512 : 1024, A_KSTEP = A_MN ? 1024 : UMMA_K * 4;
-            constexpr uint32_t B_LBO = B_MN ? 4096 : 16, B_SBO = B_MN ? 512 : 1024, B_KSTEP = B_MN ? 1024 : UMMA_K * 4;
-            constexpr uint32_t A_LT = A_MN ? 1 : 2, B_LT = B_MN ? 1 : 2;
+            constexpr uint32_t A_LBO = A_MN ? 128 * BLOCK_K : 16, A_SBO = 512, A_KSTEP = A_MN ? 1024 : UMMA_K * 4;
+            constexpr uint32_t B_LBO = B_MN ? 128 * BLOCK_K : 16, B_SBO = 512, B_KSTEP = B_MN ? 1024 : UMMA_K * 4;
+            constexpr uint32_t A_LT = A_MN ? 1 : 4, B_LT = B_MN ? 1 : 4;
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
                 const int split = w % splits;
@@ -292,45 +297,88 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     } else if (warp >= 8) {
         // =============================== epilogue ===============================
-        const int q = warp & 3;                      // TMEM lane quarter owned by this warp
+        // warp -> TMEM lane quarter q (rows 32q..32q+31 of the tile) and column half `hf`
+        const int q = warp & 3, hf = (warp - 8) >> 2;
+        constexpr int COLS_PER_WARP = BLOCK_N / 2;
+        float* stage_buf = (float*)(smem + C::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
+        const bool vec_ok = ((ldc & 3) == 0) && ((((uintptr_t)Cmat) & 15) == 0);
         uint32_t acc = 0, acc_phase = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int t = w / splits;
             const int n0 = (t % n_tiles) * BLOCK_N, m0 = (t / n_tiles) * BLOCK_M;
             mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
             tcgen05_fence_after();
-            const int row = m0 + q * 32 + lane;
-            float* crow = Cmat + (int64_t)row * ldc;
-            const bool vec_ok = ((ldc & 3) == 0) && ((((uintptr_t)Cmat) & 15) == 0);
+            const int row0 = m0 + q * 32;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
+                const int c0 = hf * COLS_PER_WARP + cc;
+                const int nb = n0 + c0;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c0, v);
-                if (row < M) {
-                    const int nb = n0 + c0;
-                    if (!atomic_out && vec_ok && nb + 32 <= N) {
+                if (nb >= N) continue;                         // warp-uniform
+                if (atomic_out) {                              // split-K partial sums
+                    const int row = row0 + lane;
+                    if (row < M) {
+                        float* crow = Cmat + (int64_t)row * ldc;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o;
-                            o.x = epi_act(__uint_as_float(v[j + 0]) + (bias ? bias[nb + j + 0] : 0.f), act, slope);
-                            o.y = epi_act(__uint_as_float(v[j + 1]) + (bias ? bias[nb + j + 1] : 0.f), act, slope);
-                            o.z = epi_act(__uint_as_float(v[j + 2]) + (bias ? bias[nb + j + 2] : 0.f), act, slope);
-                            o.w = epi_act(__uint_as_float(v[j + 3]) + (bias ? bias[nb + j + 3] : 0.f), act, slope);
-                            *reinterpret_cast<float4*>(crow + nb + j) = o;
-                        }
-                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < N) atomicAdd(crow + nb + j, __uint_as_float(v[j]));
+                    }
+                    continue;
+                }
+                float bj = 0.f;
+                if (bias != nullptr && nb + lane < N) bj = __ldg(bias + nb + lane);
+                float x[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (nb + j < N) {
-                                if (atomic_out) {
-                                    atomicAdd(crow + nb + j, __uint_as_float(v[j]));
-                                } else {
-                                    crow[nb + j] = epi_act(__uint_as_float(v[j]) + (bias ? bias[nb + j] : 0.f), act, slope);
-                                }
-                            }
+                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bj, j);
+                switch (act) {                                 // hoisted: one branch per 32 values
+                    case 1:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] : expm1f(x[j]);
+                        break;
+                    case 2:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                        break;
+                    case 3:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = __fdividef(1.f, 1.f + __expf(-fmaxf(x[j], 0.f)));
+                        break;
+                    case 4:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * slope;
+                        break;
+                    case 5:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = __fdividef(1.f, 1.f + __expf(-x[j]));
+                        break;
+                    default: break;
+                }
+                // transpose through shared memory (16-byte chunks XOR-swizzled by row) -> coalesced 128 B row stores
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    *reinterpret_cast<float4*>(stage_buf + lane * 32 + ((g ^ (lane & 7)) << 2)) =
+                        make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+                __syncwarp();
+                const int rs = lane >> 3, cg = lane & 7;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = 4 * k + rs;
+                    const float4 o = *reinterpret_cast<const float4*>(stage_buf + r * 32 + ((cg ^ (r & 7)) << 2));
+                    const int row = row0 + r, col = nb + 4 * cg;
+                    if (row < M) {
+                        float* cp = Cmat + (int64_t)row * ldc + col;
+                        if (vec_ok && col + 4 <= N) {
+                            *reinterpret_cast<float4*>(cp) = o;
+                        } else {
+                            if (col + 0 < N) cp[0] = o.x;
+                            if (col + 1 < N) cp[1] = o.y;
+                            if (col + 2 < N) cp[2] = o.z;
+                            if (col + 3 < N) cp[3] = o.w;
                         }
                     }
                 }
+                __syncwarp();
             }
             tcgen05_fence_before();
             mbar_arrive(smem_u32(&tmem_empty[acc]));
@@ -377,7 +425,7 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t o
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { msha_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -2; }
@@ -430,9 +478,9 @@ MSHA_API int msha_gemm_tf32x3(const float* A, const float* B, float* C, int64_t 
     const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
     CUtensorMap ta, tb;
     int rc;
-    if (a_mn) rc = make_map(&ta, A, M, K, lda, 32, 32, true); else rc = make_map(&ta, A, K, M, lda, 32, BLOCK_M, false);
+    if (a_mn) rc = make_map(&ta, A, M, K, lda, 32, BLOCK_K, true); else rc = make_map(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, false);
     if (rc) return rc;
-    if (b_mn) rc = make_map(&tb, B, N, K, ldb, 32, 32, true); else rc = make_map(&tb, B, K, N, ldb, 32, BN, false);
+    if (b_mn) rc = make_map(&tb, B, N, K, ldb, 32, BLOCK_K, true); else rc = make_map(&tb, B, K, N, ldb, BLOCK_K, BN, false);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int atomic_out = splits > 1 ? 1 : 0;

@@ -10,6 +10,8 @@ from msha_gnn_b200 import ops
 from conftest import rel_err
 
 DEV = "cuda:0"
+# fp32 FMA accumulates ~sqrt(K)*2^-24; the 3xTF32 split adds ~2^-21 per product.  North-star tolerance is 1e-4.
+GEMM_TOL = 2e-5
 
 SHAPES = [
     # M, N, K
@@ -38,7 +40,8 @@ def test_gemm_layouts(backend, tA, tB, M, N, K, monkeypatch):
         pytest.skip("TMA needs 16-byte row strides; ops.gemm routes such shapes to the SIMT kernel")
     out = ops.gemm(A, B, transA=tA, transB=tB)
     ref = _ref(A.cpu(), B.cpu(), tA, tB)
-    assert rel_err(out.cpu().numpy(), ref.numpy()) < 2e-6, (backend, tA, tB, M, N, K)
+    err = rel_err(out.cpu().numpy(), ref.numpy())
+    assert err < GEMM_TOL, (err, backend, tA, tB, M, N, K)
 
 
 @pytest.mark.parametrize("backend", ["simt", "tcgen05"])
@@ -58,7 +61,7 @@ def test_gemm_bias_act(backend, act, monkeypatch):
         ref = torch.sigmoid(ref.clamp_min(0))
     elif act == ops.ACT_ELU:
         ref = torch.nn.functional.elu(ref)
-    assert rel_err(out.cpu().numpy(), ref.numpy()) < 2e-6
+    assert rel_err(out.cpu().numpy(), ref.numpy()) < GEMM_TOL
 
 
 def test_gemm_split_k_weight_gradient(monkeypatch):
@@ -70,7 +73,7 @@ def test_gemm_split_k_weight_gradient(monkeypatch):
     Z = torch.randn(P, C, generator=g).to(DEV)
     out = ops.gemm(G, Z, transA=True)
     ref = G.cpu().double().t() @ Z.cpu().double()
-    assert rel_err(out.cpu().numpy(), ref.numpy()) < 2e-6
+    assert rel_err(out.cpu().numpy(), ref.numpy()) < GEMM_TOL
 
 
 def test_gemm_strided_views(monkeypatch):
@@ -86,4 +89,4 @@ def test_gemm_strided_views(monkeypatch):
             ops.gemm(U[:, h * 64:(h + 1) * 64], V[:, h * 64:(h + 1) * 64], transB=True, act=ops.ACT_ELU,
                      out=out[:, h * 32:(h + 1) * 32])
             ref = torch.nn.functional.elu(U.cpu().double()[:, h * 64:(h + 1) * 64] @ V.cpu().double()[:, h * 64:(h + 1) * 64].t())
-            assert rel_err(out[:, h * 32:(h + 1) * 32].cpu().numpy(), ref.numpy()) < 2e-6
+            assert rel_err(out[:, h * 32:(h + 1) * 32].cpu().numpy(), ref.numpy()) < GEMM_TOL
