@@ -225,7 +225,7 @@ def run_ours(args):
         dst = torch.cat([pos[1], ndst])
         opt.zero_grad(set_to_none=True)
         out = model(x, graph, src, dst)                                          # (P, pred_hidden) sigmoid scores
-        loss = torch.nn.functional.nll_loss(out, labels)                        # LLP.py:235 read-out shape
+        loss = mg.functional.nll_loss(out, labels)                               # LLP.py:235 read-out shape
         loss.backward()
         opt.step()
         return loss

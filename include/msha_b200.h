@@ -142,6 +142,12 @@ int msha_log_softmax_fwd(const float* x, int64_t n, int64_t M, int pre_elu, floa
 int msha_log_softmax_bwd(const float* dy, const float* y, const float* x, int64_t n, int64_t M, int pre_elu, float* dx,
                          void* stream);
 
+/* ---- a-8 loss read-out: F.nll_loss(logp, target), mean reduction (train.py:229, LLP.py:235) ---- */
+size_t msha_nll_workspace_bytes(void);
+int msha_nll_loss_fwd(const float* logp, const int64_t* target, int64_t P, int64_t C, float* loss, int32_t* status,
+                      void* ws, size_t ws_bytes, void* stream);
+int msha_nll_loss_bwd(const int64_t* target, const float* gout, int64_t P, int64_t C, float* dlogp, void* stream);
+
 /* ---- K-9 link scorer: replaces LinkPredictor.forward LLP.py:104-115 (x_i*x_j, Linear, ReLU, sigmoid) ---- */
 int msha_pair_gather_mul(const float* hi, const float* hj, const int64_t* src, const int64_t* dst, int64_t P, int64_t C,
                          float* z, void* stream);

@@ -596,3 +596,87 @@ MSHA_API int msha_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, flo
     MSHA_LAUNCH_OK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// a-8 loss read-out: F.nll_loss(logp, target) with mean reduction (train.py:229, LLP.py:235)
+//   forward : loss = -(1/P) * sum_p logp[p, target[p]]          (two-stage deterministic sum)
+//   backward: dlogp = 0 except dlogp[p, target[p]] = -g/P       (one streaming pass writes the dense gradient)
+// ---------------------------------------------------------------------------------------------
+constexpr int NLL_BLOCKS = 592;
+__global__ void nll_fwd_stage1(const float* __restrict__ logp, const int64_t* __restrict__ target, int64_t P, int C,
+                               double* __restrict__ partial, int32_t* __restrict__ status) {
+    __shared__ double sm[8];
+    double acc = 0.0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = target[p];
+        if (t < 0 || t >= C) { atomicOr(status, 1); continue; }
+        acc += (double)logp[p * C + t];
+    }
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w];
+        partial[blockIdx.x] = s;
+    }
+}
+__global__ void nll_fwd_stage2(const double* __restrict__ partial, int n, int64_t P, float* __restrict__ loss) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) s += partial[i];
+    s = warp_sum_d(s);
+    if (threadIdx.x == 0) *loss = (float)(-s / (double)P);
+}
+__global__ void nll_bwd_kernel(const int64_t* __restrict__ target, const float* __restrict__ gout, int64_t P, int C,
+                               float* __restrict__ dlogp) {
+    // one warp per row chunk: stream zeros, patch the picked column
+    const float g = -(*gout) / (float)P;
+    const int64_t total4 = P * C / 4;              // C % 4 == 0 fast path handled by the caller
+    float4* d4 = reinterpret_cast<float4*>(dlogp);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i * 4;
+        const int64_t p = e / C;
+        const int c = (int)(e - p * C);
+        const int t = (int)target[p];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= c && t < c + 4) {
+            if (t == c) v.x = g; else if (t == c + 1) v.y = g; else if (t == c + 2) v.z = g; else v.w = g;
+        }
+        d4[i] = v;
+    }
+}
+__global__ void nll_bwd_scalar_kernel(const int64_t* __restrict__ target, const float* __restrict__ gout, int64_t P, int C,
+                                      float* __restrict__ dlogp) {
+    const float g = -(*gout) / (float)P;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P * C; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        dlogp[i] = ((int64_t)(i - p * C) == target[p]) ? g : 0.f;
+    }
+}
+MSHA_API size_t msha_nll_workspace_bytes(void) { return NLL_BLOCKS * sizeof(double); }
+// loss: float[1] device; status: int32[1] device (bit0: a target was out of range)
+MSHA_API int msha_nll_loss_fwd(const float* logp, const int64_t* target, int64_t P, int64_t C, float* loss, int32_t* status,
+                               void* ws, size_t ws_bytes, void* stream) {
+    MSHA_REQUIRE(P >= 1 && C >= 1 && C < ((int64_t)1 << 31), "nll_loss: bad shape");
+    MSHA_REQUIRE(ws_bytes >= msha_nll_workspace_bytes(), "nll_loss: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    MSHA_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    int nb = (int)(msha_cdiv(P, 256) < NLL_BLOCKS ? msha_cdiv(P, 256) : NLL_BLOCKS);
+    nll_fwd_stage1<<<nb, 256, 0, st>>>(logp, target, P, (int)C, (double*)ws, status);
+    MSHA_LAUNCH_OK();
+    nll_fwd_stage2<<<1, 32, 0, st>>>((const double*)ws, nb, P, loss);
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+// gout: float[1] device (upstream gradient of the scalar loss)
+MSHA_API int msha_nll_loss_bwd(const int64_t* target, const float* gout, int64_t P, int64_t C, float* dlogp, void* stream) {
+    MSHA_REQUIRE(P >= 1 && C >= 1 && C < ((int64_t)1 << 31), "nll_loss_bwd: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = MSHA_NUM_SMS * 16;
+    if ((C & 3) == 0 && (((uintptr_t)dlogp) & 15) == 0)
+        nll_bwd_kernel<<<grid, 256, 0, st>>>(target, gout, P, (int)C, dlogp);
+    else
+        nll_bwd_scalar_kernel<<<grid, 256, 0, st>>>(target, gout, P, (int)C, dlogp);
+    MSHA_LAUNCH_OK();
+    return 0;
+}

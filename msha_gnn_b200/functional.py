@@ -422,6 +422,39 @@ def log_softmax(x, pre_elu=False):
     return _LogSoftmax.apply(x, pre_elu)
 
 
+class _NllLoss(torch.autograd.Function):
+    """F.nll_loss(logp, target) (mean): gather + deterministic sum; backward streams the dense gradient."""
+
+    @staticmethod
+    def forward(ctx, logp, target):
+        logp = _c(logp)
+        P, C = logp.shape
+        loss = torch.empty((), dtype=torch.float32, device=logp.device)
+        status = torch.empty(1, dtype=torch.int32, device=logp.device)
+        lib = ops._lib.lib()
+        ws = workspace(lib.msha_nll_workspace_bytes(), logp.device)
+        call("msha_nll_loss_fwd", ptr(logp), ptr(target, torch.int64), P, C, loss.data_ptr(), ptr(status, I32),
+             ws.data_ptr(), ws.numel(), _stream())
+        ctx.shape = (P, C)
+        ctx.save_for_backward(target)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (target,) = ctx.saved_tensors
+        P, C = ctx.shape
+        d = torch.empty((P, C), dtype=torch.float32, device=target.device)
+        call("msha_nll_loss_bwd", ptr(target, torch.int64), _c(g).data_ptr(), P, C, ptr(d), _stream())
+        return d, None
+
+
+def nll_loss(logp, target):
+    """Mean negative log-likelihood read-out (train.py:229).  Targets must lie in [0, C)."""
+    if target.dtype != torch.int64:
+        target = target.long()
+    return _NllLoss.apply(logp, target.contiguous())
+
+
 # ------------------------------------------------------------------------------------------------
 # link scorer pieces                                                        LLP.py:104-115
 # ------------------------------------------------------------------------------------------------

@@ -292,3 +292,17 @@ def test_nll_readout_train_step_matches_oracle_at_scale():
     assert abs(float(loss) - float(lref)) < 1e-4 * abs(float(lref))
     for n in ("attention_0.W1", "attention_1.W2", "out_att.W", "Rfeatures"):
         assert rel_err(_np(dict(model.named_parameters())[n].grad), leaves[n].grad.numpy()) < 2e-4, n
+
+
+def test_nll_readout_kernel_matches_torch():
+    g = torch.Generator().manual_seed(3)
+    for P, C in [(1000, 32), (777, 7), (50000, 256)]:
+        logp = torch.log_softmax(torch.randn(P, C, generator=g), dim=1).to(DEV).requires_grad_(True)
+        tgt = torch.randint(0, C, (P,), generator=g).to(DEV)
+        loss = Fn.nll_loss(logp, tgt)
+        (loss * 3.0).backward()
+        ref_in = logp.detach().clone().requires_grad_(True)
+        ref = torch.nn.functional.nll_loss(ref_in, tgt)
+        (ref * 3.0).backward()
+        assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+        assert torch.equal(logp.grad, ref_in.grad)
