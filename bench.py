@@ -52,18 +52,19 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------------
 # synthetic graphs (host side, numpy; deterministic)
 # ------------------------------------------------------------------------------------------------
-def er_graph(n, e, seed):
-    """Directed Erdos-Renyi edge set with exactly ~e distinct (i, j) pairs and no isolated row."""
+def er_graph(n, e, seed, n_cols=None):
+    """Directed Erdos-Renyi edge set with exactly e distinct (i, j) pairs, i < n, j < n_cols, no isolated row."""
+    m = n if n_cols is None else n_cols
     rng = np.random.default_rng(seed)
-    keys = np.unique(rng.integers(0, n * n, int(e * 1.02), dtype=np.int64))
+    keys = np.unique(rng.integers(0, n * m, int(e * 1.02), dtype=np.int64))
     while keys.size < e:
-        keys = np.unique(np.concatenate([keys, rng.integers(0, n * n, e - keys.size + 1024, dtype=np.int64)]))
+        keys = np.unique(np.concatenate([keys, rng.integers(0, n * m, e - keys.size + 1024, dtype=np.int64)]))
     keys = rng.permutation(keys)[:e]
-    rows, cols = keys // n, keys % n
+    rows, cols = keys // m, keys % m
     missing = np.setdiff1d(np.arange(n), rows)
     if missing.size:                                   # give isolated rows one neighbour (replaces a surplus edge)
         rows = np.concatenate([rows[: e - missing.size], missing])
-        cols = np.concatenate([cols[: e - missing.size], rng.integers(0, n, missing.size)])
+        cols = np.concatenate([cols[: e - missing.size], rng.integers(0, m, missing.size)])
     return rows.astype(np.int64), cols.astype(np.int64)
 
 
@@ -94,39 +95,54 @@ def make_graph_host(wl, seed_shift=0):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons DURING the timed region through NVML (in-process thread;
+    an `nvidia-smi -lms` child stalls the driver for tens of ms per query on these hosts)."""
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, period_s=0.02):
+        self.index, self.period, self.rows, self._stop, self.t, self.err = index, period_s, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:          # noqa: BLE001
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:       # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, pw, rs))
+            except Exception as e:      # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        self._stop = True
+        self.t.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = [n for n, bit in names.items() if any(r[2] & bit for r in self.rows)]
+        sm = [r[0] for r in self.rows]
+        pw = [r[1] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm),
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
@@ -202,31 +218,52 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     hbm_peak, _, peak_src = load_peaks()
 
-    # ---- data: every rank holds an independent graph replica of the workload shape (weak scaling, no exchange)
-    rows, cols = make_graph_host(wl, seed_shift=rank)
+    # ---- data.  N = 1: the workload graph.  N > 1 (weak scaling): the graph grows with N -- N*n nodes, N*E edges,
+    # same degree distribution -- and is partitioned by destination-node range; rank r generates the edges of its
+    # own rows (columns anywhere), so the per-GPU work is the N = 1 work plus the per-layer all-gather /
+    # reduce-scatter of the column-side tensors (msha_gnn_b200/dist.py).
+    from msha_gnn_b200 import dist as mdist
+    n_loc, n_glob = wl["n_nodes"], wl["n_nodes"] * world
+    part = mdist.Partition(n_glob, world, rank)
+    if world == 1:
+        rows, cols = make_graph_host(wl)
+    else:
+        rows, cols = er_graph(n_loc, wl["n_edges"], 1 + rank, n_cols=n_glob)
+        rows = rows + part.lo
     E = rows.size
     L = wl["layers"]
-    pos_host = torch.from_numpy(np.stack([rows, cols])).pin_memory()            # (2, E) int64 positives
-    graph = mg.Graph.from_coo(pos_host[0].to(dev), pos_host[1].to(dev), wl["n_nodes"], wl["n_nodes"])
+    pos_host = torch.from_numpy(np.stack([rows, cols])).pin_memory()            # (2, E) int64 positives (global ids)
+    if world == 1:
+        graph = mg.Graph.from_coo(pos_host[0].to(dev), pos_host[1].to(dev), n_loc, n_loc)
+    else:
+        graph = mdist.partition_graph(pos_host[0].to(dev), pos_host[1].to(dev), part)
     assert graph.nnz == E, (graph.nnz, E)
     graph.attention_csc()
-    torch.manual_seed(42 + rank)
+    torch.manual_seed(42)                                                        # identical parameters on every rank
     model = mg.GATLinkModel(wl["feat"], wl["hidden"], wl["heads"], L, wl["pred_hidden"], dropout=0.0).to(dev)
-    x = torch.nn.Parameter(torch.rand(wl["n_nodes"], wl["feat"], device=dev))   # learnable node features (GAT.py:42)
-    opt = torch.optim.Adam(list(model.parameters()) + [x], lr=1e-3, weight_decay=5e-4, fused=True)   # train.py:207
+    torch.manual_seed(100 + rank)
+    x = torch.nn.Parameter(torch.rand(n_loc, wl["feat"], device=dev) * 0.1)      # learnable node features (GAT.py:42)
+    params = list(model.parameters())
+    opt = torch.optim.Adam(params + [x], lr=1e-3, weight_decay=5e-4, fused=True)   # train.py:207
     P = 2 * E
     labels = torch.cat([torch.ones(E, dtype=torch.int64, device=dev), torch.zeros(E, dtype=torch.int64, device=dev)])
     pos_dev = pos_host.to(dev)
     lib = mg._lib.lib()
 
     def step(it, pos):
-        nsrc, ndst = mg.functional.negative_sample(1000 + it, E, wl["n_nodes"], wl["n_nodes"], dev)
-        src = torch.cat([pos[0], nsrc])
+        nsrc, ndst = mg.functional.negative_sample(1000 + it * world + rank, E, n_loc, n_glob, dev)
+        src = torch.cat([pos[0], nsrc + part.lo])
         dst = torch.cat([pos[1], ndst])
         opt.zero_grad(set_to_none=True)
-        out = model(x, graph, src, dst)                                          # (P, pred_hidden) sigmoid scores
+        if world == 1:
+            out = model(x, graph, src, dst)                                      # (P, pred_hidden) sigmoid scores
+        else:
+            h = mdist.gat_encode(model.convs, x, graph, part)
+            out = mdist.score_pairs(model.predictor, h, src, dst, part)
         loss = mg.functional.nll_loss(out, labels)                               # LLP.py:235 read-out shape
         loss.backward()
+        if world > 1:
+            mdist.allreduce_gradients(params, world=world)
         opt.step()
         return loss
 
@@ -303,7 +340,10 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}: {wl['n_nodes']} nodes, {E} directed edges ({wl['graph']}), F={wl['feat']}, "
                                f"{L}-layer {wl['heads']}-head GAT C={wl['hidden']} + LinkPredictor(mlp,{wl['hidden']},"
                                f"{wl['pred_hidden']}) over P={P} pairs (E positives + E Philox negatives), nll loss, Adam",
-                   "per_gpu": "one graph replica per rank (no data-path collective)",
+                   "per_gpu": ("whole graph on one GPU" if world == 1 else
+                               f"weak scaling: graph of {n_glob} nodes / {E * world} edges partitioned by destination-node range, "
+                               "per layer one NCCL all-gather (fwd) + reduce-scatter (bwd) of [Wh|s_nbr]; pairs data-parallel; "
+                               "parameter gradients all-reduced"),
                    "l2_policy": "per-step working set (>= 4*P*pred_hidden bytes of scores) exceeds the 126 MB L2; no explicit flush"},
         "pairs_per_sec": P * world / (ms_dev / 1e3),
         "e2e": {"value": total_edges / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
@@ -316,6 +356,7 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(args, wl, rows, cols)
+
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -128,6 +128,11 @@ int msha_group_gather_sum(const int32_t* rowptr, const int32_t* col, const int32
 int msha_act_fwd(const float* x, float* y, int64_t n, int act, float slope, void* stream);
 int msha_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, float slope, void* stream);
 
+/* Linear backward prologue: g = dy*act'(y) and bias gradient colsum(g) in one pass (lin(x) backward, LLP.py:108) */
+size_t msha_act_bwd_colsum_workspace_bytes(int C);
+int msha_act_bwd_colsum(const float* dy, const float* y, float* g, int64_t n, int C, int act, float slope,
+                        float* colsum, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K-6 BatchNorm1d over the node axis + LeakyReLU: replaces leakyrelu(bn(.)) Ours.py:100-101 ---- */
 size_t msha_bn_workspace_bytes(int C);
 int msha_bn_lrelu_fwd(const float* x, int64_t n, int C, const float* gamma, const float* beta, float* running_mean,

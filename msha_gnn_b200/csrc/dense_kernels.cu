@@ -680,3 +680,47 @@ MSHA_API int msha_nll_loss_bwd(const int64_t* target, const float* gout, int64_t
     MSHA_LAUNCH_OK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Linear-layer backward prologue: g = dy * act'(y) written once, and db = column sums of g in the same pass
+// (bias gradient of lin(x), LLP.py:108) -- one streaming read of dy,y and one write of g.
+// ---------------------------------------------------------------------------------------------
+constexpr int ABC_BLOCKS = 592;
+__global__ void act_bwd_colsum_stage1(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ g,
+                                      int64_t n, int C, int act, float slope, double* __restrict__ partial) {
+    const int64_t rows_per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = blockIdx.x * rows_per;
+    const int64_t r1 = r0 + rows_per < n ? r0 + rows_per : n;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double acc = 0.0;
+        float run = 0.f;                       // short fp32 runs folded into the fp64 accumulator
+        int cnt = 0;
+        for (int64_t r = r0; r < r1; ++r) {
+            const float v = dy[r * C + c] * act_grad_from_out(y[r * C + c], act, slope);
+            g[r * C + c] = v;
+            run += v;
+            if (++cnt == 64) { acc += (double)run; run = 0.f; cnt = 0; }
+        }
+        partial[(int64_t)blockIdx.x * C + c] = acc + (double)run;
+    }
+}
+__global__ void colsum_stage2(const double* __restrict__ partial, int nblocks, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * C + c];
+    out[c] = (float)acc;
+}
+MSHA_API size_t msha_act_bwd_colsum_workspace_bytes(int C) { return (size_t)ABC_BLOCKS * C * sizeof(double); }
+MSHA_API int msha_act_bwd_colsum(const float* dy, const float* y, float* g, int64_t n, int C, int act, float slope,
+                                 float* colsum, void* ws, size_t ws_bytes, void* stream) {
+    MSHA_REQUIRE(n >= 1 && C >= 1, "act_bwd_colsum: bad shape");
+    MSHA_REQUIRE(ws_bytes >= msha_act_bwd_colsum_workspace_bytes(C), "act_bwd_colsum: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = (int)(n < ABC_BLOCKS ? n : ABC_BLOCKS);
+    act_bwd_colsum_stage1<<<nb, C >= 256 ? 256 : (C >= 128 ? 128 : 64), 0, st>>>(dy, y, g, n, C, act, slope, (double*)ws);
+    MSHA_LAUNCH_OK();
+    colsum_stage2<<<(unsigned)msha_cdiv(C, 128), 128, 0, st>>>((const double*)ws, nb, C, colsum);
+    MSHA_LAUNCH_OK();
+    return 0;
+}

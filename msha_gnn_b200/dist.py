@@ -1,0 +1,156 @@
+"""Multi-GPU execution of the hot path: contiguous destination-node ranges per rank.
+
+Rank r owns rows ``[bounds[r], bounds[r+1])`` of the CSR, the matching rows of X / Wh / s_self, the outputs and
+their gradients.  The one exchange per layer and direction is on the *column* side: neighbours of local rows live
+anywhere, so the forward all-gathers the per-node tensors (``Wh``, ``s_nbr``) and the backward reduce-scatters
+their gradients -- NCCL over NVLink 5 / NVSwitch (uniform all-to-all, so plain collectives; no ring ordering).
+Score batches are split data-parallel; parameter gradients are all-reduced once per step.
+
+Every rank pads its rows to ``n_max`` so the gathered buffer is ``[world * n_max, C]`` and global node ids are
+remapped once, at partition time, to ``owner * n_max + (id - bounds[owner])`` -- no compaction copy after a gather.
+
+The reference has no distributed code at all; this module is new functionality behind the
+same kernels.  Host-side logic (bounds, id remap, collective autograd, gradient all-reduce) also runs on CPU
+tensors under the gloo backend for the tests.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import functional as Fn
+from .graph import Graph
+from .ops import ACT_ELU, ACT_NONE
+
+
+class Partition:
+    """Contiguous node ranges.  ``bounds`` has world+1 entries; pass ``rowptr`` to balance edges instead of nodes."""
+
+    def __init__(self, n_nodes: int, world: int, rank: int, bounds=None):
+        self.n_nodes, self.world, self.rank = int(n_nodes), int(world), int(rank)
+        if bounds is None:
+            bounds = [(n_nodes * r) // world for r in range(world + 1)]
+        self.bounds = [int(b) for b in bounds]
+        assert len(self.bounds) == world + 1 and self.bounds[0] == 0 and self.bounds[-1] == n_nodes
+        sizes = [self.bounds[r + 1] - self.bounds[r] for r in range(world)]
+        self.n_max = max(sizes) if sizes else 0
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.n_local = self.hi - self.lo
+        self.n_padded = self.n_max * world
+        self._bt = {}
+
+    @staticmethod
+    def edge_balanced(rowptr_cpu: torch.Tensor, world: int, rank: int) -> "Partition":
+        """Split points chosen on the cumulative edge count (power-law graphs)."""
+        n = rowptr_cpu.numel() - 1
+        total = int(rowptr_cpu[-1])
+        targets = torch.tensor([(total * r) // world for r in range(1, world)], dtype=rowptr_cpu.dtype)
+        cuts = torch.searchsorted(rowptr_cpu, targets).clamp_(0, n).tolist()
+        return Partition(n, world, rank, [0] + cuts + [n])
+
+    def owner_of(self, ids: torch.Tensor) -> torch.Tensor:
+        key = (ids.device,)
+        if key not in self._bt:
+            self._bt[key] = torch.tensor(self.bounds[1:-1], dtype=torch.int64, device=ids.device)
+        return torch.bucketize(ids, self._bt[key], right=True)
+
+    def to_padded(self, ids: torch.Tensor) -> torch.Tensor:
+        """global node id -> index into the gathered [world * n_max, C] buffer."""
+        ids = ids.to(torch.int64)
+        own = self.owner_of(ids)
+        lo = torch.tensor(self.bounds[:-1], dtype=torch.int64, device=ids.device)[own]
+        return own * self.n_max + (ids - lo)
+
+    def local_slice_of_padded(self):
+        return slice(self.rank * self.n_max, self.rank * self.n_max + self.n_local)
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """[n_local, C] -> [world * n_max, C]; backward: reduce-scatter (sum) of the gathered gradient."""
+
+    @staticmethod
+    def forward(ctx, x, part: Partition, group):
+        ctx.part, ctx.group = part, group
+        C = x.shape[1]
+        padded = x
+        if part.n_local != part.n_max:
+            padded = x.new_zeros((part.n_max, C))
+            padded[: part.n_local] = x
+        out = x.new_empty((part.n_padded, C))
+        if part.world == 1:
+            out.copy_(padded)
+        else:
+            dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        part, group = ctx.part, ctx.group
+        g = g.contiguous()
+        if part.world == 1:
+            return g[: part.n_local], None, None
+        out = g.new_empty((part.n_max, g.shape[1]))
+        if dist.get_backend(group) == "gloo":            # gloo has no reduce_scatter: all-reduce + slice (tests only)
+            dist.all_reduce(g, group=group)
+            out.copy_(g[part.rank * part.n_max:(part.rank + 1) * part.n_max])
+        else:
+            dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=group)
+        return out[: part.n_local], None, None
+
+
+def all_gather_rows(x, part: Partition, group=None):
+    return _AllGatherRows.apply(x, part, group)
+
+
+def allreduce_gradients(params, group=None, world=None):
+    """Sum parameter gradients over ranks (each rank holds the contribution of its rows / pairs)."""
+    world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+    if world == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def partition_graph(rows: torch.Tensor, cols: torch.Tensor, part: Partition) -> Graph:
+    """Local CSR of this rank: ``rows`` (global ids in [lo, hi)) and ``cols`` (global ids) of the edges whose
+    destination row the rank owns.  Columns are remapped to the padded gathered indexing."""
+    if rows.numel() and (int(rows.min()) < part.lo or int(rows.max()) >= part.hi):
+        raise IndexError("partition_graph: a row id lies outside this rank's node range")
+    return Graph.from_coo(rows.to(torch.int64) - part.lo, part.to_padded(cols), part.n_local, part.n_padded)
+
+
+def gat_encode(convs, x_local, pgraph: Graph, part: Partition, group=None, training=True):
+    """Partitioned forward of a stack of ``GATConv`` layers (same arithmetic as ``GATConv.forward``): per layer one
+    all-gather of [Wh | s_nbr] in the forward and one reduce-scatter of its gradient in the backward."""
+    h = x_local
+    for conv in convs:
+        H, D = conv.heads, conv.out_features
+        Wh = Fn.linear(h, conv.W)                                              # local rows only
+        s_nbr, s_self = Fn.node_scores(Wh, conv.a_nbr, conv.a_self, H, D)
+        gathered = all_gather_rows(torch.cat([Wh, s_nbr], dim=1), part, group)  # one collective for both tensors
+        Wh_g = gathered[:, : H * D].contiguous()
+        s_nbr_g = gathered[:, H * D:].contiguous()
+        fuse_elu = conv.activation == "elu" and conv.concat
+        out, _ = Fn.attention_block(pgraph, s_nbr_g, s_self, Wh_g, heads=H, act=ACT_ELU if fuse_elu else ACT_NONE,
+                                    dropout_p=conv.dropout, training=training)
+        if not conv.concat:
+            out = out.view(out.shape[0], H, D).mean(dim=1)
+            if conv.activation == "elu":
+                out = Fn.elu(out)
+        h = out
+    return h
+
+
+def score_pairs(predictor, h_local, src_global, dst_global, part: Partition, group=None):
+    """Data-parallel link scoring: this rank scores its own pair shard against the all-gathered embeddings;
+    the backward reduce-scatters d h to the owning ranks."""
+    h_g = all_gather_rows(h_local, part, group)
+    return predictor.forward_pairs(h_g, h_g, part.to_padded(src_global), part.to_padded(dst_global))

@@ -17,7 +17,12 @@ I32 = torch.int32
 
 
 def _c(t):
-    return t if t.is_contiguous() else t.contiguous()
+    """Contiguous and 16-byte aligned (views sliced out of a larger buffer may start at any 4-byte offset)."""
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
 
 
 # ------------------------------------------------------------------------------------------------
@@ -58,10 +63,20 @@ class _LinearBiasAct(torch.autograd.Function):
     def backward(ctx, dy):
         x, W, y = ctx.saved_tensors
         dy = _c(dy)
-        g = ops.act_bwd(dy, y, ctx.act) if ctx.act != ACT_NONE else dy
+        db = None
+        if ctx.needs_input_grad[2]:
+            # g = dy * act'(y) and db = colsum(g) in one streaming pass
+            n, C = y.shape
+            g = torch.empty_like(y)
+            db = torch.empty(C, dtype=torch.float32, device=y.device)
+            lib = ops._lib.lib()
+            ws = workspace(lib.msha_act_bwd_colsum_workspace_bytes(C), y.device)
+            call("msha_act_bwd_colsum", ptr(dy), ptr(y), ptr(g), n, C, ctx.act, LRELU_SLOPE, ptr(db), ws.data_ptr(),
+                 ws.numel(), _stream())
+        else:
+            g = ops.act_bwd(dy, y, ctx.act) if ctx.act != ACT_NONE else dy
         dx = ops.gemm(g, W) if ctx.needs_input_grad[0] else None
         dW = ops.gemm(g, x, transA=True) if ctx.needs_input_grad[1] else None
-        db = colsum(g) if ctx.needs_input_grad[2] else None
         return dx, dW, db, None
 
 
