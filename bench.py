@@ -306,6 +306,9 @@ def run_ours(args):
 
     # ---- per-kernel profile pass (outside the timed region)
     roofline, kernels = None, []
+    if rank != 0:                      # the profile steps contain collectives: every rank must run them
+        step(10_000, pos_dev)
+        step(10_001, pos_dev)
     if rank == 0:
         with KernelTimer(ops) as kt:
             step(10_000, pos_dev)
