@@ -71,13 +71,13 @@ int msha_csr_normalize_columns(const int32_t* col, const float* val, int64_t nnz
  *      HGANE.py:46-47,66-68.  alpha_in != NULL -> plain weighted SpMM (K-3 only). ---- */
 int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr, const float* s_self,
                  const float* feat, int H, int D, float slope, const float* alpha_in, float* alpha_out, float* out,
-                 int act, float drop_p, uint64_t drop_seed, void* stream);
+                 int act, float* lse_out, float drop_p, uint64_t drop_seed, void* stream);
 /* backward row pass (autograd of the lines above): d alpha, softmax and LeakyReLU backward, d s_self */
 int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
                       const float* s_self, float slope, const float* alpha, const float* feat, const float* dout,
                       const float* out, int act, float* dz_out, const float* dT, const float* fT,
-                      const float* dalpha_extra, int H, int D, float* dlogit, float* ds_self, float drop_p,
-                      uint64_t drop_seed, void* stream);
+                      const float* dalpha_extra, const float* dlse, int H, int D, float* dlogit, float* ds_self,
+                      float drop_p, uint64_t drop_seed, void* stream);
 /* ---- K-4 transposed SpMM over CSC: replaces `attention_inter.t() @ h2` Ours.py:100 and the d feat pass ---- */
 int msha_spmm_csc(const int32_t* colptr, const int32_t* rowidx, const int32_t* perm, int64_t n_cols, const float* w,
                   const float* feat, int H, int D, float* out, int accumulate, const float* esum_in, float* esum_out,

@@ -8,13 +8,13 @@ There is no CPU fallback: ops raise if the library is not built or a tensor is n
 from . import _lib                                   # noqa: F401
 from .graph import Graph, as_graph                   # noqa: F401
 from .intra import GroupLists                        # noqa: F401
-from .layers import (GAT, GATConv, GATLinkModel, GraphAttentionLayer, GraphConvolution, LinkPredictor,   # noqa: F401
+from .layers import (GAT, GATConv, GATLinkModel, GraphAttentionLayer, GraphConvolution, HGANELayer, LinkPredictor,   # noqa: F401
                      Ours, OursLayer, OursLayer2, OursLayer3, Teacher_LinkPredictor, ablation1, ablation2,
                      ablation3, dense_attention, last_attention)
 from . import functional                             # noqa: F401
 
 __all__ = ["Graph", "as_graph", "GroupLists", "GAT", "GATConv", "GATLinkModel", "GraphAttentionLayer",
-           "GraphConvolution", "LinkPredictor", "Teacher_LinkPredictor", "Ours", "OursLayer", "OursLayer2",
+           "GraphConvolution", "HGANELayer", "LinkPredictor", "Teacher_LinkPredictor", "Ours", "OursLayer", "OursLayer2",
            "OursLayer3", "ablation1", "ablation2", "ablation3", "functional"]
 
 

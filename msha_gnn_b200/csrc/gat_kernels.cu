@@ -53,7 +53,7 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
                const float* __restrict__ s_nbr, const float* __restrict__ s_self,
                const float* __restrict__ feat, int H, int D, float slope,
                const float* __restrict__ alpha_in, float* __restrict__ alpha_out,
-               float* __restrict__ out, int act, DropArgs drop) {
+               float* __restrict__ out, int act, float* __restrict__ lse_out, DropArgs drop) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * GAT_WARPS + warp;
@@ -91,6 +91,8 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
             sum = warp_sum(sum);
             if (lane == h) { m_stat = mx; l_stat = sum; }
         }
+        // log-sum-exp of the row's logits (HGANE's joint normaliser needs the un-normalised sums, HGANE.py:61-62)
+        if (lse_out != nullptr && lane < H) lse_out[(int64_t)row * H + lane] = (end > beg) ? m_stat + logf(l_stat) : -INFINITY;
     }
 
     float acc[VPL][VW];
@@ -166,7 +168,7 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
                     const float* __restrict__ dout, const float* __restrict__ outp, int act,
                     float* __restrict__ dz_out,
                     const float* __restrict__ dT, const float* __restrict__ fT,
-                    const float* __restrict__ dalpha_extra,
+                    const float* __restrict__ dalpha_extra, const float* __restrict__ dlse,
                     int H, int D, float* __restrict__ dlogit, float* __restrict__ ds_self, DropArgs drop) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -266,6 +268,12 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
         __syncwarp();
     }
     if (!softmax_mode) return;
+    // d lse_i / d e_ij = alpha_ij : fold the upstream gradient of the row's log-sum-exp into r_h
+    if (dlse != nullptr) {
+        __syncwarp();
+        for (int h = lane; h < H; h += 32) sm_r[h] -= dlse[(int64_t)row * H + h];
+        __syncwarp();
+    }
 
     // ---- phase 2: softmax + LeakyReLU backward
     for (int e0 = beg; e0 < end; e0 += 32) {
@@ -424,7 +432,8 @@ static DropArgs make_drop(float p, uint64_t seed, uint32_t stream) {
 // alpha_in != NULL: plain weighted SpMM with the given per-edge, per-head weights.
 MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
                           const float* s_self, const float* feat, int H, int D, float slope, const float* alpha_in,
-                          float* alpha_out, float* out, int act, float drop_p, uint64_t drop_seed, void* stream) {
+                          float* alpha_out, float* out, int act, float* lse_out, float drop_p, uint64_t drop_seed,
+                          void* stream) {
     MSHA_REQUIRE(H >= 1 && H <= 32 && D >= 1, "gat_fwd: need 1 <= H <= 32, D >= 1");
     MSHA_REQUIRE(alpha_in != nullptr || (s_nbr != nullptr && s_self != nullptr), "gat_fwd: scores or alpha required");
     MSHA_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), "gat_fwd: bad n_rows");
@@ -437,7 +446,7 @@ MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_r
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(A, B)                                                                                             \
     gat_fwd_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, feat, H, D, \
-                                                          slope, alpha_in, alpha_out, out, act, drop)
+                                                          slope, alpha_in, alpha_out, out, act, lse_out, drop)
     DISPATCH_LAYOUT(vw, vpl, CALL)
 #undef CALL
     MSHA_LAUNCH_OK();
@@ -448,8 +457,8 @@ MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_r
 MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
                                const float* s_self, float slope, const float* alpha, const float* feat,
                                const float* dout, const float* out, int act, float* dz_out, const float* dT,
-                               const float* fT, const float* dalpha_extra, int H, int D, float* dlogit,
-                               float* ds_self, float drop_p, uint64_t drop_seed, void* stream) {
+                               const float* fT, const float* dalpha_extra, const float* dlse, int H, int D,
+                               float* dlogit, float* ds_self, float drop_p, uint64_t drop_seed, void* stream) {
     MSHA_REQUIRE(H >= 1 && H <= 32 && D >= 1, "gat_bwd_rows: need 1 <= H <= 32, D >= 1");
     MSHA_REQUIRE((dT == nullptr) == (fT == nullptr), "gat_bwd_rows: dT and fT go together");
     MSHA_REQUIRE(act == 0 || out != nullptr, "gat_bwd_rows: activated output needed for ELU backward");
@@ -464,7 +473,7 @@ MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_
 #define CALL(A, B)                                                                                              \
     gat_bwd_rows_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, slope,  \
                                                                alpha, feat, dout, out, act, dz_out, dT, fT,     \
-                                                               dalpha_extra, H, D, dlogit, ds_self, drop)
+                                                               dalpha_extra, dlse, H, D, dlogit, ds_self, drop)
     DISPATCH_LAYOUT(vw, vpl, CALL)
 #undef CALL
     MSHA_LAUNCH_OK();

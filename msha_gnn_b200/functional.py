@@ -188,7 +188,7 @@ def node_scores(feat, a1, a2=None, H=1, D=None):
 # ------------------------------------------------------------------------------------------------
 class _AttentionBlock(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, s_nbr, s_self, feat_nbr, feat_self, dalpha_hook, graph: Graph, H, D, act, p, seed, want_cols):
+    def forward(ctx, s_nbr, s_self, feat_nbr, feat_self, graph: Graph, H, D, act, p, seed, want_cols, want_lse):
         s_nbr, s_self, feat_nbr = _c(s_nbr), _c(s_self), _c(feat_nbr)
         rp, col = graph.attention_csr()
         N, M = graph.n_rows, graph.n_cols
@@ -199,8 +199,9 @@ class _AttentionBlock(torch.autograd.Function):
         dev = feat_nbr.device
         alpha = torch.empty((E, H), dtype=torch.float32, device=dev)
         out = torch.empty((N, C), dtype=torch.float32, device=dev)
+        lse = torch.empty((N, H), dtype=torch.float32, device=dev) if want_lse else None
         call("msha_gat_fwd", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr), ptr(s_self), ptr(feat_nbr), H, D, LRELU_SLOPE,
-             None, ptr(alpha), ptr(out), act, p, seed, _stream())
+             None, ptr(alpha), ptr(out), act, ptr(lse), p, seed, _stream())
         out_cols = None
         if want_cols:
             feat_self = _c(feat_self)
@@ -209,20 +210,27 @@ class _AttentionBlock(torch.autograd.Function):
             out_cols = torch.empty((M, C), dtype=torch.float32, device=dev)
             call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(feat_self), H, D,
                  ptr(out_cols), 0, None, None, p, seed, _stream())
-        ctx.graph, ctx.H, ctx.D, ctx.act, ctx.p, ctx.seed, ctx.want_cols = graph, H, D, act, p, seed, want_cols
+        ctx.graph, ctx.H, ctx.D, ctx.act, ctx.p, ctx.seed = graph, H, D, act, p, seed
+        ctx.want_cols, ctx.want_lse = want_cols, want_lse
         ctx.save_for_backward(s_nbr, s_self, feat_nbr, feat_self if want_cols else None, alpha,
                               out if act != ACT_NONE else None)
         ctx.set_materialize_grads(False)
+        res = [out]
         if want_cols:
-            return out, out_cols, alpha
-        return out, alpha
+            res.append(out_cols)
+        res.append(alpha)
+        if want_lse:
+            res.append(lse)
+        return tuple(res)
 
     @staticmethod
     def backward(ctx, d_rows, *rest):
         s_nbr, s_self, feat_nbr, feat_self, alpha, out = ctx.saved_tensors
         graph, H, D, act, p, seed = ctx.graph, ctx.H, ctx.D, ctx.act, ctx.p, ctx.seed
-        d_cols = rest[0] if ctx.want_cols else None
-        d_alpha = rest[1] if ctx.want_cols else rest[0]      # grad w.r.t. the pre-dropout alpha (may be None)
+        rest = list(rest)
+        d_cols = rest.pop(0) if ctx.want_cols else None
+        d_alpha = rest.pop(0)                                # grad w.r.t. the pre-dropout alpha (may be None)
+        d_lse = rest.pop(0) if ctx.want_lse else None
         rp, col = graph.attention_csr()
         colptr, rowidx, perm = graph.attention_csc()
         N, M = graph.n_rows, graph.n_cols
@@ -235,9 +243,10 @@ class _AttentionBlock(torch.autograd.Function):
         ds_self = torch.empty((N, H), dtype=torch.float32, device=dev)
         dz = torch.empty((N, C), dtype=torch.float32, device=dev) if act != ACT_NONE else None
         extra = _c(d_alpha) if d_alpha is not None else None
+        dlse = _c(d_lse) if d_lse is not None else None
         call("msha_gat_bwd_rows", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr), ptr(s_self), LRELU_SLOPE, ptr(alpha),
              ptr(feat_nbr), ptr(d_rows), ptr(out), act, ptr(dz), ptr(d_cols), ptr(feat_self) if d_cols is not None else None,
-             ptr(extra), H, D, ptr(dlogit), ptr(ds_self), p, seed, _stream())
+             ptr(extra), ptr(dlse), H, D, ptr(dlogit), ptr(ds_self), p, seed, _stream())
         dzz = dz if dz is not None else d_rows
         dfeat_nbr = torch.empty((M, C), dtype=torch.float32, device=dev)
         ds_nbr = torch.empty((M, H), dtype=torch.float32, device=dev)
@@ -247,19 +256,20 @@ class _AttentionBlock(torch.autograd.Function):
         if ctx.want_cols and d_cols is not None and ctx.needs_input_grad[3]:
             dfeat_self = torch.empty((N, C), dtype=torch.float32, device=dev)
             call("msha_gat_fwd", ptr(rp, I32), ptr(col, I32), N, None, None, ptr(d_cols), H, D, LRELU_SLOPE, ptr(alpha),
-                 None, ptr(dfeat_self), ACT_NONE, p, seed, _stream())
+                 None, ptr(dfeat_self), ACT_NONE, None, p, seed, _stream())
         return ds_nbr, ds_self, dfeat_nbr, dfeat_self, None, None, None, None, None, None, None, None
 
 
 def attention_block(graph: Graph, s_nbr, s_self, feat_nbr, feat_self=None, heads=1, act=ACT_NONE, dropout_p=0.0,
-                    training=True, want_cols=False):
-    """Returns (out_rows, alpha) or (out_rows, out_cols, alpha); alpha is [E_att, H], the pre-dropout attention
-    over the attention CSR (differentiable: gradients flowing into it join the softmax backward)."""
+                    training=True, want_cols=False, want_lse=False):
+    """Returns (out_rows, [out_cols,] alpha [, lse]); alpha is [E_att, H], the pre-dropout attention over the
+    attention CSR (differentiable: gradients flowing into it join the softmax backward); lse is the row-wise
+    log-sum-exp of the logits ([N, H], -inf for rows without edges)."""
     C = feat_nbr.shape[1]
     D = C // heads
     p = float(dropout_p) if training else 0.0
     seed = ops.next_seed() if p > 0 else 0
-    return _AttentionBlock.apply(s_nbr, s_self, feat_nbr, feat_self, None, graph, heads, D, act, p, seed, want_cols)
+    return _AttentionBlock.apply(s_nbr, s_self, feat_nbr, feat_self, graph, heads, D, act, p, seed, want_cols, want_lse)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -289,7 +299,7 @@ class _SpmmT(torch.autograd.Function):
         C = dout.shape[1]
         dfeat = torch.empty((g.n_rows, C), dtype=torch.float32, device=dout.device)
         call("msha_gat_fwd", ptr(g.rowptr, I32), ptr(g.col, I32), g.n_rows, None, None, ptr(dout), 1, C, LRELU_SLOPE,
-             ptr(w), None, ptr(dfeat), ACT_NONE, 0.0, 0, _stream())
+             ptr(w), None, ptr(dfeat), ACT_NONE, None, 0.0, 0, _stream())
         return dfeat, None, None
 
 

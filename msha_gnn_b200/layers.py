@@ -285,6 +285,73 @@ class ablation1(nn.Module):
 
 
 # =================================================================================================
+# a-6  HGANE.GraphAttentionLayer                                                HGANE.py:11-76
+# =================================================================================================
+class HGANELayer(nn.Module):
+    """Batch-subgraph GAT of HGANE.py (the class is called ``GraphAttentionLayer`` there; see ``msha_gnn_b200.hgane``).
+
+    Inter attention (B x M) is a plain row softmax; the intra attention (B x B, genuine pairwise logits) is
+    normalised by the *joint* sum ``sum exp(intra) + sum exp(inter)`` (HGANE.py:61-64), i.e.
+    ``att_intra = softmax_intra * sigmoid(lse_intra - lse_inter)`` -- both softmaxes run in the fused attention kernel,
+    which also returns the rows' log-sum-exp."""
+
+    def __init__(self, in_features, out_features, Scount, Rcount, gdp, dropout=0.5):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.dropout = dropout
+        self.alpha = 0.2
+        gdp_values = _gdp_column(gdp)
+        self.features = nn.Parameter(torch.cat((torch.rand([Scount, self.in_features])[:, :-1], gdp_values), dim=1))
+        self.source_embedding = nn.Parameter(torch.rand([Scount, self.in_features]))
+        self.recipient_embedding = nn.Parameter(torch.rand([Rcount, self.in_features]))
+        self.W1 = nn.Linear(in_features, out_features, bias=False)
+        self.W2 = nn.Linear(in_features, out_features, bias=False)
+        self.a12 = nn.Linear(2 * out_features, 1, bias=False)
+        self.a3 = nn.Linear(2 * out_features, 1, bias=False)
+        self.leakyrelu = nn.LeakyReLU(self.alpha)
+        self.bn1 = nn.BatchNorm1d(out_features)
+        self.bn2 = nn.BatchNorm1d(out_features)
+        nn.init.xavier_uniform_(self.W1.weight)
+        nn.init.xavier_uniform_(self.W2.weight)
+        nn.init.xavier_uniform_(self.a12.weight)
+        nn.init.xavier_uniform_(self.a3.weight)
+
+    def forward(self, adj_inter, adj_intra, source_index):
+        if not adj_inter.is_cuda:
+            raise RuntimeError("msha_b200 is CUDA-only: move the adjacency to the GPU (no CPU fallback)")
+        src = source_index
+        d = self.out_features
+        g_inter = Graph.from_dense(adj_inter[src])                              # (B, M)   HGANE.py:39
+        g_intra = Graph.from_dense(adj_intra[src[:, None], src])                # (B, B)   HGANE.py:38
+        g_inter.isolated = g_intra.isolated = "zero"          # no -9e15 masking here: exp() of the mask is 0 (HGANE.py:61)
+        E_r = self.recipient_embedding
+        E_s = self.source_embedding.index_select(0, src)
+        h1 = Fn.linear_bias_act(E_r, self.W1.weight, None, ACT_NONE)            # HGANE.py:40
+        h2 = Fn.linear_bias_act(E_s, self.W2.weight, None, ACT_NONE)            # HGANE.py:41
+        a12, a3 = self.a12.weight, self.a3.weight
+        s12_nbr = Fn.node_scores(h1, a12[:, :d], None, 1, d)                    # a12[:d'].h1[j]   HGANE.py:46-47
+        s12_self = Fn.node_scores(h2, a12[:, d:], None, 1, d)                   # a12[d':].h2[i]
+        s3_self = Fn.node_scores(h2, a3[:, :d], None, 1, d)                     # a3[:d'].h2[i]    HGANE.py:49-52
+        s3_nbr = Fn.node_scores(h2, a3[:, d:], None, 1, d)                      # a3[d':].h2[j]
+        agg_inter, vin_raw, _, lse12 = Fn.attention_block(g_inter, s12_nbr, s12_self, E_r, E_s, heads=1,
+                                                          dropout_p=self.dropout, training=self.training,
+                                                          want_cols=True, want_lse=True)   # HGANE.py:66-68
+        agg_intra, _, lse3 = Fn.attention_block(g_intra, s3_nbr, s3_self, E_s, heads=1, dropout_p=self.dropout,
+                                                training=self.training, want_lse=True)
+        rho = torch.sigmoid(lse3 - lse12)                                       # S_intra / (S_intra + S_inter)  HGANE.py:61-64
+        u_in = Fn.linear_bias_act(agg_inter, self.W1.weight, None, ACT_NONE) \
+            + Fn.linear_bias_act(rho * agg_intra, self.W2.weight, None, ACT_NONE)               # HGANE.py:71-72
+        v_in = Fn.linear_bias_act(vin_raw, self.W1.weight, None, ACT_NONE)                      # HGANE.py:73
+        u = _bn_heads(u_in, [self.bn1], self.training)
+        v = _bn_heads(v_in, [self.bn2], self.training)
+        out = Fn.matmul_nt_act(u, v, 1, ACT_ELU)                                                # HGANE.py:75-76
+        # a batch row without inter neighbour is 0/0 in the reference (HGANE.py:67-68) and poisons v, hence everything
+        poison = torch.where((g_inter.degrees == 0).any(), float("nan"), 1.0)
+        return out * poison
+
+
+# =================================================================================================
 # a-7  LinkPredictor / Teacher_LinkPredictor                                   LLP.py:86-115,170-198
 # =================================================================================================
 class LinkPredictor(nn.Module):

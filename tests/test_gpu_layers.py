@@ -146,6 +146,27 @@ def test_msha_models_golden(name, cls):
     _check_grads(dict(model.named_parameters()), g, names, tol=2e-4)
 
 
+# ---------------------------------------------------------------------------------- a-6
+def test_hgane_layer_golden():
+    g = load_golden("hgane")
+    p = params_of(g)
+    Ns, Fin = p["source_embedding"].shape
+    M = p["recipient_embedding"].shape[0]
+    d = p["W1.weight"].shape[0]
+    layer = _load(mg.HGANELayer(Fin, d, Ns, M, {str(i): 0.0 for i in range(Ns)}, dropout=0.0), p).train()
+    out = layer(_t(g["adj_inter"]), _t(g["adj_intra"]), torch.tensor(g["src"], device=DEV))
+    assert rel_err(_np(out), g["out"]) < TOL
+    (out * _t(g["G"])).sum().backward()
+    names = ["source_embedding", "recipient_embedding", "W1.weight", "W2.weight", "a12.weight", "a3.weight",
+             "bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias"]
+    _check_grads(dict(layer.named_parameters()), g, names, tol=2e-4)
+    # a batch row without inter neighbour -> NaN everywhere (0/0, HGANE.py:67-68)
+    adj = g["adj_inter"].copy()
+    adj[g["src"][0]] = 0
+    with torch.no_grad():
+        assert torch.isnan(layer(_t(adj), _t(g["adj_intra"]), torch.tensor(g["src"], device=DEV))).all()
+
+
 # ---------------------------------------------------------------------------------- a-7
 @pytest.mark.parametrize("tag,predictor,nl", [("mlp2", "mlp", 2), ("mlp3", "mlp", 3), ("inner", "inner", 2)])
 @pytest.mark.parametrize("fused", [False, True])
