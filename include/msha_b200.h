@@ -162,6 +162,13 @@ int msha_pair_dot(const float* hi, const float* hj, const int64_t* src, const in
                   int act, float* out, void* stream);
 int msha_pair_dot_bwd(const float* dout, const float* out, const float* hi, const float* hj, const int64_t* src,
                       const int64_t* dst, int64_t P, int64_t C, int act, float* dhi, float* dhj, void* stream);
+/* fused tensor-core scorer (one hidden Linear): pair gather * Hadamard -> 3xTF32 tcgen05 GEMM -> bias, relu, sigmoid.
+ * W0 is [Hd, C] (nn.Linear layout).  Replaces LLP.py:105-115 without materialising x_i * x_j. */
+int msha_score_mlp_supported(const float* hi_tab, const float* hj_tab, const float* W0, int64_t C, int64_t Hd);
+size_t msha_score_mlp_workspace_bytes(int64_t C, int64_t Hd);
+int msha_score_mlp_fwd(const float* hi_tab, const float* hj_tab, const int64_t* src, const int64_t* dst, int64_t P,
+                       int64_t C, const float* W0, const float* b0, int64_t Hd, int act, float slope, float* out,
+                       int64_t ldo, void* ws, size_t ws_bytes, void* stream);
 /* builder-defined sampler (the reference's --ns_rate flags are dead code, LLP.py:26-29) */
 int msha_negative_sample(uint64_t seed, int64_t P, int64_t n_src, int64_t n_dst, int64_t* src, int64_t* dst,
                          void* stream);

@@ -19,7 +19,7 @@
 //     K-major : stored [MN, K] (K contiguous)  -> one TMA box {16 K, rows},  UMMA K-major SWIZZLE_64B
 //     MN-major: stored [K, MN] (MN contiguous) -> boxes {32 MN, 16 K},       UMMA MN-major SWIZZLE_128B_BASE32B
 #include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace {
 
@@ -31,89 +31,6 @@ constexpr int CVT_THREADS = 128;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4; // per epilogue warp: 32x32 fp32 transpose buffer
-constexpr uint32_t SPIN_LIMIT = 1u << 24;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done, spins = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!done && ++spins > SPIN_LIMIT) __trap();      // a dead pipeline must fault, never hang the GPU
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1.
-// K-major fp32 tiles use SWIZZLE_64B (8 rows x 64 B atoms, SBO = 512).  MN-major 32-bit operands only exist in
-// the SWIZZLE_128B_BASE32B layout (Swizzle<2,5,2>: 4 K-rows x 128 B atoms, SBO = 512 between K atoms, LBO between
-// 32-element MN chunks) -- written by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-    d |= (uint64_t)layout_type << 61;  // 4 = SWIZZLE_64B (K-major), 1 = SWIZZLE_128B_BASE32B (MN-major tf32)
-    return d;
-}
-// 32-bit instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
-    return (1u << 4)                    // c_format = F32
-           | (2u << 7)                  // a_format = TF32
-           | (2u << 10)                 // b_format = TF32
-           | ((a_mn ? 1u : 0u) << 15)   // a_major
-           | ((b_mn ? 1u : 0u) << 16)   // b_major
-           | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 __device__ __forceinline__ float epi_act(float x, int act, float slope) {
     switch (act) {
@@ -398,40 +315,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
-// 2-D fp32 tensor map: inner dimension `inner` (contiguous), `outer` rows of stride ld floats; 128B swizzle
-static int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
-                    int box_outer, bool mn_major) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) { msha_set_error("cuTensorMapEncodeTiled entry point unavailable"); return -2; }
-    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { msha_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -2; }
-    return 0;
-}
-
 template <int BN, bool AM, bool BM>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int M, int N, int K, int64_t ldc,
                   const float* bias, int act, float slope, int splits, int atomic_out, cudaStream_t st) {
@@ -478,9 +361,9 @@ MSHA_API int msha_gemm_tf32x3(const float* A, const float* B, float* C, int64_t 
     const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
     CUtensorMap ta, tb;
     int rc;
-    if (a_mn) rc = make_map(&ta, A, M, K, lda, 32, BLOCK_K, true); else rc = make_map(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, false);
+    if (a_mn) rc = tc_make_map(&ta, A, M, K, lda, 32, BLOCK_K, true); else rc = tc_make_map(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, false);
     if (rc) return rc;
-    if (b_mn) rc = make_map(&tb, B, N, K, ldb, 32, BLOCK_K, true); else rc = make_map(&tb, B, K, N, ldb, BLOCK_K, BN, false);
+    if (b_mn) rc = tc_make_map(&tb, B, N, K, ldb, 32, BLOCK_K, true); else rc = tc_make_map(&tb, B, K, N, ldb, BLOCK_K, BN, false);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int atomic_out = splits > 1 ? 1 : 0;

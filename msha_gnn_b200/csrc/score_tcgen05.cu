@@ -1,0 +1,360 @@
+// K-9: fused link-scorer kernels on the tensor cores (LinkPredictor 'mlp' with one hidden Linear, LLP.py:104-115):
+//
+//   score_fwd     out[p,:] = act( (h_i[src[p]] * h_j[dst[p]]) @ W0^T + b0 )       -- LLP.py:105-110,115
+//                 pair-gather + Hadamard + 3xTF32 split are done by producer warps straight into the swizzled
+//                 shared-memory A tile (no Z = x_i*x_j tensor in HBM); W0 (pre-split hi/lo) arrives by TMA;
+//                 tcgen05.mma accumulates in TMEM; epilogue adds bias, applies relu+sigmoid, stores coalesced.
+//   score_bwd_dz  G = dOut * act'(out) (written once, + bias gradient), dZ = G @ W0 on the tensor cores, and the
+//                 epilogue scatters  dh_i[src] += dZ*h_j[dst],  dh_j[dst] += dZ*h_i[src]  with 128-bit atomics.
+//   score_bwd_dw  dW0 = G^T @ Z with Z regenerated from the gathers (MN-major operands, whole K range per CTA in TMEM).
+//
+// Same warp-specialised skeleton as gemm_tcgen05.cu (TMA thread, MMA thread, TMEM allocator, 4 producer warps,
+// 8 epilogue warps; mbarrier rings; double-buffered TMEM accumulators).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 16;
+constexpr int UMMA_K = 8;
+constexpr int NUM_THREADS = 512;
+constexpr int PROD_THREADS = 128;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;
+
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_grad_out(float y, int act, float slope) {
+    switch (act) {
+        case 1: return y > 0.f ? 1.f : y + 1.f;
+        case 2: return y > 0.f ? 1.f : 0.f;
+        case 3: return y > 0.5f ? y * (1.f - y) : 0.f;
+        case 4: return y > 0.f ? 1.f : slope;
+        case 5: return y * (1.f - y);
+        default: return 1.f;
+    }
+}
+
+template <int BLOCK_N>
+struct SCfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;          // 8 KB per hi / lo tile
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
+    static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;
+    static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 512;
+};
+
+// Apply activation to 32 values (switch hoisted out of the element loop).
+__device__ __forceinline__ void act32(float (&x)[32], int act, float slope) {
+    switch (act) {
+        case 1:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] : expm1f(x[j]);
+            break;
+        case 2:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+            break;
+        case 3:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __fdividef(1.f, 1.f + __expf(-fmaxf(x[j], 0.f)));
+            break;
+        case 4:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * slope;
+            break;
+        case 5:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __fdividef(1.f, 1.f + __expf(-x[j]));
+            break;
+        default: break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused forward
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                 const float* __restrict__ hi_tab, const float* __restrict__ hj_tab, const int64_t* __restrict__ src,
+                 const int64_t* __restrict__ dst, int64_t P, int C, int N, const float* __restrict__ bias, int act,
+                 float slope, float* __restrict__ out, int64_t ldo) {
+    using S = SCfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + S::BAR_OFF);
+    uint64_t* full_a = bars;
+    uint64_t* full_b = bars + S::STAGES;
+    uint64_t* empty = bars + 2 * S::STAGES;
+    uint64_t* tmem_full = bars + 3 * S::STAGES;
+    uint64_t* tmem_empty = bars + 3 * S::STAGES + 2;
+    uint32_t* tmem_ptr = (uint32_t*)(bars + 3 * S::STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBl) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < S::STAGES; ++s) {
+            mbar_init(smem_u32(&full_a[s]), PROD_THREADS);
+            mbar_init(smem_u32(&full_b[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tmem_full[a]), 1);
+            mbar_init(smem_u32(&tmem_empty[a]), EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                     "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int64_t m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
+    const int total_kb = (C + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0) {
+        // ---------------- TMA producer for the (pre-split) weights ----------------
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    uint8_t* st = smem + stage * S::STAGE_BYTES;
+                    const uint32_t b_hi = smem_u32(st + 2 * S::A_BYTES), b_lo = b_hi + S::B_BYTES;
+                    const uint32_t bar = smem_u32(&full_b[stage]);
+                    mbar_arrive_expect_tx(bar, 2 * S::B_BYTES);
+                    tma_load_2d(b_hi, &tmBh, bar, kb * BLOCK_K, 0);
+                    tma_load_2d(b_lo, &tmBl, bar, kb * BLOCK_K, 0);
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, false, false);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+                mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    mbar_wait(smem_u32(&full_b[stage]), phase);
+                    mbar_wait(smem_u32(&full_a[stage]), phase);
+                    tcgen05_fence_after();
+                    uint8_t* st = smem + stage * S::STAGE_BYTES;
+                    const uint32_t a_hi = smem_u32(st), a_lo = a_hi + S::A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t dah = make_smem_desc(a_hi + k * 32, 16, 512, 4);
+                        const uint64_t dal = make_smem_desc(a_lo + k * 32, 16, 512, 4);
+                        const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 512, 4);
+                        const uint64_t dbl = make_smem_desc(b_lo + k * 32, 16, 512, 4);
+                        umma_tf32(tmem_d, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                    }
+                    tcgen05_commit(smem_u32(&empty[stage]));
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(smem_u32(&tmem_full[acc]));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ---------------- A producers: gather h_i[src], h_j[dst], multiply, split, store swizzled ----------------
+        const int tid = threadIdx.x - 128;
+        const int c = tid & 3, rbase = tid >> 2;
+        uint32_t stage = 0, phase = 0;
+        for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+            const int64_t m0 = t * BLOCK_M;
+            const float* pa[4];
+            const float* pb[4];
+            bool valid[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t p = m0 + rbase + 32 * i;
+                valid[i] = p < P;
+                const int64_t si = valid[i] ? (src ? src[p] : p) : 0;
+                const int64_t dj = valid[i] ? (dst ? dst[p] : p) : 0;
+                pa[i] = hi_tab + si * C + c * 4;
+                pb[i] = hj_tab + dj * C + c * 4;
+            }
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int k = kb * BLOCK_K;
+                const bool kvalid = k + c * 4 < C;
+                float4 a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (valid[i] && kvalid) {
+                        a[i] = ldg4(pa[i] + k);
+                        b[i] = ldg4(pb[i] + k);
+                    } else {
+                        a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        b[i] = a[i];
+                    }
+                }
+                mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                uint8_t* st = smem + stage * S::STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 h, l;
+                    split_tf32(a[i].x * b[i].x, h.x, l.x);
+                    split_tf32(a[i].y * b[i].y, h.y, l.y);
+                    split_tf32(a[i].z * b[i].z, h.z, l.z);
+                    split_tf32(a[i].w * b[i].w, h.w, l.w);
+                    const uint32_t off = sw64_offset(rbase + 32 * i, c);
+                    *reinterpret_cast<float4*>(st + off) = h;
+                    *reinterpret_cast<float4*>(st + S::A_BYTES + off) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(smem_u32(&full_a[stage]));
+                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 8) {
+        // ---------------- epilogue ----------------
+        const int q = warp & 3, hf = (warp - 8) >> 2;
+        constexpr int COLS_PER_WARP = BLOCK_N / 2;
+        float* stage_buf = (float*)(smem + S::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
+        const bool vec_ok = ((ldo & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
+        uint32_t acc = 0, acc_phase = 0;
+        for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+            const int64_t row0 = t * BLOCK_M + q * 32;
+            mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
+                const int nb = hf * COLS_PER_WARP + cc;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + nb, v);
+                if (nb >= N) continue;
+                float bj = 0.f;
+                if (bias != nullptr && nb + lane < N) bj = __ldg(bias + nb + lane);
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bj, j);
+                act32(x, act, slope);
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    *reinterpret_cast<float4*>(stage_buf + lane * 32 + ((g ^ (lane & 7)) << 2)) =
+                        make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+                __syncwarp();
+                const int rs = lane >> 3, cg = lane & 7;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = 4 * k + rs;
+                    const float4 o = *reinterpret_cast<const float4*>(stage_buf + r * 32 + ((cg ^ (r & 7)) << 2));
+                    const int64_t row = row0 + r;
+                    const int col = nb + 4 * cg;
+                    if (row < P) {
+                        float* cp = out + row * ldo + col;
+                        if (vec_ok && col + 4 <= N) {
+                            *reinterpret_cast<float4*>(cp) = o;
+                        } else {
+                            if (col + 0 < N) cp[0] = o.x;
+                            if (col + 1 < N) cp[1] = o.y;
+                            if (col + 2 < N) cp[2] = o.z;
+                            if (col + 3 < N) cp[3] = o.w;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tcgen05_fence_before();
+            mbar_arrive(smem_u32(&tmem_empty[acc]));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+    }
+}
+
+__global__ void split_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float h, l;
+    split_tf32(w[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+}
+
+template <int BN>
+int launch_fwd(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* hi_tab, const float* hj_tab, const int64_t* src,
+               const int64_t* dst, int64_t P, int C, int N, const float* bias, int act, float slope, float* out, int64_t ldo,
+               cudaStream_t st) {
+    auto kern = score_fwd_kernel<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg<BN>::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int64_t m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
+    const int grid = (int)(m_tiles < MSHA_NUM_SMS ? m_tiles : MSHA_NUM_SMS);
+    kern<<<grid, NUM_THREADS, SCfg<BN>::SMEM_BYTES, st>>>(tbh, tbl, hi_tab, hj_tab, src, dst, P, C, N, bias, act, slope, out,
+                                                         ldo);
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace
+
+// 0 when the fused scorer kernels apply: C % 4 == 0, hidden <= 256, 16-byte aligned tables
+MSHA_API int msha_score_mlp_supported(const float* hi_tab, const float* hj_tab, const float* W0, int64_t C, int64_t Hd) {
+    if (C < 4 || (C & 3) || Hd < 1 || Hd > 256 || C >= ((int64_t)1 << 20)) return -1;
+    if (((uintptr_t)hi_tab & 15) || ((uintptr_t)hj_tab & 15) || ((uintptr_t)W0 & 15)) return -1;
+    return 0;
+}
+
+// workspace: hi/lo copies of W0 [Hd, C] (and of W0^T for the backward)
+MSHA_API size_t msha_score_mlp_workspace_bytes(int64_t C, int64_t Hd) { return (size_t)4 * C * Hd * sizeof(float) + 1024; }
+
+// out[p, :Hd] = act( (hi_tab[src[p]] * hj_tab[dst[p]]) @ W0^T + b0 );  W0 is [Hd, C] (nn.Linear layout); src/dst may be
+// NULL (identity).  Replaces x_i*x_j -> lin -> relu -> sigmoid, LLP.py:105-115.
+MSHA_API int msha_score_mlp_fwd(const float* hi_tab, const float* hj_tab, const int64_t* src, const int64_t* dst, int64_t P,
+                                int64_t C, const float* W0, const float* b0, int64_t Hd, int act, float slope, float* out,
+                                int64_t ldo, void* ws, size_t ws_bytes, void* stream) {
+    MSHA_REQUIRE(msha_score_mlp_supported(hi_tab, hj_tab, W0, C, Hd) == 0, "score_mlp_fwd: unsupported shape/alignment");
+    MSHA_REQUIRE(ws_bytes >= msha_score_mlp_workspace_bytes(C, Hd), "score_mlp_fwd: workspace too small");
+    MSHA_REQUIRE(P >= 0 && ldo >= Hd, "score_mlp_fwd: bad shape");
+    if (P == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* w_hi = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    float* w_lo = w_hi + C * Hd;
+    split_weights_kernel<<<(unsigned)msha_cdiv(C * Hd, 256), 256, 0, st>>>(W0, w_hi, w_lo, C * Hd);
+    MSHA_LAUNCH_OK();
+    const int BN = Hd > 128 ? 256 : (Hd > 64 ? 128 : 64);
+    CUtensorMap tbh, tbl;
+    int rc = tc_make_map(&tbh, w_hi, C, Hd, C, BLOCK_K, BN, false);
+    if (rc) return rc;
+    rc = tc_make_map(&tbl, w_lo, C, Hd, C, BLOCK_K, BN, false);
+    if (rc) return rc;
+    if (BN == 256) return launch_fwd<256>(tbh, tbl, hi_tab, hj_tab, src, dst, P, (int)C, (int)Hd, b0, act, slope, out, ldo, st);
+    if (BN == 128) return launch_fwd<128>(tbh, tbl, hi_tab, hj_tab, src, dst, P, (int)C, (int)Hd, b0, act, slope, out, ldo, st);
+    return launch_fwd<64>(tbh, tbl, hi_tab, hj_tab, src, dst, P, (int)C, (int)Hd, b0, act, slope, out, ldo, st);
+}

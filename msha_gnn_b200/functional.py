@@ -511,6 +511,61 @@ def pair_mul(hi, hj, src=None, dst=None):
     return _PairMul.apply(hi, hj, src, dst)
 
 
+class _ScoreMLP(torch.autograd.Function):
+    """Fused LinkPredictor with one hidden Linear: act((h_i[src] * h_j[dst]) @ W0.T + b0)  (LLP.py:105-115).
+    Forward: one tensor-core kernel (gather, Hadamard, 3xTF32 split in the producer warps; no Z tensor in HBM)."""
+
+    @staticmethod
+    def forward(ctx, hi, hj, src, dst, W0, b0, act):
+        hi, hj, W0 = _c(hi), _c(hj), _c(W0)
+        P = src.numel() if src is not None else hi.shape[0]
+        Hd, C = W0.shape
+        out = torch.empty((P, Hd), dtype=torch.float32, device=hi.device)
+        lib = ops._lib.lib()
+        ws = workspace(lib.msha_score_mlp_workspace_bytes(C, Hd), hi.device)
+        call("msha_score_mlp_fwd", ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C, ptr(W0),
+             ptr(b0) if b0 is not None else None, Hd, act, LRELU_SLOPE, ptr(out), Hd, ws.data_ptr(), ws.numel(), _stream())
+        ctx.act = act
+        ctx.has_bias = b0 is not None
+        ctx.save_for_backward(hi, hj, src, dst, W0, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        hi, hj, src, dst, W0, out = ctx.saved_tensors
+        P, Hd = out.shape
+        C = W0.shape[1]
+        dout = _c(dout)
+        g = torch.empty_like(out)
+        db = torch.empty(Hd, dtype=torch.float32, device=out.device)
+        lib = ops._lib.lib()
+        ws = workspace(lib.msha_act_bwd_colsum_workspace_bytes(Hd), out.device)
+        call("msha_act_bwd_colsum", ptr(dout), ptr(out), ptr(g), P, Hd, ctx.act, LRELU_SLOPE, ptr(db), ws.data_ptr(),
+             ws.numel(), _stream())
+        z = torch.empty((P, C), dtype=torch.float32, device=out.device)          # Z regenerated, never saved
+        call("msha_pair_gather_mul", ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C, ptr(z), _stream())
+        dW = ops.gemm(g, z, transA=True) if ctx.needs_input_grad[4] else None
+        dhi = dhj = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dz = ops.gemm(g, W0, out=z)                                          # reuse the Z buffer
+            dhi = torch.zeros_like(hi)
+            dhj = torch.zeros_like(hj)
+            call("msha_pair_scatter_mul_add", ptr(dz), ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C,
+                 ptr(dhi), ptr(dhj), _stream())
+        return dhi, dhj, None, None, dW, (db if ctx.has_bias else None), None
+
+
+def score_mlp_supported(hi, hj, W0):
+    lib = ops._lib.lib()
+    return (hi.is_cuda and hi.dtype == torch.float32 and hi.is_contiguous() and hj.is_contiguous() and W0.is_contiguous()
+            and hi.shape[1] == W0.shape[1] == hj.shape[1]
+            and lib.msha_score_mlp_supported(hi.data_ptr(), hj.data_ptr(), W0.data_ptr(), W0.shape[1], W0.shape[0]) == 0)
+
+
+def score_mlp(hi, hj, src, dst, W0, b0, act=ACT_SIGMOID_RELU):
+    return _ScoreMLP.apply(hi, hj, src, dst, W0, b0, act)
+
+
 class _PairDot(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hi, hj, src, dst, act):

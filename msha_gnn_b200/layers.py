@@ -364,6 +364,7 @@ class LinkPredictor(nn.Module):
             self.lins.append(nn.Linear(hidden_channels, hidden_channels))
         self.lins.append(nn.Linear(hidden_channels, out_channels))   # allocated, never applied (LLP.py:111)
         self.dropout = dropout
+        self.fused = True        # use the fused tensor-core scorer when the shape allows (False -> unfused kernels)
 
     def reset_parameters(self):
         for lin in self.lins:
@@ -379,8 +380,13 @@ class LinkPredictor(nn.Module):
 
     def _score(self, hi, hj, src, dst):
         if self.predictor == 'mlp':
-            x = Fn.pair_mul(hi, hj, src, dst)                                   # LLP.py:105
             hidden = list(self.lins)[:-1]
+            drop_on = self.training and self.dropout > 0
+            if (self.fused and len(hidden) == 1 and not drop_on
+                    and Fn.score_mlp_supported(hi, hj, hidden[0].weight)):
+                # one tensor-core kernel: gather, Hadamard, Linear, ReLU, sigmoid (LLP.py:105-115)
+                return Fn.score_mlp(hi, hj, src, dst, hidden[0].weight, hidden[0].bias, ACT_SIGMOID_RELU)
+            x = Fn.pair_mul(hi, hj, src, dst)                                   # LLP.py:105
             for k, lin in enumerate(hidden):
                 last = k == len(hidden) - 1
                 drop = self.training and self.dropout > 0

@@ -16,7 +16,7 @@ GEMM_TOL = 2e-5
 SHAPES = [
     # M, N, K
     (128, 256, 32), (128, 64, 256), (4267, 256, 256), (300, 200, 100), (1000, 96, 260), (129, 257, 36), (5000, 32, 64),
-    (64, 128, 4096),
+    (64, 128, 4096), (70000, 256, 256), (40000, 64, 128),      # several tiles per persistent CTA
 ]
 
 
