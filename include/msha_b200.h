@@ -169,6 +169,12 @@ size_t msha_score_mlp_workspace_bytes(int64_t C, int64_t Hd);
 int msha_score_mlp_fwd(const float* hi_tab, const float* hj_tab, const int64_t* src, const int64_t* dst, int64_t P,
                        int64_t C, const float* W0, const float* b0, int64_t Hd, int act, float slope, float* out,
                        int64_t ldo, void* ws, size_t ws_bytes, void* stream);
+/* backward of msha_score_mlp_fwd in two tensor-core kernels: (1) G = dOut*act'(out), bias gradient, dZ = G @ W0 and the
+ * scatter dh_i[src] += dZ*h_j[dst], dh_j[dst] += dZ*h_i[src] in the epilogue; (2) dW0 = G^T @ Z with Z regenerated from
+ * the gathers.  dhi/dhj are accumulated into (caller zeroes them); dW0, db0 are overwritten; G is [P, Hd] scratch. */
+int msha_score_mlp_bwd(const float* dout, const float* out, const float* hi_tab, const float* hj_tab, const int64_t* src,
+                       const int64_t* dst, int64_t P, int64_t C, const float* W0, int64_t Hd, int act, float slope,
+                       float* G, float* dhi, float* dhj, float* dW0, float* db0, void* ws, size_t ws_bytes, void* stream);
 /* builder-defined sampler (the reference's --ns_rate flags are dead code, LLP.py:26-29) */
 int msha_negative_sample(uint64_t seed, int64_t P, int64_t n_src, int64_t n_dst, int64_t* src, int64_t* dst,
                          void* stream);

@@ -295,6 +295,444 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused backward, part 1:  G = dOut * act'(out)  (+ bias gradient),  dZ = G @ W0,  scatter into dh_i / dh_j
+//   A operand: G tile produced by the producer warps from dOut/out (K-major, K = hidden)
+//   B operand: W0^T [C, Hd] pre-split hi/lo by TMA (K-major)
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                    const float* __restrict__ dout, const float* __restrict__ outp, int act, float slope,
+                    float* __restrict__ G, float* __restrict__ db, const float* __restrict__ hi_tab,
+                    const float* __restrict__ hj_tab, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                    int64_t P, int K /*hidden*/, int N /*C*/, float* __restrict__ dhi, float* __restrict__ dhj) {
+    using S = SCfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + S::BAR_OFF);
+    uint64_t* full_a = bars;
+    uint64_t* full_b = bars + S::STAGES;
+    uint64_t* empty = bars + 2 * S::STAGES;
+    uint64_t* tmem_full = bars + 3 * S::STAGES;
+    uint64_t* tmem_empty = bars + 3 * S::STAGES + 2;
+    uint32_t* tmem_ptr = (uint32_t*)(bars + 3 * S::STAGES + 4);
+    __shared__ float db_sm[256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x < 256) db_sm[threadIdx.x] = 0.f;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBl) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < S::STAGES; ++s) {
+            mbar_init(smem_u32(&full_a[s]), PROD_THREADS);
+            mbar_init(smem_u32(&full_b[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tmem_full[a]), 1);
+            mbar_init(smem_u32(&tmem_empty[a]), EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                     "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int64_t m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
+    const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    uint8_t* st = smem + stage * S::STAGE_BYTES;
+                    const uint32_t b_hi = smem_u32(st + 2 * S::A_BYTES), b_lo = b_hi + S::B_BYTES;
+                    const uint32_t bar = smem_u32(&full_b[stage]);
+                    mbar_arrive_expect_tx(bar, 2 * S::B_BYTES);
+                    tma_load_2d(b_hi, &tmBh, bar, kb * BLOCK_K, 0);
+                    tma_load_2d(b_lo, &tmBl, bar, kb * BLOCK_K, 0);
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, false, false);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+                mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    mbar_wait(smem_u32(&full_b[stage]), phase);
+                    mbar_wait(smem_u32(&full_a[stage]), phase);
+                    tcgen05_fence_after();
+                    uint8_t* st = smem + stage * S::STAGE_BYTES;
+                    const uint32_t a_hi = smem_u32(st), a_lo = a_hi + S::A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t dah = make_smem_desc(a_hi + k * 32, 16, 512, 4);
+                        const uint64_t dal = make_smem_desc(a_lo + k * 32, 16, 512, 4);
+                        const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 512, 4);
+                        const uint64_t dbl = make_smem_desc(b_lo + k * 32, 16, 512, 4);
+                        umma_tf32(tmem_d, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                    }
+                    tcgen05_commit(smem_u32(&empty[stage]));
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(smem_u32(&tmem_full[acc]));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ---------------- producers: G = dOut * act'(out) -> global G, bias-gradient partials, swizzled hi/lo tiles ----
+        const int tid = threadIdx.x - 128;
+        const int c = tid & 3, rbase = tid >> 2;
+        uint32_t stage = 0, phase = 0;
+        for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+            const int64_t m0 = t * BLOCK_M;
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int k = kb * BLOCK_K + c * 4;
+                const bool kvalid = k < K;
+                float4 g[4];
+                float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t p = m0 + rbase + 32 * i;
+                    if (p < P && kvalid) {
+                        const float4 d = ldg4(dout + p * K + k);
+                        const float4 y = ldg4(outp + p * K + k);
+                        g[i].x = d.x * act_grad_out(y.x, act, slope);
+                        g[i].y = d.y * act_grad_out(y.y, act, slope);
+                        g[i].z = d.z * act_grad_out(y.z, act, slope);
+                        g[i].w = d.w * act_grad_out(y.w, act, slope);
+                        *reinterpret_cast<float4*>(G + p * K + k) = g[i];
+                        csum.x += g[i].x; csum.y += g[i].y; csum.z += g[i].z; csum.w += g[i].w;
+                    } else {
+                        g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                // bias gradient: reduce over the lanes that share the column chunk c (lane & 3)
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
+                    csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+                    csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
+                    csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+                }
+                if (lane < 4 && kvalid) {
+                    atomicAdd(&db_sm[k + 0], csum.x);
+                    atomicAdd(&db_sm[k + 1], csum.y);
+                    atomicAdd(&db_sm[k + 2], csum.z);
+                    atomicAdd(&db_sm[k + 3], csum.w);
+                }
+                mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                uint8_t* st = smem + stage * S::STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 h, l;
+                    split_tf32(g[i].x, h.x, l.x);
+                    split_tf32(g[i].y, h.y, l.y);
+                    split_tf32(g[i].z, h.z, l.z);
+                    split_tf32(g[i].w, h.w, l.w);
+                    const uint32_t off = sw64_offset(rbase + 32 * i, c);
+                    *reinterpret_cast<float4*>(st + off) = h;
+                    *reinterpret_cast<float4*>(st + S::A_BYTES + off) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(smem_u32(&full_a[stage]));
+                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        // flush the per-CTA bias-gradient partial sums
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (db != nullptr)
+            for (int k = tid; k < K; k += PROD_THREADS) atomicAdd(db + k, db_sm[k]);
+    } else if (warp >= 8) {
+        // ---------------- epilogue: dZ tile -> dh_i[src] += dZ * h_j[dst],  dh_j[dst] += dZ * h_i[src] ----------------
+        const int q = warp & 3, hf = (warp - 8) >> 2;
+        constexpr int COLS_PER_WARP = BLOCK_N / 2;
+        float* stage_buf = (float*)(smem + S::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
+        uint32_t acc = 0, acc_phase = 0;
+        for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+            const int64_t row0 = t * BLOCK_M + q * 32;
+            const int64_t prow = row0 + lane;
+            int s_l = 0, d_l = 0;
+            if (prow < P) {
+                s_l = (int)(src ? src[prow] : prow);
+                d_l = (int)(dst ? dst[prow] : prow);
+            }
+            mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
+                const int nb = hf * COLS_PER_WARP + cc;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + nb, v);
+                if (nb >= N) continue;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    *reinterpret_cast<float4*>(stage_buf + lane * 32 + ((g ^ (lane & 7)) << 2)) =
+                        make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                    __uint_as_float(v[4 * g + 3]));
+                __syncwarp();
+                const int rs = lane >> 3, cg = lane & 7;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = 4 * k + rs;
+                    const float4 dz = *reinterpret_cast<const float4*>(stage_buf + r * 32 + ((cg ^ (r & 7)) << 2));
+                    const int si = __shfl_sync(0xffffffffu, s_l, r);
+                    const int dj = __shfl_sync(0xffffffffu, d_l, r);
+                    const int col = nb + 4 * cg;
+                    if (row0 + r < P && col < N) {          // N % 4 == 0
+                        const float4 xj = ldg4(hj_tab + (int64_t)dj * N + col);
+                        const float4 xi = ldg4(hi_tab + (int64_t)si * N + col);
+                        atomicAdd(reinterpret_cast<float4*>(dhi + (int64_t)si * N + col),
+                                  make_float4(dz.x * xj.x, dz.y * xj.y, dz.z * xj.z, dz.w * xj.w));
+                        atomicAdd(reinterpret_cast<float4*>(dhj + (int64_t)dj * N + col),
+                                  make_float4(dz.x * xi.x, dz.y * xi.y, dz.z * xi.z, dz.w * xi.w));
+                    }
+                }
+                __syncwarp();
+            }
+            tcgen05_fence_before();
+            mbar_arrive(smem_u32(&tmem_empty[acc]));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused backward, part 2:  dW0[Hd, C] = G^T @ Z,  Z[p,:] = h_i[src[p]] * h_j[dst[p]] regenerated by gather warps.
+//   A operand: G [K = pairs, M = Hd]  MN-major, TMA (128B-atom-32B swizzle) + converter warps (hi / lo)
+//   B operand: Z [K = pairs, N = C]   MN-major, written hi / lo by the gather warps in the same swizzle
+//   each CTA owns a contiguous range of pairs and keeps the whole 256 x 256 accumulator in TMEM (512 columns);
+//   partial results are added to dW0 with atomics at the end.
+// ------------------------------------------------------------------------------------------------
+struct WCfg {
+    static constexpr int MN = 256;                                  // padded Hd and C
+    static constexpr int TILE_BYTES = MN * BLOCK_K * 4;             // 16 KB per hi / lo tile
+    static constexpr int STAGE_BYTES = 4 * TILE_BYTES;              // A_hi, A_lo, B_hi, B_lo
+    static constexpr int STAGES = 3;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 512;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __restrict__ hi_tab,
+                    const float* __restrict__ hj_tab, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                    int64_t P, int Hd, int C, float* __restrict__ dW) {
+    using W = WCfg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + W::BAR_OFF);
+    uint64_t* full_raw = bars;
+    uint64_t* full_cvt = bars + W::STAGES;
+    uint64_t* full_b = bars + 2 * W::STAGES;
+    uint64_t* empty = bars + 3 * W::STAGES;
+    uint64_t* acc_full = bars + 4 * W::STAGES;
+    uint32_t* tmem_ptr = (uint32_t*)(bars + 4 * W::STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmG) : "memory");
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < W::STAGES; ++s) {
+            mbar_init(smem_u32(&full_raw[s]), 1);
+            mbar_init(smem_u32(&full_cvt[s]), PROD_THREADS);
+            mbar_init(smem_u32(&full_b[s]), PROD_THREADS);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        mbar_init(smem_u32(acc_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // contiguous range of 16-pair chunks owned by this CTA
+    const int64_t n_chunks = (P + BLOCK_K - 1) / BLOCK_K;
+    const int64_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const int64_t c0 = (int64_t)blockIdx.x * per;
+    const int64_t c1 = c0 + per < n_chunks ? c0 + per : n_chunks;
+    const int m_tiles = (Hd + 127) / 128;
+    const int a_chunks = m_tiles * 4;                     // 32-wide MN chunks of G actually loaded
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t ch = c0; ch < c1; ++ch) {
+                mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                const uint32_t a_dst = smem_u32(smem + stage * W::STAGE_BYTES);
+                const uint32_t bar = smem_u32(&full_raw[stage]);
+                mbar_arrive_expect_tx(bar, (uint32_t)a_chunks * 2048u);
+                for (int i = 0; i < a_chunks; ++i) tma_load_2d(a_dst + i * 2048, &tmG, bar, 32 * i, (int)(ch * BLOCK_K));
+                if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(128, 256, true, true);
+            uint32_t stage = 0, phase = 0;
+            for (int64_t ch = c0; ch < c1; ++ch) {
+                mbar_wait(smem_u32(&full_cvt[stage]), phase);
+                mbar_wait(smem_u32(&full_b[stage]), phase);
+                tcgen05_fence_after();
+                uint8_t* st = smem + stage * W::STAGE_BYTES;
+                const uint32_t a_hi = smem_u32(st), a_lo = a_hi + W::TILE_BYTES;
+                const uint32_t b_hi = a_hi + 2 * W::TILE_BYTES, b_lo = b_hi + W::TILE_BYTES;
+                for (int mt = 0; mt < m_tiles; ++mt) {
+                    const uint32_t tmem_d = tmem_base + mt * 256;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t dah = make_smem_desc(a_hi + mt * 8192 + k * 1024, 2048, 512, 1);
+                        const uint64_t dal = make_smem_desc(a_lo + mt * 8192 + k * 1024, 2048, 512, 1);
+                        const uint64_t dbh = make_smem_desc(b_hi + k * 1024, 2048, 512, 1);
+                        const uint64_t dbl = make_smem_desc(b_lo + k * 1024, 2048, 512, 1);
+                        umma_tf32(tmem_d, dal, dbh, idesc, (ch > c0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                    }
+                }
+                tcgen05_commit(smem_u32(&empty[stage]));
+                if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
+            }
+            tcgen05_commit(smem_u32(acc_full));
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ---------------- converters for the TMA-loaded G tile ----------------
+        const int tid = threadIdx.x - 128;
+        uint32_t stage = 0, phase = 0;
+        for (int64_t ch = c0; ch < c1; ++ch) {
+            mbar_wait(smem_u32(&full_raw[stage]), phase);
+            uint8_t* st = smem + stage * W::STAGE_BYTES;
+            uint4* a_hi = (uint4*)st;
+            uint4* a_lo = (uint4*)(st + W::TILE_BYTES);
+            const int n16 = a_chunks * 2048 / 16;
+#pragma unroll 4
+            for (int c = tid; c < n16; c += PROD_THREADS) {
+                uint4 x = a_hi[c], h, l;
+                h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
+                l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+                l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+                l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+                l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+                a_hi[c] = h; a_lo[c] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(smem_u32(&full_cvt[stage]));
+            if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // ---------------- Z producers: 16 pairs x C channels per stage, MN-major 128B-atom-32B swizzle ----------------
+        const int tid = threadIdx.x - 256;
+        const int kk = tid >> 3, c16 = tid & 7;
+        const int n_blocks = (C + 31) / 32;
+        uint32_t stage = 0, phase = 0;
+        for (int64_t ch = c0; ch < c1; ++ch) {
+            const int64_t p = ch * BLOCK_K + kk;
+            const bool pvalid = p < P;
+            const int64_t si = pvalid ? (src ? src[p] : p) : 0;
+            const int64_t dj = pvalid ? (dst ? dst[p] : p) : 0;
+            const float* pa = hi_tab + si * C + c16 * 4;
+            const float* pb = hj_tab + dj * C + c16 * 4;
+            float4 z[8];
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                if (pvalid && nb < n_blocks && nb * 32 + c16 * 4 < C) {
+                    const float4 a = ldg4(pa + nb * 32), b = ldg4(pb + nb * 32);
+                    z[nb] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+                } else {
+                    z[nb] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+            uint8_t* st = smem + stage * W::STAGE_BYTES + 2 * W::TILE_BYTES;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                float4 h, l;
+                split_tf32(z[nb].x, h.x, l.x);
+                split_tf32(z[nb].y, h.y, l.y);
+                split_tf32(z[nb].z, h.z, l.z);
+                split_tf32(z[nb].w, h.w, l.w);
+                const uint32_t off = nb * 2048 + sw128b32_offset(kk, c16);
+                *reinterpret_cast<float4*>(st + off) = h;
+                *reinterpret_cast<float4*>(st + W::TILE_BYTES + off) = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(smem_u32(&full_b[stage]));
+            if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+    // ---------------- epilogue (warps 8-15): TMEM -> atomicAdd into dW0 ----------------
+    if (warp >= 8 && c1 > c0) {
+        const int q = warp & 3, hf = (warp - 8) >> 2;
+        mbar_wait(smem_u32(acc_full), 0);
+        tcgen05_fence_after();
+        for (int mt = 0; mt < m_tiles; ++mt) {
+            const int row = mt * 128 + q * 32 + lane;
+#pragma unroll 1
+            for (int cc = 0; cc < 128; cc += 32) {
+                const int nb = hf * 128 + cc;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mt * 256 + nb, v);
+                if (row < Hd && nb < C) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < C) atomicAdd(dW + (int64_t)row * C + nb + j, __uint_as_float(v[j]));
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+__global__ void split_weights_t_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int Hd,
+                                       int C) {
+    // w [Hd, C] -> hi/lo [C, Hd] (transposed)
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Hd * C) return;
+    const int c = (int)(i / Hd), h = (int)(i % Hd);
+    float hh, ll;
+    split_tf32(w[(int64_t)h * C + c], hh, ll);
+    hi[i] = hh;
+    lo[i] = ll;
+}
+
 __global__ void split_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -357,4 +795,70 @@ MSHA_API int msha_score_mlp_fwd(const float* hi_tab, const float* hj_tab, const 
     if (BN == 256) return launch_fwd<256>(tbh, tbl, hi_tab, hj_tab, src, dst, P, (int)C, (int)Hd, b0, act, slope, out, ldo, st);
     if (BN == 128) return launch_fwd<128>(tbh, tbl, hi_tab, hj_tab, src, dst, P, (int)C, (int)Hd, b0, act, slope, out, ldo, st);
     return launch_fwd<64>(tbh, tbl, hi_tab, hj_tab, src, dst, P, (int)C, (int)Hd, b0, act, slope, out, ldo, st);
+}
+
+namespace {
+template <int BN>
+int launch_dz(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* dout, const float* outp, int act, float slope,
+              float* G, float* db, const float* hi_tab, const float* hj_tab, const int64_t* src, const int64_t* dst, int64_t P,
+              int Hd, int C, float* dhi, float* dhj, cudaStream_t st) {
+    auto kern = score_bwd_dz_kernel<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg<BN>::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int64_t m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
+    const int grid = (int)(m_tiles < MSHA_NUM_SMS ? m_tiles : MSHA_NUM_SMS);
+    kern<<<grid, NUM_THREADS, SCfg<BN>::SMEM_BYTES, st>>>(tbh, tbl, dout, outp, act, slope, G, db, hi_tab, hj_tab, src, dst, P, Hd,
+                                                         C, dhi, dhj);
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+}  // namespace
+
+// Backward of msha_score_mlp_fwd.  dout/out: [P, Hd] contiguous.  G: [P, Hd] scratch (receives dOut*act'(out)).
+// dhi/dhj [n, C] must hold the running gradients (atomically accumulated); dW0 [Hd, C] and db0 [Hd] are overwritten.
+// Needs Hd % 4 == 0 in addition to msha_score_mlp_supported.
+MSHA_API int msha_score_mlp_bwd(const float* dout, const float* out, const float* hi_tab, const float* hj_tab,
+                                const int64_t* src, const int64_t* dst, int64_t P, int64_t C, const float* W0, int64_t Hd,
+                                int act, float slope, float* G, float* dhi, float* dhj, float* dW0, float* db0, void* ws,
+                                size_t ws_bytes, void* stream) {
+    MSHA_REQUIRE(msha_score_mlp_supported(hi_tab, hj_tab, W0, C, Hd) == 0 && (Hd & 3) == 0 && C <= 256,
+                 "score_mlp_bwd: unsupported shape/alignment (need C <= 256, Hd <= 256, both multiples of 4)");
+    MSHA_REQUIRE(ws_bytes >= msha_score_mlp_workspace_bytes(C, Hd), "score_mlp_bwd: workspace too small");
+    MSHA_REQUIRE(((uintptr_t)dout & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)G & 15) == 0,
+                 "score_mlp_bwd: dout/out/G must be 16-byte aligned");
+    if (P == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* wt_hi = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255) + 2 * C * Hd;
+    float* wt_lo = wt_hi + C * Hd;
+    split_weights_t_kernel<<<(unsigned)msha_cdiv(C * Hd, 256), 256, 0, st>>>(W0, wt_hi, wt_lo, (int)Hd, (int)C);
+    MSHA_LAUNCH_OK();
+    MSHA_CUDA(cudaMemsetAsync(db0, 0, (size_t)Hd * sizeof(float), st));
+    MSHA_CUDA(cudaMemsetAsync(dW0, 0, (size_t)Hd * C * sizeof(float), st));
+    // ---- part 1: G, db0, dZ = G @ W0, scatter
+    const int BN = C > 128 ? 256 : (C > 64 ? 128 : 64);
+    CUtensorMap tbh, tbl, tg;
+    int rc = tc_make_map(&tbh, wt_hi, Hd, C, Hd, BLOCK_K, BN, false);     // B operand: [N = C rows, K = Hd] K-major
+    if (rc) return rc;
+    rc = tc_make_map(&tbl, wt_lo, Hd, C, Hd, BLOCK_K, BN, false);
+    if (rc) return rc;
+    if (BN == 256) rc = launch_dz<256>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, st);
+    else if (BN == 128) rc = launch_dz<128>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, st);
+    else rc = launch_dz<64>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, st);
+    if (rc) return rc;
+    // ---- part 2: dW0 = G^T @ Z
+    rc = tc_make_map(&tg, G, Hd, P, Hd, 32, BLOCK_K, true);               // A operand: G stored [K = P, M = Hd] MN-major
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MSHA_CUDA(cudaFuncSetAttribute(score_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int64_t n_chunks = (P + BLOCK_K - 1) / BLOCK_K;
+    const int grid = (int)(n_chunks < MSHA_NUM_SMS ? n_chunks : MSHA_NUM_SMS);
+    score_bwd_dw_kernel<<<grid, NUM_THREADS, WCfg::SMEM_BYTES, st>>>(tg, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dW0);
+    MSHA_LAUNCH_OK();
+    return 0;
 }

@@ -537,8 +537,19 @@ class _ScoreMLP(torch.autograd.Function):
         C = W0.shape[1]
         dout = _c(dout)
         g = torch.empty_like(out)
-        db = torch.empty(Hd, dtype=torch.float32, device=out.device)
         lib = ops._lib.lib()
+        if FUSED_SCORE_BWD and Hd % 4 == 0 and C <= 256:
+            # two tensor-core kernels: (G, db, dZ, scatter) and (dW0 with Z regenerated from the gathers)
+            dhi = torch.zeros_like(hi)
+            dhj = torch.zeros_like(hj)
+            dW = torch.empty_like(W0)
+            db = torch.empty(Hd, dtype=torch.float32, device=out.device)
+            ws = workspace(lib.msha_score_mlp_workspace_bytes(C, Hd), out.device)
+            call("msha_score_mlp_bwd", ptr(dout), ptr(out), ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P,
+                 C, ptr(W0), Hd, ctx.act, LRELU_SLOPE, ptr(g), ptr(dhi), ptr(dhj), ptr(dW), ptr(db), ws.data_ptr(), ws.numel(),
+                 _stream())
+            return dhi, dhj, None, None, dW, (db if ctx.has_bias else None), None
+        db = torch.empty(Hd, dtype=torch.float32, device=out.device)
         ws = workspace(lib.msha_act_bwd_colsum_workspace_bytes(Hd), out.device)
         call("msha_act_bwd_colsum", ptr(dout), ptr(out), ptr(g), P, Hd, ctx.act, LRELU_SLOPE, ptr(db), ws.data_ptr(),
              ws.numel(), _stream())
@@ -553,6 +564,9 @@ class _ScoreMLP(torch.autograd.Function):
             call("msha_pair_scatter_mul_add", ptr(dz), ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C,
                  ptr(dhi), ptr(dhj), _stream())
         return dhi, dhj, None, None, dW, (db if ctx.has_bias else None), None
+
+
+FUSED_SCORE_BWD = True     # False: unfused backward (act', gather, two GEMMs, scatter) -- kept for validation
 
 
 def score_mlp_supported(hi, hj, W0):

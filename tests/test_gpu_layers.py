@@ -330,8 +330,11 @@ def test_nll_readout_kernel_matches_torch():
         assert torch.equal(logp.grad, ref_in.grad)
 
 
-@pytest.mark.parametrize("P,C,Hd,Nn", [(1000, 256, 256, 300), (4097, 64, 128, 50), (129, 32, 40, 17), (70000, 256, 256, 4267)])
-def test_fused_scorer_vs_oracle(P, C, Hd, Nn):
+@pytest.mark.parametrize("fused_bwd", [True, False])
+@pytest.mark.parametrize("P,C,Hd,Nn", [(1000, 256, 256, 300), (4097, 64, 128, 50), (129, 32, 40, 17), (70000, 256, 256, 4267),
+                                      (5000, 128, 200, 64), (33, 8, 4, 5)])
+def test_fused_scorer_vs_oracle(P, C, Hd, Nn, fused_bwd, monkeypatch):
+    monkeypatch.setattr(Fn, "FUSED_SCORE_BWD", fused_bwd)
     g = torch.Generator().manual_seed(P)
     lp = mg.LinkPredictor("mlp", C, Hd, 1, 2, 0.0).to(DEV)
     h = (torch.randn(Nn, C, generator=g) * 0.5).to(DEV).requires_grad_(True)
@@ -344,16 +347,26 @@ def test_fused_scorer_vs_oracle(P, C, Hd, Nn):
     W = [l.weight.detach().cpu().double().requires_grad_(True) for l in lp.lins]
     b = [l.bias.detach().cpu().double().requires_grad_(True) for l in lp.lins]
     ref = O.link_predictor(hd[src.cpu()], hd[dst.cpu()], W, b)
-    (ref * G.cpu().double()).sum().backward()
     assert rel_err(_np(out), ref.detach().numpy()) < TOL
-    # relu'(x) is discontinuous at 0: among P*Hd pre-activations a handful land within fp32 round-off (~2e-7) of 0,
-    # where no fp32 implementation (the reference included) can agree with the fp64 oracle on the active set and one
-    # flipped element moves a gradient entry by ~1 % of max.  Large cases are therefore checked in the L2 norm.
-    def err(a, b_):
-        a, b_ = np.asarray(a, np.float64), np.asarray(b_, np.float64)
-        if P * Hd > 2_000_000:
-            return float(np.linalg.norm(a - b_) / np.linalg.norm(b_))
-        return rel_err(a, b_)
-    assert err(_np(h.grad), hd.grad.numpy()) < TOL
-    assert err(_np(lp.lins[0].weight.grad), W[0].grad.numpy()) < TOL
-    assert err(_np(lp.lins[0].bias.grad), b[0].grad.numpy()) < TOL
+    # relu'(x) is discontinuous at 0: among P*Hd pre-activations a handful land within fp32 round-off of 0, where the
+    # active set is implementation-defined in fp32 (the reference included).  The gradient oracle therefore uses the
+    # kernel's active set for those elements -- after checking that it differs from the exact one only at |pre| < 1e-6.
+    pre = (hd[src.cpu()] * hd[dst.cpu()]) @ W[0].t() + b[0]
+    mask = torch.from_numpy(_np(out) > 0.5)
+    flips = mask != (pre.detach() > 0)
+    assert int(flips.sum()) <= 64 and (not flips.any() or float(pre.detach()[flips].abs().max()) < 1e-6)
+
+    class _Relu(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            return x.clamp_min(0)
+
+        @staticmethod
+        def backward(ctx, g_):
+            return g_ * mask
+
+    ref2 = torch.sigmoid(_Relu.apply(pre))
+    (ref2 * G.cpu().double()).sum().backward()
+    assert rel_err(_np(h.grad), hd.grad.numpy()) < TOL
+    assert rel_err(_np(lp.lins[0].weight.grad), W[0].grad.numpy()) < TOL
+    assert rel_err(_np(lp.lins[0].bias.grad), b[0].grad.numpy()) < TOL
