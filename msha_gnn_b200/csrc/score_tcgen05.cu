@@ -8,10 +8,12 @@
 //                 epilogue scatters  dh_i[src] += dZ*h_j[dst],  dh_j[dst] += dZ*h_i[src]  with 128-bit atomics.
 //   score_bwd_dw  dW0 = G^T @ Z with Z regenerated from the gathers (MN-major operands, whole K range per CTA in TMEM).
 //
-// Same warp-specialised skeleton as gemm_tcgen05.cu (TMA thread, MMA thread, TMEM allocator, 4 producer warps,
-// 8 epilogue warps; mbarrier rings; double-buffered TMEM accumulators).
+// Same warp-specialised skeleton as gemm_tcgen05.cu (TMA thread, MMA thread, TMEM allocator; mbarrier rings;
+// double-buffered TMEM accumulators) with 8 producer warps (the gathers / streaming reads are software-pipelined one
+// k-block ahead in registers) and 4 epilogue warps.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -19,8 +21,9 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 16;
 constexpr int UMMA_K = 8;
 constexpr int NUM_THREADS = 512;
-constexpr int PROD_THREADS = 128;
-constexpr int EPI_WARPS = 8;
+constexpr int PROD_THREADS = 256;             // warps 4-11 of the forward / dZ kernels (gather + split producers)
+constexpr int CVT_THREADS = 128;              // warps 4-7 of the dW kernel (TMA tile converters)
+constexpr int EPI_WARPS = 4;                  // warps 12-15: one per TMEM lane quarter
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;
 
@@ -180,62 +183,70 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 12) {
         // ---------------- A producers: gather h_i[src], h_j[dst], multiply, split, store swizzled ----------------
         const int tid = threadIdx.x - 128;
-        const int c = tid & 3, rbase = tid >> 2;
+        const int c = tid & 3, rbase = tid >> 2;                 // 16-byte chunk c of rows rbase, rbase + 64
         uint32_t stage = 0, phase = 0;
         for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
             const int64_t m0 = t * BLOCK_M;
-            const float* pa[4];
-            const float* pb[4];
-            bool valid[4];
+            const float* pa[2];
+            const float* pb[2];
+            bool valid[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t p = m0 + rbase + 32 * i;
+            for (int i = 0; i < 2; ++i) {
+                const int64_t p = m0 + rbase + 64 * i;
                 valid[i] = p < P;
                 const int64_t si = valid[i] ? (src ? src[p] : p) : 0;
                 const int64_t dj = valid[i] ? (dst ? dst[p] : p) : 0;
                 pa[i] = hi_tab + si * C + c * 4;
                 pb[i] = hj_tab + dj * C + c * 4;
             }
-            for (int kb = 0; kb < total_kb; ++kb) {
+            // gathers are software-pipelined one k-block ahead (L2 latency ~ one stage of MMA work)
+            float4 a[2], b[2], an[2], bn[2];
+            auto load = [&](int kb, float4 (&x)[2], float4 (&y)[2]) {
                 const int k = kb * BLOCK_K;
-                const bool kvalid = k + c * 4 < C;
-                float4 a[4], b[4];
+                const bool kvalid = (kb < total_kb) && (k + c * 4 < C);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 2; ++i) {
                     if (valid[i] && kvalid) {
-                        a[i] = ldg4(pa[i] + k);
-                        b[i] = ldg4(pb[i] + k);
+                        x[i] = ldg4(pa[i] + k);
+                        y[i] = ldg4(pb[i] + k);
                     } else {
-                        a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        b[i] = a[i];
+                        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        y[i] = x[i];
                     }
                 }
+            };
+            load(0, a, b);
+            for (int kb = 0; kb < total_kb; ++kb) {
+                load(kb + 1, an, bn);
                 mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                 uint8_t* st = smem + stage * S::STAGE_BYTES;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 2; ++i) {
                     float4 h, l;
                     split_tf32(a[i].x * b[i].x, h.x, l.x);
                     split_tf32(a[i].y * b[i].y, h.y, l.y);
                     split_tf32(a[i].z * b[i].z, h.z, l.z);
                     split_tf32(a[i].w * b[i].w, h.w, l.w);
-                    const uint32_t off = sw64_offset(rbase + 32 * i, c);
+                    const uint32_t off = sw64_offset(rbase + 64 * i, c);
                     *reinterpret_cast<float4*>(st + off) = h;
                     *reinterpret_cast<float4*>(st + S::A_BYTES + off) = l;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(smem_u32(&full_a[stage]));
                 if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) { a[i] = an[i]; b[i] = bn[i]; }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 12) {
         // ---------------- epilogue ----------------
-        const int q = warp & 3, hf = (warp - 8) >> 2;
-        constexpr int COLS_PER_WARP = BLOCK_N / 2;
-        float* stage_buf = (float*)(smem + S::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
+        const int q = warp & 3;
+        constexpr int hf = 0;
+        constexpr int COLS_PER_WARP = BLOCK_N;
+        float* stage_buf = (float*)(smem + S::EPI_OFF + (warp - 12) * EPI_STAGE_BYTES);
         const bool vec_ok = ((ldo & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
         uint32_t acc = 0, acc_phase = 0;
         for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
@@ -399,75 +410,97 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 12) {
         // ---------------- producers: G = dOut * act'(out) -> global G, bias-gradient partials, swizzled hi/lo tiles ----
         const int tid = threadIdx.x - 128;
-        const int c = tid & 3, rbase = tid >> 2;
+        const int c = tid & 3, rbase = tid >> 2;                 // 16-byte chunk c of rows rbase, rbase + 64
         uint32_t stage = 0, phase = 0;
+        float4 csum[16];                                         // bias-gradient partials per k-block (K <= 256)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) csum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
             const int64_t m0 = t * BLOCK_M;
-            for (int kb = 0; kb < total_kb; ++kb) {
+            const int64_t p0 = m0 + rbase, p1 = p0 + 64;
+            const bool v0 = p0 < P, v1 = p1 < P;
+            float4 d[2], y[2], dn[2], yn[2];
+            auto load = [&](int kb, float4 (&dd)[2], float4 (&yy)[2]) {
                 const int k = kb * BLOCK_K + c * 4;
-                const bool kvalid = k < K;
-                float4 g[4];
-                float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool kvalid = (kb < total_kb) && (k < K);
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                dd[0] = (v0 && kvalid) ? ldg4(dout + p0 * K + k) : z4;
+                yy[0] = (v0 && kvalid) ? ldg4(outp + p0 * K + k) : z4;
+                dd[1] = (v1 && kvalid) ? ldg4(dout + p1 * K + k) : z4;
+                yy[1] = (v1 && kvalid) ? ldg4(outp + p1 * K + k) : z4;
+            };
+            load(0, d, y);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t p = m0 + rbase + 32 * i;
-                    if (p < P && kvalid) {
-                        const float4 d = ldg4(dout + p * K + k);
-                        const float4 y = ldg4(outp + p * K + k);
-                        g[i].x = d.x * act_grad_out(y.x, act, slope);
-                        g[i].y = d.y * act_grad_out(y.y, act, slope);
-                        g[i].z = d.z * act_grad_out(y.z, act, slope);
-                        g[i].w = d.w * act_grad_out(y.w, act, slope);
-                        *reinterpret_cast<float4*>(G + p * K + k) = g[i];
-                        csum.x += g[i].x; csum.y += g[i].y; csum.z += g[i].z; csum.w += g[i].w;
-                    } else {
-                        g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int kb = 0; kb < 16; ++kb) {
+                if (kb < total_kb) {
+                    load(kb + 1, dn, yn);
+                    const int k = kb * BLOCK_K + c * 4;
+                    const bool kvalid = k < K;
+                    float4 g[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        g[i].x = d[i].x * act_grad_out(y[i].x, act, slope);
+                        g[i].y = d[i].y * act_grad_out(y[i].y, act, slope);
+                        g[i].z = d[i].z * act_grad_out(y[i].z, act, slope);
+                        g[i].w = d[i].w * act_grad_out(y[i].w, act, slope);
+                        csum[kb].x += g[i].x; csum[kb].y += g[i].y; csum[kb].z += g[i].z; csum[kb].w += g[i].w;
                     }
-                }
-                // bias gradient: reduce over the lanes that share the column chunk c (lane & 3)
+                    if (v0 && kvalid) *reinterpret_cast<float4*>(G + p0 * K + k) = g[0];
+                    if (v1 && kvalid) *reinterpret_cast<float4*>(G + p1 * K + k) = g[1];
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    uint8_t* st = smem + stage * S::STAGE_BYTES;
 #pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
-                    csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
-                    csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
-                    csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
-                }
-                if (lane < 4 && kvalid) {
-                    atomicAdd(&db_sm[k + 0], csum.x);
-                    atomicAdd(&db_sm[k + 1], csum.y);
-                    atomicAdd(&db_sm[k + 2], csum.z);
-                    atomicAdd(&db_sm[k + 3], csum.w);
-                }
-                mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
-                uint8_t* st = smem + stage * S::STAGE_BYTES;
+                    for (int i = 0; i < 2; ++i) {
+                        float4 h, l;
+                        split_tf32(g[i].x, h.x, l.x);
+                        split_tf32(g[i].y, h.y, l.y);
+                        split_tf32(g[i].z, h.z, l.z);
+                        split_tf32(g[i].w, h.w, l.w);
+                        const uint32_t off = sw64_offset(rbase + 64 * i, c);
+                        *reinterpret_cast<float4*>(st + off) = h;
+                        *reinterpret_cast<float4*>(st + S::A_BYTES + off) = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(smem_u32(&full_a[stage]));
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 h, l;
-                    split_tf32(g[i].x, h.x, l.x);
-                    split_tf32(g[i].y, h.y, l.y);
-                    split_tf32(g[i].z, h.z, l.z);
-                    split_tf32(g[i].w, h.w, l.w);
-                    const uint32_t off = sw64_offset(rbase + 32 * i, c);
-                    *reinterpret_cast<float4*>(st + off) = h;
-                    *reinterpret_cast<float4*>(st + S::A_BYTES + off) = l;
+                    for (int i = 0; i < 2; ++i) { d[i] = dn[i]; y[i] = yn[i]; }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(smem_u32(&full_a[stage]));
-                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-        // flush the per-CTA bias-gradient partial sums
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // bias gradient: reduce the register partials over the lanes sharing chunk c, then over warps / CTAs
+#pragma unroll
+        for (int kb = 0; kb < 16; ++kb) {
+            if (kb < total_kb) {
+                float4 v = csum[kb];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+                    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+                    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+                    v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+                }
+                const int k = kb * BLOCK_K + c * 4;
+                if (lane < 4 && k < K) {
+                    atomicAdd(&db_sm[k + 0], v.x);
+                    atomicAdd(&db_sm[k + 1], v.y);
+                    atomicAdd(&db_sm[k + 2], v.z);
+                    atomicAdd(&db_sm[k + 3], v.w);
+                }
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (db != nullptr)
             for (int k = tid; k < K; k += PROD_THREADS) atomicAdd(db + k, db_sm[k]);
-    } else if (warp >= 8) {
+    } else if (warp >= 12) {
         // ---------------- epilogue: dZ tile -> dh_i[src] += dZ * h_j[dst],  dh_j[dst] += dZ * h_i[src] ----------------
-        const int q = warp & 3, hf = (warp - 8) >> 2;
-        constexpr int COLS_PER_WARP = BLOCK_N / 2;
-        float* stage_buf = (float*)(smem + S::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
+        const int q = warp & 3;
+        constexpr int hf = 0;
+        constexpr int COLS_PER_WARP = BLOCK_N;
+        float* stage_buf = (float*)(smem + S::EPI_OFF + (warp - 12) * EPI_STAGE_BYTES);
         uint32_t acc = 0, acc_phase = 0;
         for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
             const int64_t row0 = t * BLOCK_M + q * 32;
@@ -492,20 +525,33 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                                     __uint_as_float(v[4 * g + 3]));
                 __syncwarp();
                 const int rs = lane >> 3, cg = lane & 7;
+                const int col = nb + 4 * cg;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int r = 4 * k + rs;
-                    const float4 dz = *reinterpret_cast<const float4*>(stage_buf + r * 32 + ((cg ^ (r & 7)) << 2));
-                    const int si = __shfl_sync(0xffffffffu, s_l, r);
-                    const int dj = __shfl_sync(0xffffffffu, d_l, r);
-                    const int col = nb + 4 * cg;
-                    if (row0 + r < P && col < N) {          // N % 4 == 0
-                        const float4 xj = ldg4(hj_tab + (int64_t)dj * N + col);
-                        const float4 xi = ldg4(hi_tab + (int64_t)si * N + col);
-                        atomicAdd(reinterpret_cast<float4*>(dhi + (int64_t)si * N + col),
-                                  make_float4(dz.x * xj.x, dz.y * xj.y, dz.z * xj.z, dz.w * xj.w));
-                        atomicAdd(reinterpret_cast<float4*>(dhj + (int64_t)dj * N + col),
-                                  make_float4(dz.x * xi.x, dz.y * xi.y, dz.z * xi.z, dz.w * xi.w));
+                for (int kh = 0; kh < 2; ++kh) {             // two batches of 4 row groups: 8 gathers in flight per lane
+                    float4 dzv[4], xi[4], xj[4];
+                    int si[4], dj[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int r = 4 * (4 * kh + kk) + rs;
+                        dzv[kk] = *reinterpret_cast<const float4*>(stage_buf + r * 32 + ((cg ^ (r & 7)) << 2));
+                        si[kk] = __shfl_sync(0xffffffffu, s_l, r);
+                        dj[kk] = __shfl_sync(0xffffffffu, d_l, r);
+                        ok[kk] = (row0 + r < P) && (col < N);          // N % 4 == 0
+                        if (ok[kk]) {
+                            xj[kk] = ldg4(hj_tab + (int64_t)dj[kk] * N + col);
+                            xi[kk] = ldg4(hi_tab + (int64_t)si[kk] * N + col);
+                        }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (ok[kk]) {
+                            const float4 dz = dzv[kk];
+                            atomicAdd(reinterpret_cast<float4*>(dhi + (int64_t)si[kk] * N + col),
+                                      make_float4(dz.x * xj[kk].x, dz.y * xj[kk].y, dz.z * xj[kk].z, dz.w * xj[kk].w));
+                            atomicAdd(reinterpret_cast<float4*>(dhj + (int64_t)dj[kk] * N + col),
+                                      make_float4(dz.x * xi[kk].x, dz.y * xi[kk].y, dz.z * xi[kk].z, dz.w * xi[kk].w));
+                        }
                     }
                 }
                 __syncwarp();
@@ -561,7 +607,7 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < W::STAGES; ++s) {
             mbar_init(smem_u32(&full_raw[s]), 1);
-            mbar_init(smem_u32(&full_cvt[s]), PROD_THREADS);
+            mbar_init(smem_u32(&full_cvt[s]), CVT_THREADS);
             mbar_init(smem_u32(&full_b[s]), PROD_THREADS);
             mbar_init(smem_u32(&empty[s]), 1);
         }
@@ -639,7 +685,7 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
             uint4* a_lo = (uint4*)(st + W::TILE_BYTES);
             const int n16 = a_chunks * 2048 / 16;
 #pragma unroll 4
-            for (int c = tid; c < n16; c += PROD_THREADS) {
+            for (int c = tid; c < n16; c += CVT_THREADS) {
                 uint4 x = a_hi[c], h, l;
                 h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
                 l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
@@ -652,45 +698,51 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
             mbar_arrive(smem_u32(&full_cvt[stage]));
             if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
         }
-    } else if (warp >= 8 && warp < 12) {
-        // ---------------- Z producers: 16 pairs x C channels per stage, MN-major 128B-atom-32B swizzle ----------------
+    } else if (warp >= 8) {
+        // ---------------- Z producers (8 warps): 16 pairs x C channels per stage, MN-major 128B-atom-32B swizzle ----------------
         const int tid = threadIdx.x - 256;
-        const int kk = tid >> 3, c16 = tid & 7;
-        const int n_blocks = (C + 31) / 32;
+        const int kk = tid >> 4, j = tid & 15;                   // pair kk of the chunk; 16-byte column j (+16 per step)
         uint32_t stage = 0, phase = 0;
-        for (int64_t ch = c0; ch < c1; ++ch) {
+        float4 za[4], zb[4], na[4], nb4[4];
+        auto load = [&](int64_t ch, float4 (&x)[4], float4 (&y)[4]) {
             const int64_t p = ch * BLOCK_K + kk;
-            const bool pvalid = p < P;
+            const bool pvalid = (ch < c1) && (p < P);
             const int64_t si = pvalid ? (src ? src[p] : p) : 0;
             const int64_t dj = pvalid ? (dst ? dst[p] : p) : 0;
-            const float* pa = hi_tab + si * C + c16 * 4;
-            const float* pb = hj_tab + dj * C + c16 * 4;
-            float4 z[8];
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) {
-                if (pvalid && nb < n_blocks && nb * 32 + c16 * 4 < C) {
-                    const float4 a = ldg4(pa + nb * 32), b = ldg4(pb + nb * 32);
-                    z[nb] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+            for (int i = 0; i < 4; ++i) {
+                const int col = j * 4 + 64 * i;
+                if (pvalid && col < C) {
+                    x[i] = ldg4(hi_tab + si * C + col);
+                    y[i] = ldg4(hj_tab + dj * C + col);
                 } else {
-                    z[nb] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    y[i] = x[i];
                 }
             }
+        };
+        if (c0 < c1) load(c0, za, zb);
+        for (int64_t ch = c0; ch < c1; ++ch) {
+            load(ch + 1, na, nb4);
             mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
             uint8_t* st = smem + stage * W::STAGE_BYTES + 2 * W::TILE_BYTES;
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) {
+            for (int i = 0; i < 4; ++i) {
                 float4 h, l;
-                split_tf32(z[nb].x, h.x, l.x);
-                split_tf32(z[nb].y, h.y, l.y);
-                split_tf32(z[nb].z, h.z, l.z);
-                split_tf32(z[nb].w, h.w, l.w);
-                const uint32_t off = nb * 2048 + sw128b32_offset(kk, c16);
+                split_tf32(za[i].x * zb[i].x, h.x, l.x);
+                split_tf32(za[i].y * zb[i].y, h.y, l.y);
+                split_tf32(za[i].z * zb[i].z, h.z, l.z);
+                split_tf32(za[i].w * zb[i].w, h.w, l.w);
+                const int col = j * 4 + 64 * i;                  // channel of this 16-byte chunk
+                const uint32_t off = (col >> 5) * 2048 + sw128b32_offset(kk, (col & 31) >> 2);
                 *reinterpret_cast<float4*>(st + off) = h;
                 *reinterpret_cast<float4*>(st + W::TILE_BYTES + off) = l;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(smem_u32(&full_b[stage]));
             if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { za[i] = na[i]; zb[i] = nb4[i]; }
         }
     }
     // ---------------- epilogue (warps 8-15): TMEM -> atomicAdd into dW0 ----------------
