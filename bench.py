@@ -30,12 +30,14 @@ import torch
 
 WORKLOADS = {
     # BASELINE.json configs[2]: OGBL-DDI-shaped graph, 2-layer 8-head GAT (C = 256) + LinkPredictor(256,256)
-    "ddi": dict(n_nodes=4267, n_edges=1_334_889, feat=256, hidden=256, heads=8, layers=2, pred_hidden=256,
+    "ddi": dict(n_nodes=4267, n_edges=1_334_889, feat=256, hidden=256, heads=8, layers=2, pred_hidden=256, pos_pairs=None,
                 graph="erdos-renyi(seed=1), no isolated rows"),
     # BASELINE.json configs[3]: power-law 2M nodes / 100M edges, 3 layers
     "rmat": dict(n_nodes=2_000_000, n_edges=100_000_000, feat=256, hidden=256, heads=8, layers=3, pred_hidden=256,
-                 graph="R-MAT(.57,.19,.19, seed=4) + self loops, ids permuted"),
-    "small": dict(n_nodes=1000, n_edges=50_000, feat=64, hidden=64, heads=4, layers=2, pred_hidden=64,
+                 pos_pairs=2_000_000, graph="R-MAT(.57,.19,.19, seed=4) + self loops, ids permuted"),
+    "rmat-s": dict(n_nodes=250_000, n_edges=12_500_000, feat=256, hidden=256, heads=8, layers=3, pred_hidden=256,
+                   pos_pairs=500_000, graph="R-MAT(.57,.19,.19, seed=4) + self loops, ids permuted"),
+    "small": dict(n_nodes=1000, n_edges=50_000, feat=64, hidden=64, heads=4, layers=2, pred_hidden=64, pos_pairs=None,
                   graph="erdos-renyi(seed=1), no isolated rows"),
 }
 
@@ -226,21 +228,37 @@ def run_ours(args):
     # own rows (columns anywhere), so the per-GPU work is the N = 1 work plus the per-layer all-gather /
     # reduce-scatter of the column-side tensors (msha_gnn_b200/dist.py).
     from msha_gnn_b200 import dist as mdist
-    n_loc, n_glob = wl["n_nodes"], wl["n_nodes"] * world
-    part = mdist.Partition(n_glob, world, rank)
-    if world == 1:
-        rows, cols = make_graph_host(wl)
+    strong = wl["graph"].startswith("R-MAT")          # fixed graph partitioned over the ranks (BASELINE.json configs[3])
+    if strong:
+        n_glob = wl["n_nodes"]
+        rows, cols = make_graph_host(wl)               # identical on every rank (seeded)
+        if world > 1:
+            rowptr_h = np.zeros(n_glob + 1, dtype=np.int64)
+            np.cumsum(np.bincount(rows, minlength=n_glob), out=rowptr_h[1:])
+            part = mdist.Partition.edge_balanced(torch.from_numpy(rowptr_h), world, rank)
+            keep = (rows >= part.lo) & (rows < part.hi)
+            rows, cols = rows[keep], cols[keep]
+        else:
+            part = mdist.Partition(n_glob, 1, 0)
+        n_loc = part.n_local
     else:
-        rows, cols = er_graph(n_loc, wl["n_edges"], 1 + rank, n_cols=n_glob)
-        rows = rows + part.lo
-    E = rows.size
+        n_loc, n_glob = wl["n_nodes"], wl["n_nodes"] * world
+        part = mdist.Partition(n_glob, world, rank)
+        if world == 1:
+            rows, cols = make_graph_host(wl)
+        else:
+            rows, cols = er_graph(n_loc, wl["n_edges"], 1 + rank, n_cols=n_glob)
+            rows = rows + part.lo
     L = wl["layers"]
-    pos_host = torch.from_numpy(np.stack([rows, cols])).pin_memory()            # (2, E) int64 positives (global ids)
+    n_pos = rows.size if wl["pos_pairs"] is None else min(rows.size, wl["pos_pairs"] // (world if strong else 1))
+    pos_host = torch.from_numpy(np.stack([rows[:n_pos], cols[:n_pos]])).pin_memory()   # (2, n_pos) int64 positives (global ids)
+    rows_d, cols_d = torch.from_numpy(rows).to(dev), torch.from_numpy(cols).to(dev)
     if world == 1:
-        graph = mg.Graph.from_coo(pos_host[0].to(dev), pos_host[1].to(dev), n_loc, n_loc)
+        graph = mg.Graph.from_coo(rows_d, cols_d, n_loc, n_loc)
     else:
-        graph = mdist.partition_graph(pos_host[0].to(dev), pos_host[1].to(dev), part)
-    assert graph.nnz == E, (graph.nnz, E)
+        graph = mdist.partition_graph(rows_d, cols_d, part)
+    del rows_d, cols_d
+    E = graph.nnz                                      # distinct directed edges owned by this rank
     graph.attention_csc()
     torch.manual_seed(42)                                                        # identical parameters on every rank
     model = mg.GATLinkModel(wl["feat"], wl["hidden"], wl["heads"], L, wl["pred_hidden"], dropout=0.0).to(dev)
@@ -248,13 +266,17 @@ def run_ours(args):
     x = torch.nn.Parameter(torch.rand(n_loc, wl["feat"], device=dev) * 0.1)      # learnable node features (GAT.py:42)
     params = list(model.parameters())
     opt = torch.optim.Adam(params + [x], lr=1e-3, weight_decay=5e-4, fused=True)   # train.py:207
-    P = 2 * E
-    labels = torch.cat([torch.ones(E, dtype=torch.int64, device=dev), torch.zeros(E, dtype=torch.int64, device=dev)])
+    P = 2 * n_pos
+    labels = torch.cat([torch.ones(n_pos, dtype=torch.int64, device=dev), torch.zeros(n_pos, dtype=torch.int64, device=dev)])
     pos_dev = pos_host.to(dev)
     lib = mg._lib.lib()
+    e_tot = torch.tensor([E, P], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_tot)
+    E_global, P_global = (int(v) for v in e_tot.tolist())
 
     def step(it, pos):
-        nsrc, ndst = mg.functional.negative_sample(1000 + it * world + rank, E, n_loc, n_glob, dev)
+        nsrc, ndst = mg.functional.negative_sample(1000 + it * world + rank, n_pos, n_loc, n_glob, dev)
         src = torch.cat([pos[0], nsrc + part.lo])
         dst = torch.cat([pos[1], ndst])
         opt.zero_grad(set_to_none=True)
@@ -327,23 +349,26 @@ def run_ours(args):
                 row["GBps"] = round(ab[fname] / 1e6 / per, 1)
                 row["frac_hbm"] = round(ab[fname] / 1e6 / per / hbm_peak, 4)
             kernels.append(row)
-        # dense-contraction flops of the step (2*M*N*K per GEMM, fp32-equivalent; the 3xTF32 split issues 3x that)
+        # dense-contraction flops per call (fp32-equivalent 2*M*N*K; the 3xTF32 split issues 3x that on the tensor pipe)
         gemm_flops = sum(2.0 * sh[0] * sh[1] * sh[2] for f, a, b, sh in kt.records if f.startswith("msha_gemm") and len(sh) >= 3) / 2
+        C_, Hd_ = wl["hidden"], wl["pred_hidden"]
+        tensor_flops = {"msha_gemm_tf32x3": gemm_flops, "msha_score_mlp_fwd": 2.0 * P * C_ * Hd_,
+                        "msha_score_mlp_bwd": 4.0 * P * C_ * Hd_}
+        _, bf16_peak, _ = load_peaks()
+        tf32_peak = bf16_peak / 2.0              # kind::tf32 runs at half the bf16 rate; bf16 peak = measured cuBLAS number
         for k in kernels:
-            if k["call"] == "msha_gemm_tf32x3":
-                tf = gemm_flops / (k["avg_ms"] * k["launches_per_step"] * 1e-3) / 1e12
+            if k["call"] in tensor_flops:
+                tf = tensor_flops[k["call"]] / (k["avg_ms"] * k["launches_per_step"] * 1e-3) / 1e12
                 k["algorithmic_TFLOPs"] = round(tf, 1)
                 k["issued_tf32_TFLOPs"] = round(3 * tf, 1)
+                k["frac_tf32_peak"] = round(3 * tf / tf32_peak, 4)
         dom = kernels[0] if kernels else None
-        if dom and dom["call"] == "msha_gemm_tf32x3":
-            _, bf16_peak, _ = load_peaks()
-            tf32_peak = bf16_peak / 2.0          # kind::tf32 runs at half the bf16 rate; bf16 peak is the measured cuBLAS number
-            roofline = {"bound": "tensor", "kernel": "msha_gemm_tf32x3 (all GEMM launches of the step)",
-                        "achieved": dom["issued_tf32_TFLOPs"], "peak": tf32_peak, "unit": "TFLOP/s",
-                        "frac": round(dom["issued_tf32_TFLOPs"] / tf32_peak, 4), "traffic": None,
+        if dom and dom["call"] in tensor_flops:
+            roofline = {"bound": "tensor", "kernel": dom["call"], "achieved": dom["issued_tf32_TFLOPs"], "peak": tf32_peak,
+                        "unit": "TFLOP/s", "frac": dom["frac_tf32_peak"], "traffic": None,
                         "algorithmic_fp32_equiv_TFLOPs": dom["algorithmic_TFLOPs"],
-                        "note": "achieved = tf32 flops issued (3 per fp32-accurate product, 3xTF32 split); peak = measured bf16 "
-                                "cuBLAS peak / 2; " + peak_src,
+                        "note": "achieved = tf32 flops issued per launch (3 per fp32-accurate product: 3xTF32 split) / CUDA-event "
+                                "time; peak = measured bf16 cuBLAS peak / 2 (kind::tf32 rate); " + peak_src,
                         "share_of_step": dom["share"]}
         elif dom and "GBps" in dom:
             roofline = {"bound": "hbm", "kernel": dom["call"], "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
@@ -366,20 +391,20 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    total_edges = E * L * world
+    total_edges = E_global * L
     out = {
         "metric": "gat_fwd_bwd_layer_edges_per_sec", "value": total_edges / (ms_dev / 1e3), "unit": "edges/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['n_nodes']} nodes, {E} directed edges ({wl['graph']}), F={wl['feat']}, "
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {n_glob} nodes, {E_global} directed edges ({wl['graph']}), F={wl['feat']}, "
                                f"{L}-layer {wl['heads']}-head GAT C={wl['hidden']} + LinkPredictor(mlp,{wl['hidden']},"
-                               f"{wl['pred_hidden']}) over P={P} pairs (E positives + E Philox negatives), nll loss, Adam",
+                               f"{wl['pred_hidden']}) over P={P_global} pairs (positives + as many Philox negatives), nll loss, Adam",
                    "per_gpu": ("whole graph on one GPU" if world == 1 else
-                               f"weak scaling: graph of {n_glob} nodes / {E * world} edges partitioned by destination-node range, "
+                               f"{'strong' if strong else 'weak'} scaling: graph of {n_glob} nodes / {E_global} edges partitioned by destination-node range, "
                                "per layer one NCCL all-gather (fwd) + reduce-scatter (bwd) of [Wh|s_nbr]; pairs data-parallel; "
                                "parameter gradients all-reduced"),
                    "l2_policy": "per-step working set (>= 4*P*pred_hidden bytes of scores) exceeds the 126 MB L2; no explicit flush"},
-        "pairs_per_sec": P * world / (ms_dev / 1e3),
+        "pairs_per_sec": P_global / (ms_dev / 1e3),
         "e2e": {"value": total_edges / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(pos_host.numel() * 8), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),

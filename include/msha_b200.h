@@ -67,21 +67,36 @@ int msha_csc_from_csr(const int32_t* rowptr, const int32_t* col, int64_t n_rows,
 int msha_csr_normalize_columns(const int32_t* col, const float* val, int64_t nnz, int64_t n_cols, float* colsum,
                                float* out, void* stream);
 
+/* Hub rows / columns of power-law graphs: rows with more than seg_limit entries are split into segments of at most
+ * seg_limit consecutive CSR (CSC) slots, processed by independent warps and merged.  All pointers are device arrays;
+ * the struct itself lives in host memory.  Pass NULL when the graph has no such rows. */
+typedef struct msha_hub {
+    int32_t seg_limit, n_segs;
+    const int32_t* seg_item; /* row (column) id per segment */
+    const int32_t* seg_beg;  /* first slot of the segment */
+    const int32_t* seg_end;  /* one past its last slot */
+    int32_t n_hub, pad_;
+    const int32_t* hub_ids;     /* the split rows (columns) */
+    const int32_t* hub_seg_ptr; /* [n_hub + 1] offsets into the segment arrays */
+} msha_hub_t;
+size_t msha_gat_fwd_hub_scratch_floats(int64_t n_segs, int H, int D);
+
 /* ---- K-2/K-3 fused logit + segmented softmax + aggregation: replaces Ours.py:64-69,98 / Ablation.py:265-271,274 /
  *      HGANE.py:46-47,66-68.  alpha_in != NULL -> plain weighted SpMM (K-3 only). ---- */
 int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr, const float* s_self,
                  const float* feat, int H, int D, float slope, const float* alpha_in, float* alpha_out, float* out,
-                 int act, float* lse_out, float drop_p, uint64_t drop_seed, void* stream);
+                 int act, float* lse_out, float drop_p, uint64_t drop_seed, const msha_hub_t* hub, float* hub_scratch,
+                 void* stream);
 /* backward row pass (autograd of the lines above): d alpha, softmax and LeakyReLU backward, d s_self */
 int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
                       const float* s_self, float slope, const float* alpha, const float* feat, const float* dout,
                       const float* out, int act, float* dz_out, const float* dT, const float* fT,
                       const float* dalpha_extra, const float* dlse, int H, int D, float* dlogit, float* ds_self,
-                      float drop_p, uint64_t drop_seed, void* stream);
+                      float drop_p, uint64_t drop_seed, const msha_hub_t* hub, float* r_buf, void* stream);
 /* ---- K-4 transposed SpMM over CSC: replaces `attention_inter.t() @ h2` Ours.py:100 and the d feat pass ---- */
 int msha_spmm_csc(const int32_t* colptr, const int32_t* rowidx, const int32_t* perm, int64_t n_cols, const float* w,
                   const float* feat, int H, int D, float* out, int accumulate, const float* esum_in, float* esum_out,
-                  float drop_p, uint64_t drop_seed, void* stream);
+                  float drop_p, uint64_t drop_seed, const msha_hub_t* hub, void* stream);
 /* node-level pieces of the logit: s = Wh . a (Ours.py:64: matmul(inter_input, a)) and its backward */
 int msha_node_scores(const float* feat, int64_t n, int H, int D, const float* a1, float* s1, const float* a2,
                      float* s2, void* stream);

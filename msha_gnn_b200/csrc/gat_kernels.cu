@@ -13,6 +13,7 @@
 // loads), VPL vectors per lane.  Per-edge weights of the current 32-edge chunk are staged in shared memory.
 // Masked edges (col < 0, j = ~col) are the reference's isolated-row semantics: logit = -9e15, no gradient.
 #include "common.cuh"
+#include "msha_b200.h"
 
 #define NEG_MASK_F (-9e15f)
 
@@ -37,6 +38,19 @@ template <> struct VecT<1> {
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 
+// Hub rows / columns (power-law graphs): entries beyond `seg_limit` per row are processed as independent segments
+// of at most seg_limit edges (one warp each) and merged afterwards, so no warp walks a 100k-edge row alone.
+struct HubArgs {
+    int seg_limit;                 // 0: disabled
+    int n_segs;
+    const int32_t* seg_item;       // row (column) id of the segment
+    const int32_t* seg_beg;
+    const int32_t* seg_end;
+    int n_hub;
+    const int32_t* hub_ids;        // the split rows (columns)
+    const int32_t* hub_seg_ptr;    // [n_hub + 1] into the segment arrays
+};
+
 struct DropArgs {
     uint32_t thr;       // keep iff philox word >= thr ; 0 -> dropout inactive
     float inv_keep;     // 1/(1-p)
@@ -53,15 +67,24 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
                const float* __restrict__ s_nbr, const float* __restrict__ s_self,
                const float* __restrict__ feat, int H, int D, float slope,
                const float* __restrict__ alpha_in, float* __restrict__ alpha_out,
-               float* __restrict__ out, int act, float* __restrict__ lse_out, DropArgs drop) {
+               float* __restrict__ out, int act, float* __restrict__ lse_out, DropArgs drop, HubArgs hub,
+               float* __restrict__ part) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * GAT_WARPS + warp;
-    if (row >= n_rows) return;
+    const int w = blockIdx.x * GAT_WARPS + warp;
+    int row, beg, end, seg = -1;
+    if (w < n_rows) {
+        row = w; beg = rowptr[row]; end = rowptr[row + 1];
+        if (hub.seg_limit && end - beg > hub.seg_limit) return;         // handled segment-wise below
+    } else {
+        seg = w - n_rows;
+        if (seg >= hub.n_segs) return;
+        row = hub.seg_item[seg]; beg = hub.seg_beg[seg]; end = hub.seg_end[seg];
+    }
+    const bool part_mode = seg >= 0;       // partial (un-normalised) result of one segment; merged by gat_fwd_merge_kernel
     float* sm_w = smem + warp * 32 * H;
     const int C = H * D;
     const int nvec = C / VW;
-    const int beg = rowptr[row], end = rowptr[row + 1];
 
     int head_of[VPL];
 #pragma unroll
@@ -92,7 +115,8 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
             if (lane == h) { m_stat = mx; l_stat = sum; }
         }
         // log-sum-exp of the row's logits (HGANE's joint normaliser needs the un-normalised sums, HGANE.py:61-62)
-        if (lse_out != nullptr && lane < H) lse_out[(int64_t)row * H + lane] = (end > beg) ? m_stat + logf(l_stat) : -INFINITY;
+        if (!part_mode && lse_out != nullptr && lane < H)
+            lse_out[(int64_t)row * H + lane] = (end > beg) ? m_stat + logf(l_stat) : -INFINITY;
     }
 
     float acc[VPL][VW];
@@ -117,7 +141,7 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
                 } else {
                     float lg = masked ? NEG_MASK_F
                                       : lrelu(__ldg(s_nbr + (int64_t)j * H + h) + s_self[(int64_t)row * H + h], slope);
-                    a = expf(lg - mh) / lh;
+                    a = part_mode ? expf(lg - mh) : expf(lg - mh) / lh;      // hub segments: normalised at merge time
                     if (alpha_out) alpha_out[(int64_t)e * H + h] = a;
                 }
                 if (drop.thr) a *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + h, drop.thr, drop.inv_keep);
@@ -144,6 +168,19 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
         }
         __syncwarp();
     }
+    if (part_mode) {
+        float* P = part + (int64_t)seg * (2 * H + C);
+        if (lane < H) { P[lane] = m_stat; P[H + lane] = l_stat; }
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int v = lane + 32 * k;
+            if (v < nvec) {
+#pragma unroll
+                for (int q = 0; q < VW; ++q) P[2 * H + v * VW + q] = acc[k][q];
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
         const int v = lane + 32 * k;
@@ -154,6 +191,46 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
             }
             VecT<VW>::store(out + (int64_t)row * C + v * VW, acc[k]);
         }
+    }
+}
+
+// Merge of the hub-row segments: online-softmax combination (m, l, acc) -> out, lse, and the final scaling of the
+// un-normalised alpha the segments stored.  plain_sum: weights were given (no softmax) -> plain sum of partials.
+__global__ void gat_fwd_merge_kernel(HubArgs hub, const float* __restrict__ part, int H, int D, float* __restrict__ alpha,
+                                     float* __restrict__ out, int act, float* __restrict__ lse_out, int plain_sum) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * GAT_WARPS + warp;
+    if (i >= hub.n_hub) return;
+    float* sc = smem + warp * H;
+    const int C = H * D;
+    const int row = hub.hub_ids[i];
+    const int s0 = hub.hub_seg_ptr[i], s1 = hub.hub_seg_ptr[i + 1];
+    float M = -INFINITY, L = 0.f;                        // lane h < H owns head h
+    if (!plain_sum && lane < H) {
+        for (int s = s0; s < s1; ++s) M = fmaxf(M, part[(int64_t)s * (2 * H + C) + lane]);
+        for (int s = s0; s < s1; ++s) {
+            const float* P = part + (int64_t)s * (2 * H + C);
+            L += P[H + lane] * expf(P[lane] - M);
+        }
+        if (lse_out) lse_out[(int64_t)row * H + lane] = M + logf(L);
+    }
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        const int h = c < C ? c / D : 0;
+        float acc = 0.f;
+        for (int s = s0; s < s1; ++s) {
+            const float* P = part + (int64_t)s * (2 * H + C);
+            __syncwarp();
+            if (lane < H) sc[lane] = plain_sum ? 1.f : expf(P[lane] - M) / L;
+            __syncwarp();
+            if (c < C) acc = fmaf(P[2 * H + c], sc[h], acc);
+            if (c0 == 0 && !plain_sum && alpha != nullptr) {       // scale this segment's alpha entries once
+                const int64_t b = (int64_t)hub.seg_beg[s] * H, e = (int64_t)hub.seg_end[s] * H;
+                for (int64_t idx = b + lane; idx < e; idx += 32) alpha[idx] *= sc[idx % H];
+            }
+        }
+        if (c < C) out[(int64_t)row * C + c] = act == 1 ? elu1(acc) : acc;
     }
 }
 
@@ -169,11 +246,22 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
                     float* __restrict__ dz_out,
                     const float* __restrict__ dT, const float* __restrict__ fT,
                     const float* __restrict__ dalpha_extra, const float* __restrict__ dlse,
-                    int H, int D, float* __restrict__ dlogit, float* __restrict__ ds_self, DropArgs drop) {
+                    int H, int D, float* __restrict__ dlogit, float* __restrict__ ds_self, DropArgs drop, HubArgs hub,
+                    int mode, float* __restrict__ r_buf) {
+    // mode 0: one warp per row (hub rows skipped); mode 1 / 2: hub segments, phase 1 (d alpha, partial r -> r_buf) and
+    // phase 2 (softmax / LeakyReLU backward with the complete r, partial d s_self -> atomics)
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * GAT_WARPS + warp;
-    if (row >= n_rows) return;
+    const int w = blockIdx.x * GAT_WARPS + warp;
+    int row, beg, end;
+    if (mode == 0) {
+        if (w >= n_rows) return;
+        row = w; beg = rowptr[row]; end = rowptr[row + 1];
+        if (hub.seg_limit && end - beg > hub.seg_limit) return;
+    } else {
+        if (w >= hub.n_segs) return;
+        row = hub.seg_item[w]; beg = hub.seg_beg[w]; end = hub.seg_end[w];
+    }
     float* sm_d = smem + warp * (32 * H + 2 * H);
     float* sm_r = sm_d + 32 * H;
     float* sm_ds = sm_r + H;
@@ -181,7 +269,6 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
     const int nvec = C / VW;
     const int LPH = D / VW;                        // lanes (vectors) per head
     const bool pow2 = (LPH & (LPH - 1)) == 0;
-    const int beg = rowptr[row], end = rowptr[row + 1];
     const bool softmax_mode = (s_nbr != nullptr);
 
     float dz[VPL][VW], ft[VPL][VW];
@@ -200,7 +287,8 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
 #pragma unroll
                 for (int q = 0; q < VW; ++q) dz[k][q] = o[q] > 0.f ? dz[k][q] : dz[k][q] * (o[q] + 1.f);
             }
-            if (dz_out) VecT<VW>::store(dz_out + (int64_t)row * C + v * VW, dz[k]);
+            if (dz_out && (mode == 0 || (mode == 1 && beg == rowptr[row])))
+                VecT<VW>::store(dz_out + (int64_t)row * C + v * VW, dz[k]);
             if (fT) VecT<VW>::load(fT + (int64_t)row * C + v * VW, ft[k]);
         }
     }
@@ -208,7 +296,7 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
     __syncwarp();
 
     // ---- phase 1: d alpha per edge (-> dlogit as scratch), r_h = sum alpha * dalpha
-    for (int e0 = beg; e0 < end; e0 += 32) {
+    for (int e0 = beg; mode != 2 && e0 < end; e0 += 32) {
         const int e = e0 + lane;
         const bool valid = e < end;
         const int c = valid ? col[e] : 0;
@@ -268,6 +356,14 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
         __syncwarp();
     }
     if (!softmax_mode) return;
+    if (mode == 1) {                                   // hub segment: publish the partial r and stop
+        for (int h = lane; h < H; h += 32) atomicAdd(&r_buf[(int64_t)row * H + h], sm_r[h]);
+        return;
+    }
+    if (mode == 2) {
+        for (int h = lane; h < H; h += 32) sm_r[h] = r_buf[(int64_t)row * H + h];
+        __syncwarp();
+    }
     // d lse_i / d e_ij = alpha_ij : fold the upstream gradient of the row's log-sum-exp into r_h
     if (dlse != nullptr) {
         __syncwarp();
@@ -297,8 +393,13 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
         }
     }
     __syncwarp();
-    if (ds_self)
-        for (int h = lane; h < H; h += 32) ds_self[(int64_t)row * H + h] = sm_ds[h];
+    if (ds_self) {
+        if (mode == 2) {
+            for (int h = lane; h < H; h += 32) atomicAdd(&ds_self[(int64_t)row * H + h], sm_ds[h]);
+        } else {
+            for (int h = lane; h < H; h += 32) ds_self[(int64_t)row * H + h] = sm_ds[h];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -310,16 +411,25 @@ spmm_csc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ 
                 const int32_t* __restrict__ perm, int n_cols,
                 const float* __restrict__ w, const float* __restrict__ feat, int H, int D,
                 float* __restrict__ out, int accumulate,
-                const float* __restrict__ esum_in, float* __restrict__ esum_out, DropArgs drop) {
+                const float* __restrict__ esum_in, float* __restrict__ esum_out, DropArgs drop, HubArgs hub) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cidx = blockIdx.x * GAT_WARPS + warp;
-    if (cidx >= n_cols) return;
+    const int w0 = blockIdx.x * GAT_WARPS + warp;
+    int cidx, beg, end;
+    bool part_mode = false;
+    if (w0 < n_cols) {
+        cidx = w0; beg = colptr[cidx]; end = colptr[cidx + 1];
+        if (hub.seg_limit && end - beg > hub.seg_limit) return;
+    } else {
+        const int seg = w0 - n_cols;
+        if (seg >= hub.n_segs) return;
+        cidx = hub.seg_item[seg]; beg = hub.seg_beg[seg]; end = hub.seg_end[seg];
+        part_mode = true;                   // partial sums of one segment: atomically added (rows zeroed beforehand)
+    }
     float* sm_w = smem + warp * (32 * H + H);
     float* sm_s = sm_w + 32 * H;
     const int C = H * D;
     const int nvec = C / VW;
-    const int beg = colptr[cidx], end = colptr[cidx + 1];
 
     int head_of[VPL];
     float acc[VPL][VW];
@@ -379,6 +489,11 @@ spmm_csc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ 
             const int v = lane + 32 * k;
             if (v < nvec) {
                 float* o = out + (int64_t)cidx * C + v * VW;
+                if (part_mode) {
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) atomicAdd(o + q, acc[k][q]);
+                    continue;
+                }
                 if (accumulate) {
 #pragma unroll
                     for (int q = 0; q < VW; ++q) acc[k][q] += o[q];
@@ -387,8 +502,21 @@ spmm_csc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ 
             }
         }
     }
-    if (esum_out)
-        for (int h = lane; h < H; h += 32) esum_out[(int64_t)cidx * H + h] = sm_s[h];
+    if (esum_out) {
+        if (part_mode) {
+            for (int h = lane; h < H; h += 32) atomicAdd(&esum_out[(int64_t)cidx * H + h], sm_s[h]);
+        } else {
+            for (int h = lane; h < H; h += 32) esum_out[(int64_t)cidx * H + h] = sm_s[h];
+        }
+    }
+}
+
+// zero the rows `ids` of a [n, C] matrix (hub rows / columns that are accumulated with atomics)
+__global__ void zero_rows_kernel(float* __restrict__ x, const int32_t* __restrict__ ids, int n_ids, int C) {
+    const int i = blockIdx.x;
+    if (i >= n_ids) return;
+    float* r = x + (int64_t)ids[i] * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) r[c] = 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -428,37 +556,74 @@ static DropArgs make_drop(float p, uint64_t seed, uint32_t stream) {
     else if (VWv == 1 && VPLv == 4) { CALL(1, 4); }             \
     else { CALL(1, 8); }
 
+// host view of the hub description (include/msha_b200.h: msha_hub_t)
+struct msha_hub_host {
+    int32_t seg_limit, n_segs;
+    const int32_t* seg_item;
+    const int32_t* seg_beg;
+    const int32_t* seg_end;
+    int32_t n_hub, pad_;
+    const int32_t* hub_ids;
+    const int32_t* hub_seg_ptr;
+};
+static HubArgs make_hub(const void* hp) {
+    HubArgs h;
+    h.seg_limit = 0; h.n_segs = 0; h.seg_item = h.seg_beg = h.seg_end = nullptr; h.n_hub = 0; h.hub_ids = h.hub_seg_ptr = nullptr;
+    if (hp) {
+        const msha_hub_host* s = (const msha_hub_host*)hp;
+        if (s->n_hub > 0 && s->n_segs > 0) {
+            h.seg_limit = s->seg_limit; h.n_segs = s->n_segs; h.seg_item = s->seg_item; h.seg_beg = s->seg_beg;
+            h.seg_end = s->seg_end; h.n_hub = s->n_hub; h.hub_ids = s->hub_ids; h.hub_seg_ptr = s->hub_seg_ptr;
+        }
+    }
+    return h;
+}
+
+// floats of scratch msha_gat_fwd needs for a hub description with n_segs segments
+MSHA_API size_t msha_gat_fwd_hub_scratch_floats(int64_t n_segs, int H, int D) { return (size_t)n_segs * (2 * H + H * D); }
+
 // alpha_in == NULL: compute softmax attention from (s_nbr, s_self) and optionally store it in alpha_out.
 // alpha_in != NULL: plain weighted SpMM with the given per-edge, per-head weights.
+// hub (nullable): rows with more than hub->seg_limit edges are processed as segments; hub_scratch holds their partials.
 MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
                           const float* s_self, const float* feat, int H, int D, float slope, const float* alpha_in,
                           float* alpha_out, float* out, int act, float* lse_out, float drop_p, uint64_t drop_seed,
-                          void* stream) {
+                          const msha_hub_t* hub_p, float* hub_scratch, void* stream) {
     MSHA_REQUIRE(H >= 1 && H <= 32 && D >= 1, "gat_fwd: need 1 <= H <= 32, D >= 1");
     MSHA_REQUIRE(alpha_in != nullptr || (s_nbr != nullptr && s_self != nullptr), "gat_fwd: scores or alpha required");
     MSHA_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), "gat_fwd: bad n_rows");
     int vw, vpl;
     MSHA_REQUIRE(pick_layout(H, D, &vw, &vpl) == 0, "gat_fwd: unsupported channel count H*D=%d", H * D);
     if (n_rows == 0) return 0;
+    HubArgs hub = make_hub(hub_p);
+    MSHA_REQUIRE(hub.n_segs == 0 || hub_scratch != nullptr, "gat_fwd: hub rows need scratch");
+    MSHA_REQUIRE(hub.n_segs == 0 || alpha_in != nullptr || alpha_out != nullptr, "gat_fwd: hub rows need alpha_out");
     DropArgs drop = make_drop(drop_p, drop_seed, 2u);
-    const unsigned grid = (unsigned)msha_cdiv(n_rows, GAT_WARPS);
+    const unsigned grid = (unsigned)msha_cdiv(n_rows + hub.n_segs, GAT_WARPS);
     const size_t smem = (size_t)GAT_WARPS * 32 * H * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(A, B)                                                                                             \
     gat_fwd_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, feat, H, D, \
-                                                          slope, alpha_in, alpha_out, out, act, lse_out, drop)
+                                                          slope, alpha_in, alpha_out, out, act, lse_out, drop, hub, hub_scratch)
     DISPATCH_LAYOUT(vw, vpl, CALL)
 #undef CALL
     MSHA_LAUNCH_OK();
+    if (hub.n_hub > 0) {
+        gat_fwd_merge_kernel<<<(unsigned)msha_cdiv(hub.n_hub, GAT_WARPS), GAT_THREADS, GAT_WARPS * H * sizeof(float), st>>>(
+            hub, hub_scratch, H, D, alpha_in ? nullptr : alpha_out, out, act, lse_out, alpha_in != nullptr ? 1 : 0);
+        MSHA_LAUNCH_OK();
+    }
     return 0;
 }
 
 // Row pass of the backward.  s_nbr == NULL -> no softmax: dlogit receives d(weights).
+// hub (nullable) + r_buf (float[n_rows * H] scratch) handle rows split into segments.
 MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
                                const float* s_self, float slope, const float* alpha, const float* feat,
                                const float* dout, const float* out, int act, float* dz_out, const float* dT,
                                const float* fT, const float* dalpha_extra, const float* dlse, int H, int D,
-                               float* dlogit, float* ds_self, float drop_p, uint64_t drop_seed, void* stream) {
+                               float* dlogit, float* ds_self, float drop_p, uint64_t drop_seed,
+                               const msha_hub_t* hub_p, float* r_buf, void* stream) {
     MSHA_REQUIRE(H >= 1 && H <= 32 && D >= 1, "gat_bwd_rows: need 1 <= H <= 32, D >= 1");
     MSHA_REQUIRE((dT == nullptr) == (fT == nullptr), "gat_bwd_rows: dT and fT go together");
     MSHA_REQUIRE(act == 0 || out != nullptr, "gat_bwd_rows: activated output needed for ELU backward");
@@ -466,37 +631,72 @@ MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_
     int vw, vpl;
     MSHA_REQUIRE(pick_layout(H, D, &vw, &vpl) == 0, "gat_bwd_rows: unsupported channel count H*D=%d", H * D);
     if (n_rows == 0) return 0;
+    HubArgs hub = make_hub(hub_p);
+    MSHA_REQUIRE(hub.n_segs == 0 || r_buf != nullptr, "gat_bwd_rows: hub rows need r_buf");
     DropArgs drop = make_drop(drop_p, drop_seed, 2u);
-    const unsigned grid = (unsigned)msha_cdiv(n_rows, GAT_WARPS);
     const size_t smem = (size_t)GAT_WARPS * (32 * H + 2 * H) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(A, B)                                                                                              \
-    gat_bwd_rows_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, slope,  \
-                                                               alpha, feat, dout, out, act, dz_out, dT, fT,     \
-                                                               dalpha_extra, dlse, H, D, dlogit, ds_self, drop)
+    if (hub.n_segs > 0) {
+        MSHA_CUDA(cudaMemsetAsync(r_buf, 0, (size_t)n_rows * H * sizeof(float), st));
+        if (ds_self) {
+            zero_rows_kernel<<<hub.n_hub, 32, 0, st>>>(ds_self, hub.hub_ids, hub.n_hub, H);
+            MSHA_LAUNCH_OK();
+        }
+    }
+#define CALL(A, B)                                                                                                   \
+    gat_bwd_rows_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, slope,       \
+                                                               alpha, feat, dout, out, act, dz_out, dT, fT,          \
+                                                               dalpha_extra, dlse, H, D, dlogit, ds_self, drop, hub, \
+                                                               mode, r_buf)
+    unsigned grid = (unsigned)msha_cdiv(n_rows, GAT_WARPS);
+    int mode = 0;
     DISPATCH_LAYOUT(vw, vpl, CALL)
-#undef CALL
     MSHA_LAUNCH_OK();
+    if (hub.n_segs > 0) {
+        grid = (unsigned)msha_cdiv(hub.n_segs, GAT_WARPS);
+        mode = 1;
+        DISPATCH_LAYOUT(vw, vpl, CALL)
+        MSHA_LAUNCH_OK();
+        if (s_nbr != nullptr) {
+            mode = 2;
+            DISPATCH_LAYOUT(vw, vpl, CALL)
+            MSHA_LAUNCH_OK();
+        }
+    }
+#undef CALL
     return 0;
 }
 
 // out[j] (+)= sum_{i in col j} w[perm]*feat[i];  esum_out[j,h] = sum esum_in[perm,h].   w may be NULL (sums only).
+// hub (nullable): columns with more than hub->seg_limit entries are processed as segments with atomic accumulation.
 MSHA_API int msha_spmm_csc(const int32_t* colptr, const int32_t* rowidx, const int32_t* perm, int64_t n_cols,
                            const float* w, const float* feat, int H, int D, float* out, int accumulate,
-                           const float* esum_in, float* esum_out, float drop_p, uint64_t drop_seed, void* stream) {
+                           const float* esum_in, float* esum_out, float drop_p, uint64_t drop_seed,
+                           const msha_hub_t* hub_p, void* stream) {
     MSHA_REQUIRE(H >= 1 && H <= 32 && D >= 1, "spmm_csc: need 1 <= H <= 32, D >= 1");
     MSHA_REQUIRE(w == nullptr || (feat != nullptr && out != nullptr), "spmm_csc: feat/out required with weights");
     MSHA_REQUIRE((esum_in == nullptr) == (esum_out == nullptr), "spmm_csc: esum_in/esum_out go together");
     int vw, vpl;
     MSHA_REQUIRE(pick_layout(H, D, &vw, &vpl) == 0, "spmm_csc: unsupported channel count H*D=%d", H * D);
     if (n_cols == 0) return 0;
+    HubArgs hub = make_hub(hub_p);
     DropArgs drop = make_drop(drop_p, drop_seed, 2u);
-    const unsigned grid = (unsigned)msha_cdiv(n_cols, GAT_WARPS);
+    const unsigned grid = (unsigned)msha_cdiv(n_cols + hub.n_segs, GAT_WARPS);
     const size_t smem = (size_t)GAT_WARPS * (32 * H + H) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    if (hub.n_hub > 0) {
+        if (w != nullptr && !accumulate) {
+            zero_rows_kernel<<<hub.n_hub, 128, 0, st>>>(out, hub.hub_ids, hub.n_hub, H * D);
+            MSHA_LAUNCH_OK();
+        }
+        if (esum_out != nullptr) {
+            zero_rows_kernel<<<hub.n_hub, 32, 0, st>>>(esum_out, hub.hub_ids, hub.n_hub, H);
+            MSHA_LAUNCH_OK();
+        }
+    }
 #define CALL(A, B)                                                                                             \
     spmm_csc_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(colptr, rowidx, perm, (int)n_cols, w, feat, H, D,   \
-                                                           out, accumulate, esum_in, esum_out, drop)
+                                                           out, accumulate, esum_in, esum_out, drop, hub)
     DISPATCH_LAYOUT(vw, vpl, CALL)
 #undef CALL
     MSHA_LAUNCH_OK();

@@ -16,6 +16,14 @@ from .ops import (ACT_ELU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SIGMO
 I32 = torch.int32
 
 
+def _hub_scratch(hub, H, D, device):
+    """Partial-result buffer of the hub-row segments (None when the graph has no hub rows)."""
+    if not hub.n_segs:
+        return None
+    n = ops._lib.lib().msha_gat_fwd_hub_scratch_floats(hub.n_segs, H, D)
+    return torch.empty(n, dtype=torch.float32, device=device)
+
+
 def _c(t):
     """Contiguous and 16-byte aligned (views sliced out of a larger buffer may start at any 4-byte offset)."""
     if not t.is_contiguous():
@@ -200,8 +208,10 @@ class _AttentionBlock(torch.autograd.Function):
         alpha = torch.empty((E, H), dtype=torch.float32, device=dev)
         out = torch.empty((N, C), dtype=torch.float32, device=dev)
         lse = torch.empty((N, H), dtype=torch.float32, device=dev) if want_lse else None
+        hub = graph.hub_rows()
+        scr = _hub_scratch(hub, H, D, dev)
         call("msha_gat_fwd", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr), ptr(s_self), ptr(feat_nbr), H, D, LRELU_SLOPE,
-             None, ptr(alpha), ptr(out), act, ptr(lse), p, seed, _stream())
+             None, ptr(alpha), ptr(out), act, ptr(lse), p, seed, hub.ptr, ptr(scr), _stream())
         out_cols = None
         if want_cols:
             feat_self = _c(feat_self)
@@ -209,7 +219,7 @@ class _AttentionBlock(torch.autograd.Function):
             colptr, rowidx, perm = graph.attention_csc()
             out_cols = torch.empty((M, C), dtype=torch.float32, device=dev)
             call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(feat_self), H, D,
-                 ptr(out_cols), 0, None, None, p, seed, _stream())
+                 ptr(out_cols), 0, None, None, p, seed, graph.hub_cols().ptr, _stream())
         ctx.graph, ctx.H, ctx.D, ctx.act, ctx.p, ctx.seed = graph, H, D, act, p, seed
         ctx.want_cols, ctx.want_lse = want_cols, want_lse
         ctx.save_for_backward(s_nbr, s_self, feat_nbr, feat_self if want_cols else None, alpha,
@@ -242,21 +252,24 @@ class _AttentionBlock(torch.autograd.Function):
         dlogit = torch.empty_like(alpha)
         ds_self = torch.empty((N, H), dtype=torch.float32, device=dev)
         dz = torch.empty((N, C), dtype=torch.float32, device=dev) if act != ACT_NONE else None
+        hub = graph.hub_rows()
+        r_buf = torch.empty((N, H), dtype=torch.float32, device=dev) if hub.n_segs else None
         extra = _c(d_alpha) if d_alpha is not None else None
         dlse = _c(d_lse) if d_lse is not None else None
         call("msha_gat_bwd_rows", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr), ptr(s_self), LRELU_SLOPE, ptr(alpha),
              ptr(feat_nbr), ptr(d_rows), ptr(out), act, ptr(dz), ptr(d_cols), ptr(feat_self) if d_cols is not None else None,
-             ptr(extra), ptr(dlse), H, D, ptr(dlogit), ptr(ds_self), p, seed, _stream())
+             ptr(extra), ptr(dlse), H, D, ptr(dlogit), ptr(ds_self), p, seed, hub.ptr, ptr(r_buf), _stream())
         dzz = dz if dz is not None else d_rows
         dfeat_nbr = torch.empty((M, C), dtype=torch.float32, device=dev)
         ds_nbr = torch.empty((M, H), dtype=torch.float32, device=dev)
         call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(dzz), H, D,
-             ptr(dfeat_nbr), 0, ptr(dlogit), ptr(ds_nbr), p, seed, _stream())
+             ptr(dfeat_nbr), 0, ptr(dlogit), ptr(ds_nbr), p, seed, graph.hub_cols().ptr, _stream())
         dfeat_self = None
         if ctx.want_cols and d_cols is not None and ctx.needs_input_grad[3]:
             dfeat_self = torch.empty((N, C), dtype=torch.float32, device=dev)
+            scr = _hub_scratch(hub, H, D, dev)
             call("msha_gat_fwd", ptr(rp, I32), ptr(col, I32), N, None, None, ptr(d_cols), H, D, LRELU_SLOPE, ptr(alpha),
-                 None, ptr(dfeat_self), ACT_NONE, None, p, seed, _stream())
+                 None, ptr(dfeat_self), ACT_NONE, None, p, seed, hub.ptr, ptr(scr), _stream())
         return ds_nbr, ds_self, dfeat_nbr, dfeat_self, None, None, None, None, None, None, None, None
 
 
@@ -286,7 +299,7 @@ class _SpmmT(torch.autograd.Function):
         M, C = graph.n_cols, feat.shape[1]
         out = torch.empty((M, C), dtype=torch.float32, device=feat.device)
         call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(w), ptr(feat), 1, C, ptr(out), 0,
-             None, None, 0.0, 0, _stream())
+             None, None, 0.0, 0, graph.hub_cols_plain().ptr, _stream())
         ctx.graph = graph
         ctx.save_for_backward(w)
         return out
@@ -298,8 +311,10 @@ class _SpmmT(torch.autograd.Function):
         dout = _c(dout)
         C = dout.shape[1]
         dfeat = torch.empty((g.n_rows, C), dtype=torch.float32, device=dout.device)
+        hub = g.hub_rows_plain()
+        scr = _hub_scratch(hub, 1, C, dout.device)
         call("msha_gat_fwd", ptr(g.rowptr, I32), ptr(g.col, I32), g.n_rows, None, None, ptr(dout), 1, C, LRELU_SLOPE,
-             ptr(w), None, ptr(dfeat), ACT_NONE, None, 0.0, 0, _stream())
+             ptr(w), None, ptr(dfeat), ACT_NONE, None, 0.0, 0, hub.ptr, ptr(scr), _stream())
         return dfeat, None, None
 
 

@@ -7,6 +7,7 @@ Ours.py:54,67; HGANE.py:38-39) and the O(N^2) Python builders ``dataset.py:260-2
 """
 from __future__ import annotations
 
+import ctypes
 import weakref
 
 import torch
@@ -15,6 +16,44 @@ from . import ops
 from .ops import call, ptr, workspace, _stream
 
 _L = ops._lib
+
+
+SEG_LIMIT = 1024     # rows / columns with more entries are processed as segments of this many slots (hub handling)
+
+
+class _HubStruct(ctypes.Structure):
+    """Mirror of ``msha_hub_t`` (include/msha_b200.h)."""
+    _fields_ = [("seg_limit", ctypes.c_int32), ("n_segs", ctypes.c_int32), ("seg_item", ctypes.c_void_p),
+                ("seg_beg", ctypes.c_void_p), ("seg_end", ctypes.c_void_p), ("n_hub", ctypes.c_int32),
+                ("pad_", ctypes.c_int32), ("hub_ids", ctypes.c_void_p), ("hub_seg_ptr", ctypes.c_void_p)]
+
+
+class Hub:
+    """Segment decomposition of the rows (columns) with more than ``seg_limit`` entries; ``ptr`` is 0 when none."""
+
+    def __init__(self, ptr_arr: torch.Tensor, seg_limit: int = None):
+        seg_limit = SEG_LIMIT if seg_limit is None else seg_limit
+        deg = (ptr_arr[1:] - ptr_arr[:-1]).long()
+        ids = torch.nonzero(deg > seg_limit).flatten()
+        self.n_hub = int(ids.numel())
+        self.n_segs = 0
+        self.ptr = None
+        if self.n_hub == 0:
+            return
+        nseg = (deg[ids] + seg_limit - 1) // seg_limit
+        seg_ptr = torch.zeros(self.n_hub + 1, dtype=torch.int64, device=ptr_arr.device)
+        seg_ptr[1:] = torch.cumsum(nseg, 0)
+        self.n_segs = int(seg_ptr[-1].item())
+        which = torch.repeat_interleave(torch.arange(self.n_hub, device=ptr_arr.device), nseg)
+        local = torch.arange(self.n_segs, device=ptr_arr.device) - seg_ptr[:-1][which]
+        item = ids[which]
+        beg = ptr_arr.long()[item] + local * seg_limit
+        end = torch.minimum(beg + seg_limit, ptr_arr.long()[item + 1])
+        self.tensors = [t.to(torch.int32).contiguous() for t in (item, beg, end, ids, seg_ptr)]
+        self.struct = _HubStruct(seg_limit, self.n_segs, self.tensors[0].data_ptr(), self.tensors[1].data_ptr(),
+                                 self.tensors[2].data_ptr(), self.n_hub, 0, self.tensors[3].data_ptr(),
+                                 self.tensors[4].data_ptr())
+        self.ptr = ctypes.addressof(self.struct)
 
 
 class Graph:
@@ -29,6 +68,7 @@ class Graph:
         self._csc = None
         self._csc_plain = None
         self._deg = None
+        self._hubs = {}
         self.isolated = isolated
 
     # ---------------------------------------------------------------- constructors
@@ -131,6 +171,27 @@ class Graph:
             rp, c = self.attention_csr()
             self._csc = _csc(rp, c, self.n_rows, self.n_cols)
         return self._csc
+
+    def hub_rows(self) -> Hub:
+        """Segments of the attention-CSR rows with more than SEG_LIMIT neighbours (power-law hubs)."""
+        if "rows" not in self._hubs:
+            self._hubs["rows"] = Hub(self.attention_csr()[0])
+        return self._hubs["rows"]
+
+    def hub_cols(self) -> Hub:
+        if "cols" not in self._hubs:
+            self._hubs["cols"] = Hub(self.attention_csc()[0])
+        return self._hubs["cols"]
+
+    def hub_rows_plain(self) -> Hub:
+        if "rows_plain" not in self._hubs:
+            self._hubs["rows_plain"] = Hub(self.rowptr)
+        return self._hubs["rows_plain"]
+
+    def hub_cols_plain(self) -> Hub:
+        if "cols_plain" not in self._hubs:
+            self._hubs["cols_plain"] = Hub(self.transpose_structure()[0])
+        return self._hubs["cols_plain"]
 
     def transpose_structure(self):
         """CSC of the canonical CSR (no masked edges)."""

@@ -45,7 +45,7 @@ def test_workspace_queries_are_host_only(lib):
 
 
 def test_invalid_arguments_report_errors(lib):
-    rc = lib.msha_gat_fwd(None, None, 10, None, None, None, 64, 8, 0.2, None, None, None, 0, None, 0.0, 0, None)
+    rc = lib.msha_gat_fwd(None, None, 10, None, None, None, 64, 8, 0.2, None, None, None, 0, None, 0.0, 0, None, None, None)
     assert rc < 0 and b"H <= 32" in lib.msha_last_error()
     rc = lib.msha_gemm_f32(None, None, None, -1, 1, 1, 1, 1, 1, 0, 0, None, 0.0, 0, 0.2, None)
     assert rc < 0

@@ -81,8 +81,11 @@ def test_gat_model_golden(via):
 # ---------------------------------------------------------------------------------- a-3 / a-4
 @pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("mode", ["train", "eval"])
-@pytest.mark.parametrize("intra", ["dense", "groups"])
-def test_ours_layers_golden(variant, mode, intra):
+@pytest.mark.parametrize("intra", ["dense", "groups", "groups+hubs"])
+def test_ours_layers_golden(variant, mode, intra, monkeypatch):
+    if intra.endswith("+hubs"):         # hub-segment path on the bipartite graph (every recipient column is a hub)
+        monkeypatch.setattr(mg.graph, "SEG_LIMIT", 3)
+        intra = "groups"
     g = load_golden(f"ourslayer{variant}_{mode}")
     cls = {1: mg.OursLayer, 2: mg.OursLayer2, 3: mg.OursLayer3}[variant]
     layer = _load(cls(16, 8, 0.0), params_of(g))
@@ -227,7 +230,10 @@ def test_generic_gat_golden():
     (180, 24, 1, 128, 0.1, True),       # one head spanning the whole warp
     (120, 16, 2, 12, 0.2, True),        # vector path, lanes-per-head = 3 (not a power of two)
 ])
-def test_gat_conv_vs_oracle(N, Fin, H, d, density, concat):
+@pytest.mark.parametrize("seg_limit", [None, 16])
+def test_gat_conv_vs_oracle(N, Fin, H, d, density, concat, seg_limit, monkeypatch):
+    if seg_limit:                       # force the hub-segment path: rows / columns above 16 entries are split and merged
+        monkeypatch.setattr(mg.graph, "SEG_LIMIT", seg_limit)
     rng = np.random.default_rng(N)
     adj = (rng.random((N, N)) < density).astype(np.float32)
     adj[5] = 0                                            # isolated row -> uniform 1/N attention
