@@ -93,9 +93,30 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
         head_of[k] = (v < nvec) ? (v * VW) / D : 0;
     }
 
-    // ---- softmax statistics: lane h keeps (max, sum) of head h
+    // ---- softmax statistics
+    // H a power of two: lanes are (edge slot es, head hh) pairs -> coalesced s_nbr / alpha accesses, one online
+    // max/sum pass and log2(32/H) shuffle steps per row.  Other H: per-head loops, lane h keeps (max, sum) of head h.
+    const bool hp2 = (H & (H - 1)) == 0;
+    const int hh = lane & (H - 1), es = hp2 ? lane / H : 0, EPI = hp2 ? 32 / H : 1;
     float m_stat = 0.f, l_stat = 1.f;
-    if (alpha_in == nullptr) {
+    if (alpha_in == nullptr && hp2) {
+        const float ss = s_self[(int64_t)row * H + hh];
+        float m = -INFINITY, l = 0.f;
+        for (int e = beg + es; e < end; e += EPI) {
+            const int c = col[e];
+            const float lg = c < 0 ? NEG_MASK_F : lrelu(__ldg(s_nbr + (int64_t)c * H + hh) + ss, slope);
+            if (lg > m) { l = l * expf(m - lg) + 1.f; m = lg; } else { l += expf(lg - m); }
+        }
+        for (int o = H; o < 32; o <<= 1) {
+            const float m2 = __shfl_xor_sync(FULL_MASK, m, o), l2 = __shfl_xor_sync(FULL_MASK, l, o);
+            const float M = fmaxf(m, m2);
+            l = (m == -INFINITY ? 0.f : l * expf(m - M)) + (m2 == -INFINITY ? 0.f : l2 * expf(m2 - M));
+            m = M;
+        }
+        m_stat = m; l_stat = l;                     // every lane: statistics of its head hh
+        if (!part_mode && lse_out != nullptr && lane < H)
+            lse_out[(int64_t)row * H + lane] = (end > beg) ? m_stat + logf(l_stat) : -INFINITY;
+    } else if (alpha_in == nullptr) {
         for (int h = 0; h < H; ++h) {
             const float ss = s_self[(int64_t)row * H + h];
             float mx = -INFINITY;
@@ -118,6 +139,7 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
         if (!part_mode && lse_out != nullptr && lane < H)
             lse_out[(int64_t)row * H + lane] = (end > beg) ? m_stat + logf(l_stat) : -INFINITY;
     }
+    int* sm_j = reinterpret_cast<int*>(smem + GAT_WARPS * 32 * H) + warp * 32;     // neighbour ids of the current chunk
 
     float acc[VPL][VW];
 #pragma unroll
@@ -126,33 +148,61 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
         for (int q = 0; q < VW; ++q) acc[k][q] = 0.f;
 
     for (int e0 = beg; e0 < end; e0 += 32) {
-        const int e = e0 + lane;
-        const bool valid = e < end;
-        const int c = valid ? col[e] : 0;
-        const bool masked = c < 0;
-        const int j = masked ? ~c : c;
-        for (int h = 0; h < H; ++h) {
-            const float mh = __shfl_sync(FULL_MASK, m_stat, h);
-            const float lh = __shfl_sync(FULL_MASK, l_stat, h);
-            float a = 0.f;
-            if (valid) {
-                if (alpha_in != nullptr) {
-                    a = alpha_in[(int64_t)e * H + h];
-                } else {
-                    float lg = masked ? NEG_MASK_F
-                                      : lrelu(__ldg(s_nbr + (int64_t)j * H + h) + s_self[(int64_t)row * H + h], slope);
-                    a = part_mode ? expf(lg - mh) : expf(lg - mh) / lh;      // hub segments: normalised at merge time
-                    if (alpha_out) alpha_out[(int64_t)e * H + h] = a;
+        int j = 0;
+        if (hp2) {
+            // (edge slot, head) lanes: H sub-iterations cover the 32 edges of the chunk
+            for (int sub = 0; sub < H; ++sub) {
+                const int t = sub * EPI + es;
+                const int e = e0 + t;
+                float a = 0.f;
+                int jj = 0;
+                if (e < end) {
+                    const int c = col[e];
+                    const bool masked = c < 0;
+                    jj = masked ? ~c : c;
+                    if (alpha_in != nullptr) {
+                        a = alpha_in[(int64_t)e * H + hh];
+                    } else {
+                        const float lg = masked ? NEG_MASK_F
+                                                : lrelu(__ldg(s_nbr + (int64_t)jj * H + hh) + s_self[(int64_t)row * H + hh], slope);
+                        a = part_mode ? expf(lg - m_stat) : expf(lg - m_stat) / l_stat;
+                        if (alpha_out) alpha_out[(int64_t)e * H + hh] = a;            // coalesced
+                    }
+                    if (drop.thr) a *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + hh, drop.thr, drop.inv_keep);
                 }
-                if (drop.thr) a *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + h, drop.thr, drop.inv_keep);
+                sm_w[t * H + hh] = a;
+                if (hh == 0) sm_j[t] = jj;
             }
-            sm_w[lane * H + h] = a;
+        } else {
+            const int e = e0 + lane;
+            const bool valid = e < end;
+            const int c = valid ? col[e] : 0;
+            const bool masked = c < 0;
+            j = masked ? ~c : c;
+            sm_j[lane] = j;
+            for (int h = 0; h < H; ++h) {
+                const float mh = __shfl_sync(FULL_MASK, m_stat, h);
+                const float lh = __shfl_sync(FULL_MASK, l_stat, h);
+                float a = 0.f;
+                if (valid) {
+                    if (alpha_in != nullptr) {
+                        a = alpha_in[(int64_t)e * H + h];
+                    } else {
+                        float lg = masked ? NEG_MASK_F
+                                          : lrelu(__ldg(s_nbr + (int64_t)j * H + h) + s_self[(int64_t)row * H + h], slope);
+                        a = part_mode ? expf(lg - mh) : expf(lg - mh) / lh;      // hub segments: normalised at merge time
+                        if (alpha_out) alpha_out[(int64_t)e * H + h] = a;
+                    }
+                    if (drop.thr) a *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + h, drop.thr, drop.inv_keep);
+                }
+                sm_w[lane * H + h] = a;
+            }
         }
         __syncwarp();
         const int cnt = min(32, end - e0);
 #pragma unroll 4
         for (int t = 0; t < cnt; ++t) {
-            const int jt = __shfl_sync(FULL_MASK, j, t);
+            const int jt = sm_j[t];
             const float* f = feat + (int64_t)jt * C;
 #pragma unroll
             for (int k = 0; k < VPL; ++k) {
@@ -196,41 +246,60 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
 
 // Merge of the hub-row segments: online-softmax combination (m, l, acc) -> out, lse, and the final scaling of the
 // un-normalised alpha the segments stored.  plain_sum: weights were given (no softmax) -> plain sum of partials.
-__global__ void gat_fwd_merge_kernel(HubArgs hub, const float* __restrict__ part, int H, int D, float* __restrict__ alpha,
-                                     float* __restrict__ out, int act, float* __restrict__ lse_out, int plain_sum) {
-    extern __shared__ float smem[];
+__global__ void gat_fwd_merge_kernel(HubArgs hub, float* __restrict__ part, int H, int D, float* __restrict__ out,
+                                     int act, float* __restrict__ lse_out, int plain_sum) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * GAT_WARPS + warp;
     if (i >= hub.n_hub) return;
-    float* sc = smem + warp * H;
     const int C = H * D;
     const int row = hub.hub_ids[i];
     const int s0 = hub.hub_seg_ptr[i], s1 = hub.hub_seg_ptr[i + 1];
-    float M = -INFINITY, L = 0.f;                        // lane h < H owns head h
-    if (!plain_sum && lane < H) {
-        for (int s = s0; s < s1; ++s) M = fmaxf(M, part[(int64_t)s * (2 * H + C) + lane]);
-        for (int s = s0; s < s1; ++s) {
-            const float* P = part + (int64_t)s * (2 * H + C);
-            L += P[H + lane] * expf(P[lane] - M);
+    // pass A: per-head combination weights  sc_s = exp(m_s - M) / L, stored in the segment record's `l` slot
+    if (lane < H) {
+        if (plain_sum) {
+            for (int s = s0; s < s1; ++s) part[(int64_t)s * (2 * H + C) + H + lane] = 1.f;
+        } else {
+            float M = -INFINITY, L = 0.f;
+            for (int s = s0; s < s1; ++s) M = fmaxf(M, part[(int64_t)s * (2 * H + C) + lane]);
+            for (int s = s0; s < s1; ++s) {
+                const float* P = part + (int64_t)s * (2 * H + C);
+                L += P[H + lane] * expf(P[lane] - M);
+            }
+            for (int s = s0; s < s1; ++s) {
+                float* P = part + (int64_t)s * (2 * H + C);
+                P[H + lane] = expf(P[lane] - M) / L;
+            }
+            if (lse_out) lse_out[(int64_t)row * H + lane] = M + logf(L);
         }
-        if (lse_out) lse_out[(int64_t)row * H + lane] = M + logf(L);
     }
+    __syncwarp();
+    // pass B: weighted sum of the partial accumulators
     for (int c0 = 0; c0 < C; c0 += 32) {
         const int c = c0 + lane;
-        const int h = c < C ? c / D : 0;
-        float acc = 0.f;
-        for (int s = s0; s < s1; ++s) {
-            const float* P = part + (int64_t)s * (2 * H + C);
-            __syncwarp();
-            if (lane < H) sc[lane] = plain_sum ? 1.f : expf(P[lane] - M) / L;
-            __syncwarp();
-            if (c < C) acc = fmaf(P[2 * H + c], sc[h], acc);
-            if (c0 == 0 && !plain_sum && alpha != nullptr) {       // scale this segment's alpha entries once
-                const int64_t b = (int64_t)hub.seg_beg[s] * H, e = (int64_t)hub.seg_end[s] * H;
-                for (int64_t idx = b + lane; idx < e; idx += 32) alpha[idx] *= sc[idx % H];
+        if (c < C) {
+            const int h = c / D;
+            float acc = 0.f;
+            for (int s = s0; s < s1; ++s) {
+                const float* P = part + (int64_t)s * (2 * H + C);
+                acc = fmaf(P[2 * H + c], P[H + h], acc);
             }
+            out[(int64_t)row * C + c] = act == 1 ? elu1(acc) : acc;
         }
-        if (c < C) out[(int64_t)row * C + c] = act == 1 ? elu1(acc) : acc;
+    }
+}
+
+// final scaling of the un-normalised alpha stored by the hub segments: one warp per segment
+__global__ void gat_fwd_rescale_kernel(HubArgs hub, const float* __restrict__ part, int H, int D, float* __restrict__ alpha) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * GAT_WARPS + warp;
+    if (s >= hub.n_segs) return;
+    const float* P = part + (int64_t)s * (2 * H + H * D);
+    const int64_t b = (int64_t)hub.seg_beg[s] * H, e = (int64_t)hub.seg_end[s] * H;
+    if ((H & (H - 1)) == 0 && H <= 32) {
+        const float sc = P[H + (lane & (H - 1))];          // 32 % H == 0: a lane always hits the same head
+        for (int64_t idx = b + lane; idx < e; idx += 32) alpha[idx] *= sc;
+    } else {
+        for (int64_t idx = b + lane; idx < e; idx += 32) alpha[idx] *= P[H + (int)(idx % H)];
     }
 }
 
@@ -238,7 +307,7 @@ __global__ void gat_fwd_merge_kernel(HubArgs hub, const float* __restrict__ part
 // backward, row pass
 // ---------------------------------------------------------------------------------------------
 template <int VW, int VPL>
-__global__ void __launch_bounds__(GAT_THREADS)
+__global__ void __launch_bounds__(GAT_THREADS, 3)
 gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_rows,
                     const float* __restrict__ s_nbr, const float* __restrict__ s_self, float slope,
                     const float* __restrict__ alpha, const float* __restrict__ feat,
@@ -270,6 +339,9 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
     const int LPH = D / VW;                        // lanes (vectors) per head
     const bool pow2 = (LPH & (LPH - 1)) == 0;
     const bool softmax_mode = (s_nbr != nullptr);
+    const bool hp2 = (H & (H - 1)) == 0;              // (edge slot, head) lane mapping for the per-edge scalar work
+    const int hh = lane & (H - 1), es = hp2 ? lane / H : 0, EPI = hp2 ? 32 / H : 1;
+    float r_lane = 0.f;
 
     float dz[VPL][VW], ft[VPL][VW];
     int head_of[VPL];
@@ -304,55 +376,88 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
         for (int q = lane; q < 32 * H; q += 32) sm_d[q] = 0.f;
         __syncwarp();
         const int cnt = min(32, end - e0);
-#pragma unroll 2
-        for (int t = 0; t < cnt; ++t) {
-            const int jt = __shfl_sync(FULL_MASK, j, t);
-            const float* f = feat + (int64_t)jt * C;
-            const float* g = dT ? dT + (int64_t)jt * C : nullptr;
+        constexpr int EB = 2;                               // edges whose gathers are in flight together
+        for (int t0 = 0; t0 < cnt; t0 += EB) {
+            float x[EB][VPL][VW], y[EB][VPL][VW];
 #pragma unroll
-            for (int k = 0; k < VPL; ++k) {
-                const int v = lane + 32 * k;
-                float p = 0.f;
-                if (v < nvec) {
-                    float x[VW];
-                    VecT<VW>::load(f + v * VW, x);
+            for (int u = 0; u < EB; ++u) {
+                const int jt = __shfl_sync(FULL_MASK, j, (t0 + u) & 31);
+                const bool on = t0 + u < cnt;
+                const float* f = feat + (int64_t)jt * C;
+                const float* g = dT ? dT + (int64_t)jt * C : nullptr;
 #pragma unroll
-                    for (int q = 0; q < VW; ++q) p = fmaf(x[q], dz[k][q], p);
-                    if (g) {
-                        float y[VW];
-                        VecT<VW>::load(g + v * VW, y);
+                for (int k = 0; k < VPL; ++k) {
+                    const int v = lane + 32 * k;
 #pragma unroll
-                        for (int q = 0; q < VW; ++q) p = fmaf(y[q], ft[k][q], p);
+                    for (int q = 0; q < VW; ++q) { x[u][k][q] = 0.f; y[u][k][q] = 0.f; }
+                    if (on && v < nvec) {
+                        VecT<VW>::load(f + v * VW, x[u][k]);
+                        if (g) VecT<VW>::load(g + v * VW, y[u][k]);
                     }
                 }
-                if (pow2) {
-                    if (LPH >= 32) {
-                        p = warp_sum(p);
-                        if (lane == 0 && (32 * k) < nvec) sm_d[t * H + head_of[k]] += p;
-                    } else {
-                        for (int o = LPH >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(FULL_MASK, p, o);
-                        if ((lane & (LPH - 1)) == 0 && v < nvec) sm_d[t * H + head_of[k]] += p;
+            }
+#pragma unroll
+            for (int u = 0; u < EB; ++u) {
+                const int t = t0 + u;
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    const int v = lane + 32 * k;
+                    float p = 0.f;
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) p = fmaf(x[u][k][q], dz[k][q], p);
+                    if (dT) {
+#pragma unroll
+                        for (int q = 0; q < VW; ++q) p = fmaf(y[u][k][q], ft[k][q], p);
                     }
-                } else if (v < nvec) {
-                    atomicAdd(&sm_d[t * H + head_of[k]], p);
+                    if (pow2) {
+                        if (LPH >= 32) {
+                            p = warp_sum(p);
+                            if (lane == 0 && (32 * k) < nvec && t < cnt) sm_d[t * H + head_of[k]] += p;
+                        } else {
+                            for (int o = LPH >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(FULL_MASK, p, o);
+                            if ((lane & (LPH - 1)) == 0 && v < nvec && t < cnt) sm_d[t * H + head_of[k]] += p;
+                        }
+                    } else if (v < nvec && t < cnt) {
+                        atomicAdd(&sm_d[t * H + head_of[k]], p);
+                    }
                 }
             }
         }
         __syncwarp();
-        for (int h = 0; h < H; ++h) {
-            float da = 0.f, a = 0.f;
-            if (valid) {
-                da = sm_d[lane * H + h];
-                if (drop.thr) da *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + h, drop.thr, drop.inv_keep);
-                if (dalpha_extra) da += dalpha_extra[(int64_t)e * H + h];   // grad w.r.t. the pre-dropout alpha
-                if (softmax_mode) a = alpha[(int64_t)e * H + h];
-                dlogit[(int64_t)e * H + h] = da;
+        if (hp2) {
+            // (edge slot, head) lanes: coalesced alpha / dlogit accesses, r accumulated per lane
+            for (int sub = 0; sub < H; ++sub) {
+                const int t = sub * EPI + es;
+                const int ee = e0 + t;
+                if (ee < end) {
+                    float da = sm_d[t * H + hh];
+                    if (drop.thr) da *= dropout_scale(drop.seed, drop.stream, (uint64_t)ee * H + hh, drop.thr, drop.inv_keep);
+                    if (dalpha_extra) da += dalpha_extra[(int64_t)ee * H + hh];   // grad w.r.t. the pre-dropout alpha
+                    if (softmax_mode) r_lane = fmaf(alpha[(int64_t)ee * H + hh], da, r_lane);
+                    dlogit[(int64_t)ee * H + hh] = da;
+                }
             }
-            if (softmax_mode) {
-                float s = warp_sum(a * da);
-                if (lane == 0) sm_r[h] += s;
+        } else {
+            for (int h = 0; h < H; ++h) {
+                float da = 0.f, a = 0.f;
+                if (valid) {
+                    da = sm_d[lane * H + h];
+                    if (drop.thr) da *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + h, drop.thr, drop.inv_keep);
+                    if (dalpha_extra) da += dalpha_extra[(int64_t)e * H + h];   // grad w.r.t. the pre-dropout alpha
+                    if (softmax_mode) a = alpha[(int64_t)e * H + h];
+                    dlogit[(int64_t)e * H + h] = da;
+                }
+                if (softmax_mode) {
+                    float s = warp_sum(a * da);
+                    if (lane == 0) sm_r[h] += s;
+                }
             }
         }
+        __syncwarp();
+    }
+    if (hp2 && softmax_mode && mode != 2) {           // fold the per-lane partials: every lane gets r of its head
+        for (int o = H; o < 32; o <<= 1) r_lane += __shfl_xor_sync(FULL_MASK, r_lane, o);
+        if (lane < H) sm_r[lane] = r_lane;
         __syncwarp();
     }
     if (!softmax_mode) return;
@@ -372,24 +477,60 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
     }
 
     // ---- phase 2: softmax + LeakyReLU backward
-    for (int e0 = beg; e0 < end; e0 += 32) {
-        const int e = e0 + lane;
-        const bool valid = e < end;
-        const int c = valid ? col[e] : 0;
-        const bool masked = c < 0;
-        const int j = masked ? ~c : c;
-        for (int h = 0; h < H; ++h) {
-            float dl = 0.f;
-            if (valid) {
-                const float a = alpha[(int64_t)e * H + h];
-                const float da = dlogit[(int64_t)e * H + h];
-                const float de = a * (da - sm_r[h]);
-                const float pre = __ldg(s_nbr + (int64_t)j * H + h) + s_self[(int64_t)row * H + h];
-                dl = masked ? 0.f : (pre > 0.f ? de : de * slope);
-                dlogit[(int64_t)e * H + h] = dl;
+    if (hp2) {
+        const float r = sm_r[hh];
+        const float ss = s_self[(int64_t)row * H + hh];
+        float ds = 0.f;
+        for (int e0 = beg + es; e0 < end; e0 += 4 * EPI) {      // 4 independent edges per lane in flight
+            int cc[4];
+            float av[4], dav[4], sv[4];
+            bool on[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * EPI;
+                on[u] = e < end;
+                cc[u] = on[u] ? col[e] : 0;
+                av[u] = on[u] ? alpha[(int64_t)e * H + hh] : 0.f;
+                dav[u] = on[u] ? dlogit[(int64_t)e * H + hh] : 0.f;
             }
-            float s = warp_sum(dl);
-            if (lane == 0) sm_ds[h] += s;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = cc[u] < 0 ? ~cc[u] : cc[u];
+                sv[u] = on[u] ? __ldg(s_nbr + (int64_t)j * H + hh) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (on[u]) {
+                    const float de = av[u] * (dav[u] - r);
+                    const float pre = sv[u] + ss;
+                    const float dl = cc[u] < 0 ? 0.f : (pre > 0.f ? de : de * slope);
+                    dlogit[(int64_t)(e0 + u * EPI) * H + hh] = dl;
+                    ds += dl;
+                }
+            }
+        }
+        for (int o = H; o < 32; o <<= 1) ds += __shfl_xor_sync(FULL_MASK, ds, o);
+        if (lane < H) sm_ds[lane] = ds;
+    } else {
+        for (int e0 = beg; e0 < end; e0 += 32) {
+            const int e = e0 + lane;
+            const bool valid = e < end;
+            const int c = valid ? col[e] : 0;
+            const bool masked = c < 0;
+            const int j = masked ? ~c : c;
+            for (int h = 0; h < H; ++h) {
+                float dl = 0.f;
+                if (valid) {
+                    const float a = alpha[(int64_t)e * H + h];
+                    const float da = dlogit[(int64_t)e * H + h];
+                    const float de = a * (da - sm_r[h]);
+                    const float pre = __ldg(s_nbr + (int64_t)j * H + h) + s_self[(int64_t)row * H + h];
+                    dl = masked ? 0.f : (pre > 0.f ? de : de * slope);
+                    dlogit[(int64_t)e * H + h] = dl;
+                }
+                float s = warp_sum(dl);
+                if (lane == 0) sm_ds[h] += s;
+            }
         }
     }
     __syncwarp();
@@ -600,7 +741,7 @@ MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_r
     MSHA_REQUIRE(hub.n_segs == 0 || alpha_in != nullptr || alpha_out != nullptr, "gat_fwd: hub rows need alpha_out");
     DropArgs drop = make_drop(drop_p, drop_seed, 2u);
     const unsigned grid = (unsigned)msha_cdiv(n_rows + hub.n_segs, GAT_WARPS);
-    const size_t smem = (size_t)GAT_WARPS * 32 * H * sizeof(float);
+    const size_t smem = (size_t)GAT_WARPS * (32 * H + 32) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(A, B)                                                                                             \
     gat_fwd_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, feat, H, D, \
@@ -609,9 +750,14 @@ MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_r
 #undef CALL
     MSHA_LAUNCH_OK();
     if (hub.n_hub > 0) {
-        gat_fwd_merge_kernel<<<(unsigned)msha_cdiv(hub.n_hub, GAT_WARPS), GAT_THREADS, GAT_WARPS * H * sizeof(float), st>>>(
-            hub, hub_scratch, H, D, alpha_in ? nullptr : alpha_out, out, act, lse_out, alpha_in != nullptr ? 1 : 0);
+        gat_fwd_merge_kernel<<<(unsigned)msha_cdiv(hub.n_hub, GAT_WARPS), GAT_THREADS, 0, st>>>(
+            hub, hub_scratch, H, D, out, act, lse_out, alpha_in != nullptr ? 1 : 0);
         MSHA_LAUNCH_OK();
+        if (alpha_in == nullptr && alpha_out != nullptr) {
+            gat_fwd_rescale_kernel<<<(unsigned)msha_cdiv(hub.n_segs, GAT_WARPS), GAT_THREADS, 0, st>>>(hub, hub_scratch, H, D,
+                                                                                                   alpha_out);
+            MSHA_LAUNCH_OK();
+        }
     }
     return 0;
 }
