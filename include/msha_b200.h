@@ -92,7 +92,8 @@ int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_t n_rows,
                       const float* s_self, float slope, const float* alpha, const float* feat, const float* dout,
                       const float* out, int act, float* dz_out, const float* dT, const float* fT,
                       const float* dalpha_extra, const float* dlse, int H, int D, float* dlogit, float* ds_self,
-                      float drop_p, uint64_t drop_seed, const msha_hub_t* hub, float* r_buf, void* stream);
+                      float drop_p, uint64_t drop_seed, const msha_hub_t* hub, float* r_buf, int avg_degree_hint,
+                      void* stream);
 /* ---- K-4 transposed SpMM over CSC: replaces `attention_inter.t() @ h2` Ours.py:100 and the d feat pass ---- */
 int msha_spmm_csc(const int32_t* colptr, const int32_t* rowidx, const int32_t* perm, int64_t n_cols, const float* w,
                   const float* feat, int H, int D, float* out, int accumulate, const float* esum_in, float* esum_out,

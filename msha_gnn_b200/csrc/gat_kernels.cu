@@ -306,8 +306,10 @@ __global__ void gat_fwd_rescale_kernel(HubArgs hub, const float* __restrict__ pa
 // ---------------------------------------------------------------------------------------------
 // backward, row pass
 // ---------------------------------------------------------------------------------------------
-template <int VW, int VPL>
-__global__ void __launch_bounds__(GAT_THREADS, 3)
+// EB: edges whose feature gathers are in flight together; MINB: resident CTAs per SM the register budget targets.
+// <4, 2> suits dense rows (long gather streams), <2, 3> sparse power-law rows (latency hidden by occupancy).
+template <int VW, int VPL, int EB, int MINB>
+__global__ void __launch_bounds__(GAT_THREADS, MINB)
 gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_rows,
                     const float* __restrict__ s_nbr, const float* __restrict__ s_self, float slope,
                     const float* __restrict__ alpha, const float* __restrict__ feat,
@@ -376,7 +378,6 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
         for (int q = lane; q < 32 * H; q += 32) sm_d[q] = 0.f;
         __syncwarp();
         const int cnt = min(32, end - e0);
-        constexpr int EB = 2;                               // edges whose gathers are in flight together
         for (int t0 = 0; t0 < cnt; t0 += EB) {
             float x[EB][VPL][VW], y[EB][VPL][VW];
 #pragma unroll
@@ -769,7 +770,7 @@ MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_
                                const float* dout, const float* out, int act, float* dz_out, const float* dT,
                                const float* fT, const float* dalpha_extra, const float* dlse, int H, int D,
                                float* dlogit, float* ds_self, float drop_p, uint64_t drop_seed,
-                               const msha_hub_t* hub_p, float* r_buf, void* stream) {
+                               const msha_hub_t* hub_p, float* r_buf, int avg_degree_hint, void* stream) {
     MSHA_REQUIRE(H >= 1 && H <= 32 && D >= 1, "gat_bwd_rows: need 1 <= H <= 32, D >= 1");
     MSHA_REQUIRE((dT == nullptr) == (fT == nullptr), "gat_bwd_rows: dT and fT go together");
     MSHA_REQUIRE(act == 0 || out != nullptr, "gat_bwd_rows: activated output needed for ELU backward");
@@ -789,11 +790,18 @@ MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_
             MSHA_LAUNCH_OK();
         }
     }
-#define CALL(A, B)                                                                                                   \
-    gat_bwd_rows_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, slope,       \
-                                                               alpha, feat, dout, out, act, dz_out, dT, fT,          \
-                                                               dalpha_extra, dlse, H, D, dlogit, ds_self, drop, hub, \
-                                                               mode, r_buf)
+    const bool dense_rows = avg_degree_hint >= 64;
+#define CALL(A, B)                                                                                                       \
+    if (dense_rows)                                                                                                      \
+        gat_bwd_rows_kernel<A, B, 4, 2><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, slope, \
+                                                                         alpha, feat, dout, out, act, dz_out, dT, fT,    \
+                                                                         dalpha_extra, dlse, H, D, dlogit, ds_self,      \
+                                                                         drop, hub, mode, r_buf);                        \
+    else                                                                                                                 \
+        gat_bwd_rows_kernel<A, B, 2, 3><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, slope, \
+                                                                         alpha, feat, dout, out, act, dz_out, dT, fT,    \
+                                                                         dalpha_extra, dlse, H, D, dlogit, ds_self,      \
+                                                                         drop, hub, mode, r_buf)
     unsigned grid = (unsigned)msha_cdiv(n_rows, GAT_WARPS);
     int mode = 0;
     DISPATCH_LAYOUT(vw, vpl, CALL)

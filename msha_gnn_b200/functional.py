@@ -258,7 +258,8 @@ class _AttentionBlock(torch.autograd.Function):
         dlse = _c(d_lse) if d_lse is not None else None
         call("msha_gat_bwd_rows", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr), ptr(s_self), LRELU_SLOPE, ptr(alpha),
              ptr(feat_nbr), ptr(d_rows), ptr(out), act, ptr(dz), ptr(d_cols), ptr(feat_self) if d_cols is not None else None,
-             ptr(extra), ptr(dlse), H, D, ptr(dlogit), ptr(ds_self), p, seed, hub.ptr, ptr(r_buf), _stream())
+             ptr(extra), ptr(dlse), H, D, ptr(dlogit), ptr(ds_self), p, seed, hub.ptr, ptr(r_buf),
+             int(alpha.shape[0] // max(N, 1)), _stream())
         dzz = dz if dz is not None else d_rows
         dfeat_nbr = torch.empty((M, C), dtype=torch.float32, device=dev)
         ds_nbr = torch.empty((M, H), dtype=torch.float32, device=dev)
