@@ -23,8 +23,11 @@ constexpr int UMMA_K = 8;
 constexpr int NUM_THREADS = 512;
 constexpr int PROD_THREADS = 256;             // warps 4-11 of the forward / dZ kernels (gather + split producers)
 constexpr int CVT_THREADS = 128;              // warps 4-7 of the dW kernel (TMA tile converters)
-constexpr int EPI_WARPS = 4;                  // warps 12-15: one per TMEM lane quarter
+constexpr int EPI_WARPS = 4;                  // dZ kernel, warps 12-15: one per TMEM lane quarter
 constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int FWD_PROD_THREADS = 128;         // forward kernel: warps 4-7 gather (L2-resident tables, prefetched),
+constexpr int FWD_EPI_WARPS = 8;              //                 warps 8-15 run the store-heavy epilogue
+constexpr int FWD_EPI_THREADS = FWD_EPI_WARPS * 32;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;
 
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
@@ -51,7 +54,7 @@ struct SCfg {
     static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BLOCK_N;
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BAR_OFF = EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int BAR_OFF = EPI_OFF + FWD_EPI_WARPS * EPI_STAGE_BYTES;
     static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 512;
 };
 
@@ -109,13 +112,13 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S::STAGES; ++s) {
-            mbar_init(smem_u32(&full_a[s]), PROD_THREADS);
+            mbar_init(smem_u32(&full_a[s]), FWD_PROD_THREADS);
             mbar_init(smem_u32(&full_b[s]), 1);
             mbar_init(smem_u32(&empty[s]), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tmem_full[a]), 1);
-            mbar_init(smem_u32(&tmem_empty[a]), EPI_THREADS);
+            mbar_init(smem_u32(&tmem_empty[a]), FWD_EPI_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -183,19 +186,20 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 12) {
+    } else if (warp >= 4 && warp < 8) {
         // ---------------- A producers: gather h_i[src], h_j[dst], multiply, split, store swizzled ----------------
+        constexpr int RPT = 4, RSTEP = 32;                       // rows per thread, row stride between them
         const int tid = threadIdx.x - 128;
-        const int c = tid & 3, rbase = tid >> 2;                 // 16-byte chunk c of rows rbase, rbase + 64
+        const int c = tid & 3, rbase = tid >> 2;                 // 16-byte chunk c of rows rbase + 32*i
         uint32_t stage = 0, phase = 0;
         for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
             const int64_t m0 = t * BLOCK_M;
-            const float* pa[2];
-            const float* pb[2];
-            bool valid[2];
+            const float* pa[RPT];
+            const float* pb[RPT];
+            bool valid[RPT];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int64_t p = m0 + rbase + 64 * i;
+            for (int i = 0; i < RPT; ++i) {
+                const int64_t p = m0 + rbase + RSTEP * i;
                 valid[i] = p < P;
                 const int64_t si = valid[i] ? (src ? src[p] : p) : 0;
                 const int64_t dj = valid[i] ? (dst ? dst[p] : p) : 0;
@@ -203,12 +207,12 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
                 pb[i] = hj_tab + dj * C + c * 4;
             }
             // gathers are software-pipelined one k-block ahead (L2 latency ~ one stage of MMA work)
-            float4 a[2], b[2], an[2], bn[2];
-            auto load = [&](int kb, float4 (&x)[2], float4 (&y)[2]) {
+            float4 a[RPT], b[RPT], an[RPT], bn[RPT];
+            auto load = [&](int kb, float4 (&x)[RPT], float4 (&y)[RPT]) {
                 const int k = kb * BLOCK_K;
                 const bool kvalid = (kb < total_kb) && (k + c * 4 < C);
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < RPT; ++i) {
                     if (valid[i] && kvalid) {
                         x[i] = ldg4(pa[i] + k);
                         y[i] = ldg4(pb[i] + k);
@@ -224,13 +228,13 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
                 mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                 uint8_t* st = smem + stage * S::STAGE_BYTES;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < RPT; ++i) {
                     float4 h, l;
                     split_tf32(a[i].x * b[i].x, h.x, l.x);
                     split_tf32(a[i].y * b[i].y, h.y, l.y);
                     split_tf32(a[i].z * b[i].z, h.z, l.z);
                     split_tf32(a[i].w * b[i].w, h.w, l.w);
-                    const uint32_t off = sw64_offset(rbase + 64 * i, c);
+                    const uint32_t off = sw64_offset(rbase + RSTEP * i, c);
                     *reinterpret_cast<float4*>(st + off) = h;
                     *reinterpret_cast<float4*>(st + S::A_BYTES + off) = l;
                 }
@@ -238,15 +242,14 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
                 mbar_arrive(smem_u32(&full_a[stage]));
                 if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
-                for (int i = 0; i < 2; ++i) { a[i] = an[i]; b[i] = bn[i]; }
+                for (int i = 0; i < RPT; ++i) { a[i] = an[i]; b[i] = bn[i]; }
             }
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 8) {
         // ---------------- epilogue ----------------
-        const int q = warp & 3;
-        constexpr int hf = 0;
-        constexpr int COLS_PER_WARP = BLOCK_N;
-        float* stage_buf = (float*)(smem + S::EPI_OFF + (warp - 12) * EPI_STAGE_BYTES);
+        const int q = warp & 3, hf = (warp - 8) >> 2;
+        constexpr int COLS_PER_WARP = BLOCK_N / 2;
+        float* stage_buf = (float*)(smem + S::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
         const bool vec_ok = ((ldo & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
         uint32_t acc = 0, acc_phase = 0;
         for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
