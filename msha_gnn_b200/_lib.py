@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = list(NVCC_FLAGS)
+    flags = list(NVCC_FLAGS) + os.environ.get("MSHA_NVCC_EXTRA", "").split()     # e.g. -DMSHA_DZ_PROD_WARPS=8 (tuning)
     objs = []
     obj_dir = os.path.join(_PKG_DIR, "build")
     os.makedirs(obj_dir, exist_ok=True)

@@ -21,12 +21,18 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 16;
 constexpr int UMMA_K = 8;
 constexpr int NUM_THREADS = 512;
-constexpr int PROD_THREADS = 256;             // warps 4-11 of the forward / dZ kernels (gather + split producers)
+constexpr int PROD_THREADS = 256;             // warps 8-15 of the dW kernel (Z gather producers)
 constexpr int CVT_THREADS = 128;              // warps 4-7 of the dW kernel (TMA tile converters)
-constexpr int EPI_WARPS = 4;                  // dZ kernel, warps 12-15: one per TMEM lane quarter
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int FWD_PROD_THREADS = 128;         // forward kernel: warps 4-7 gather (L2-resident tables, prefetched),
-constexpr int FWD_EPI_WARPS = 8;              //                 warps 8-15 run the store-heavy epilogue
+constexpr int FWD_PROD_THREADS = 128;         // forward kernel: warps 4-7 produce the A tile (pair gather),
+constexpr int FWD_EPI_WARPS = 8;              //                       warps 8-15 run the store / scatter epilogue
+#ifndef MSHA_DZ_PROD_WARPS
+#define MSHA_DZ_PROD_WARPS 4
+#endif
+constexpr int DZ_PROD_WARPS = MSHA_DZ_PROD_WARPS;    // dZ kernel: warps 4.. turn the TMA-staged dOut / out tiles into G_hi / G_lo,
+constexpr int DZ_PROD_THREADS = DZ_PROD_WARPS * 32;
+constexpr int DZ_EPI_WARPS = 12 - DZ_PROD_WARPS;     //            the remaining warps scatter (TMEM lane quarter = warp % 4)
+constexpr int DZ_EPI_THREADS = DZ_EPI_WARPS * 32;
+static_assert(DZ_EPI_WARPS == 4 || DZ_EPI_WARPS == 8, "epilogue warps come in groups of four");
 constexpr int FWD_EPI_THREADS = FWD_EPI_WARPS * 32;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;
 
@@ -317,7 +323,7 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                    const float* __restrict__ dout, const float* __restrict__ outp, int act, float slope,
+                    const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY, int act, float slope,
                     float* __restrict__ G, float* __restrict__ db, const float* __restrict__ hi_tab,
                     const float* __restrict__ hj_tab, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                     int64_t P, int K /*hidden*/, int N /*C*/, float* __restrict__ dhi, float* __restrict__ dhj) {
@@ -338,16 +344,18 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBh) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBl) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmD) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmY) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S::STAGES; ++s) {
-            mbar_init(smem_u32(&full_a[s]), PROD_THREADS);
+            mbar_init(smem_u32(&full_a[s]), DZ_PROD_THREADS);
             mbar_init(smem_u32(&full_b[s]), 1);
             mbar_init(smem_u32(&empty[s]), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tmem_full[a]), 1);
-            mbar_init(smem_u32(&tmem_empty[a]), EPI_THREADS);
+            mbar_init(smem_u32(&tmem_empty[a]), DZ_EPI_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -372,9 +380,12 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     uint8_t* st = smem + stage * S::STAGE_BYTES;
+                    const uint32_t a_d = smem_u32(st), a_y = a_d + S::A_BYTES;
                     const uint32_t b_hi = smem_u32(st + 2 * S::A_BYTES), b_lo = b_hi + S::B_BYTES;
                     const uint32_t bar = smem_u32(&full_b[stage]);
-                    mbar_arrive_expect_tx(bar, 2 * S::B_BYTES);
+                    mbar_arrive_expect_tx(bar, 2 * S::A_BYTES + 2 * S::B_BYTES);
+                    tma_load_2d(a_d, &tmD, bar, kb * BLOCK_K, (int)(t * BLOCK_M));      // dOut tile -> becomes G_hi in place
+                    tma_load_2d(a_y, &tmY, bar, kb * BLOCK_K, (int)(t * BLOCK_M));      // out  tile -> becomes G_lo in place
                     tma_load_2d(b_hi, &tmBh, bar, kb * BLOCK_K, 0);
                     tma_load_2d(b_lo, &tmBl, bar, kb * BLOCK_K, 0);
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
@@ -413,64 +424,68 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 12) {
-        // ---------------- producers: G = dOut * act'(out) -> global G, bias-gradient partials, swizzled hi/lo tiles ----
+    } else if (warp >= 4 && warp < 4 + DZ_PROD_WARPS) {
+        // ---------------- producers: the TMA-staged dOut / out tiles become G_hi / G_lo in place; G also goes to HBM
+        // (for the dW kernel) and its column sums (bias gradient) accumulate in registers ----
+        constexpr int RSTEP = DZ_PROD_THREADS / 4, RPT = BLOCK_M / RSTEP;
         const int tid = threadIdx.x - 128;
-        const int c = tid & 3, rbase = tid >> 2;                 // 16-byte chunk c of rows rbase, rbase + 64
+        const int c = tid & 3, rbase = tid >> 2;                 // 16-byte chunk c of rows rbase + RSTEP * i
         uint32_t stage = 0, phase = 0;
+        // act'(x) from the output y, branch free:  y > thr ? a0 + y*(a1 + a2*y) : b0 + b1*y
+        float thr = -INFINITY, a0 = 1.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f;
+        switch (act) {
+            case 1: thr = 0.f; b0 = 1.f; b1 = 1.f; break;                       // ELU: 1 | y + 1
+            case 2: thr = 0.f; break;                                            // ReLU: 1 | 0
+            case 3: thr = 0.5f; a0 = 0.f; a1 = 1.f; a2 = -1.f; break;            // sigmoid(relu): y(1-y) | 0
+            case 4: thr = 0.f; b0 = slope; break;                                // LeakyReLU: 1 | slope
+            case 5: a0 = 0.f; a1 = 1.f; a2 = -1.f; break;                        // sigmoid: y(1-y)
+            default: break;
+        }
+        auto dact = [&](float yv) { return yv > thr ? fmaf(yv, fmaf(a2, yv, a1), a0) : fmaf(b1, yv, b0); };
         float4 csum[16];                                         // bias-gradient partials per k-block (K <= 256)
 #pragma unroll
         for (int j = 0; j < 16; ++j) csum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
             const int64_t m0 = t * BLOCK_M;
-            const int64_t p0 = m0 + rbase, p1 = p0 + 64;
-            const bool v0 = p0 < P, v1 = p1 < P;
-            float4 d[2], y[2], dn[2], yn[2];
-            auto load = [&](int kb, float4 (&dd)[2], float4 (&yy)[2]) {
-                const int k = kb * BLOCK_K + c * 4;
-                const bool kvalid = (kb < total_kb) && (k < K);
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                dd[0] = (v0 && kvalid) ? ldg4(dout + p0 * K + k) : z4;
-                yy[0] = (v0 && kvalid) ? ldg4(outp + p0 * K + k) : z4;
-                dd[1] = (v1 && kvalid) ? ldg4(dout + p1 * K + k) : z4;
-                yy[1] = (v1 && kvalid) ? ldg4(outp + p1 * K + k) : z4;
-            };
-            load(0, d, y);
+            uint32_t off[RPT];
+            bool pv[RPT];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                off[i] = sw64_offset(rbase + RSTEP * i, c);
+                pv[i] = m0 + rbase + RSTEP * i < P;
+            }
 #pragma unroll
             for (int kb = 0; kb < 16; ++kb) {
                 if (kb < total_kb) {
-                    load(kb + 1, dn, yn);
                     const int k = kb * BLOCK_K + c * 4;
                     const bool kvalid = k < K;
-                    float4 g[2];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        g[i].x = d[i].x * act_grad_out(y[i].x, act, slope);
-                        g[i].y = d[i].y * act_grad_out(y[i].y, act, slope);
-                        g[i].z = d[i].z * act_grad_out(y[i].z, act, slope);
-                        g[i].w = d[i].w * act_grad_out(y[i].w, act, slope);
-                        csum[kb].x += g[i].x; csum[kb].y += g[i].y; csum[kb].z += g[i].z; csum[kb].w += g[i].w;
-                    }
-                    if (v0 && kvalid) *reinterpret_cast<float4*>(G + p0 * K + k) = g[0];
-                    if (v1 && kvalid) *reinterpret_cast<float4*>(G + p1 * K + k) = g[1];
-                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    mbar_wait(smem_u32(&full_b[stage]), phase);          // dOut / out tiles of this stage have landed
                     uint8_t* st = smem + stage * S::STAGE_BYTES;
+                    float4 d[RPT], y[RPT];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        float4 h, l;
-                        split_tf32(g[i].x, h.x, l.x);
-                        split_tf32(g[i].y, h.y, l.y);
-                        split_tf32(g[i].z, h.z, l.z);
-                        split_tf32(g[i].w, h.w, l.w);
-                        const uint32_t off = sw64_offset(rbase + 64 * i, c);
-                        *reinterpret_cast<float4*>(st + off) = h;
-                        *reinterpret_cast<float4*>(st + S::A_BYTES + off) = l;
+                    for (int i = 0; i < RPT; ++i) {
+                        d[i] = *reinterpret_cast<const float4*>(st + off[i]);
+                        y[i] = *reinterpret_cast<const float4*>(st + S::A_BYTES + off[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < RPT; ++i) {                      // rows beyond P / columns beyond K arrive as zeros
+                        float4 g, h, l;
+                        g.x = d[i].x * dact(y[i].x);
+                        g.y = d[i].y * dact(y[i].y);
+                        g.z = d[i].z * dact(y[i].z);
+                        g.w = d[i].w * dact(y[i].w);
+                        csum[kb].x += g.x; csum[kb].y += g.y; csum[kb].z += g.z; csum[kb].w += g.w;
+                        if (pv[i] && kvalid) *reinterpret_cast<float4*>(G + (m0 + rbase + RSTEP * i) * K + k) = g;
+                        split_tf32(g.x, h.x, l.x);
+                        split_tf32(g.y, h.y, l.y);
+                        split_tf32(g.z, h.z, l.z);
+                        split_tf32(g.w, h.w, l.w);
+                        *reinterpret_cast<float4*>(st + off[i]) = h;                    // in place: G_hi over the dOut tile
+                        *reinterpret_cast<float4*>(st + S::A_BYTES + off[i]) = l;       //           G_lo over the out tile
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_arrive(smem_u32(&full_a[stage]));
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) { d[i] = dn[i]; y[i] = yn[i]; }
                 }
             }
         }
@@ -495,15 +510,18 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                 }
             }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(DZ_PROD_THREADS) : "memory");
         if (db != nullptr)
-            for (int k = tid; k < K; k += PROD_THREADS) atomicAdd(db + k, db_sm[k]);
-    } else if (warp >= 12) {
+            for (int k = tid; k < K; k += DZ_PROD_THREADS) atomicAdd(db + k, db_sm[k]);
+    } else if (warp >= 4 + DZ_PROD_WARPS) {
         // ---------------- epilogue: dZ tile -> dh_i[src] += dZ * h_j[dst],  dh_j[dst] += dZ * h_i[src] ----------------
-        const int q = warp & 3;
-        constexpr int hf = 0;
-        constexpr int COLS_PER_WARP = BLOCK_N;
-        float* stage_buf = (float*)(smem + S::EPI_OFF + (warp - 12) * EPI_STAGE_BYTES);
+        // The gathers of h_i / h_j do not depend on the accumulator, so they run one batch (4 row groups x 2 tables =
+        // 8 x 16 B per lane) ahead of the multiply + atomics, ping-ponging between two register buffers.
+        const int ew = warp - (4 + DZ_PROD_WARPS);
+        const int q = warp & 3, hf = ew >> 2;
+        constexpr int COLS_PER_WARP = BLOCK_N / (DZ_EPI_WARPS / 4);
+        float* stage_buf = (float*)(smem + S::EPI_OFF + ew * EPI_STAGE_BYTES);
+        const int rs = lane >> 3, cg = lane & 7;
         uint32_t acc = 0, acc_phase = 0;
         for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
             const int64_t row0 = t * BLOCK_M + q * 32;
@@ -513,6 +531,35 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                 s_l = (int)(src ? src[prow] : prow);
                 d_l = (int)(dst ? dst[prow] : prow);
             }
+            auto gather = [&](int nb, int kh, float4 (&xi)[4], float4 (&xj)[4]) {
+                const int col = nb + 4 * cg;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int r = 4 * (4 * kh + kk) + rs;
+                    const int si = __shfl_sync(0xffffffffu, s_l, r), dj = __shfl_sync(0xffffffffu, d_l, r);
+                    if ((row0 + r < P) && (col < N)) {                 // N % 4 == 0
+                        xj[kk] = ldg4(hj_tab + (int64_t)dj * N + col);
+                        xi[kk] = ldg4(hi_tab + (int64_t)si * N + col);
+                    }
+                }
+            };
+            auto scatter = [&](int nb, int kh, const float4 (&xi)[4], const float4 (&xj)[4]) {
+                const int col = nb + 4 * cg;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int r = 4 * (4 * kh + kk) + rs;
+                    const int si = __shfl_sync(0xffffffffu, s_l, r), dj = __shfl_sync(0xffffffffu, d_l, r);
+                    if ((row0 + r < P) && (col < N)) {
+                        const float4 dz = *reinterpret_cast<const float4*>(stage_buf + r * 32 + ((cg ^ (r & 7)) << 2));
+                        atomicAdd(reinterpret_cast<float4*>(dhi + (int64_t)si * N + col),
+                                  make_float4(dz.x * xj[kk].x, dz.y * xj[kk].y, dz.z * xj[kk].z, dz.w * xj[kk].w));
+                        atomicAdd(reinterpret_cast<float4*>(dhj + (int64_t)dj * N + col),
+                                  make_float4(dz.x * xi[kk].x, dz.y * xi[kk].y, dz.z * xi[kk].z, dz.w * xi[kk].w));
+                    }
+                }
+            };
+            float4 xi0[4], xj0[4], xi1[4], xj1[4];
+            gather(hf * COLS_PER_WARP, 0, xi0, xj0);             // in flight while the accumulator finishes
             mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
             tcgen05_fence_after();
 #pragma unroll 1
@@ -520,43 +567,16 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                 const int nb = hf * COLS_PER_WARP + cc;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + nb, v);
-                if (nb >= N) continue;
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
                     *reinterpret_cast<float4*>(stage_buf + lane * 32 + ((g ^ (lane & 7)) << 2)) =
                         make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
                                     __uint_as_float(v[4 * g + 3]));
                 __syncwarp();
-                const int rs = lane >> 3, cg = lane & 7;
-                const int col = nb + 4 * cg;
-#pragma unroll
-                for (int kh = 0; kh < 2; ++kh) {             // two batches of 4 row groups: 8 gathers in flight per lane
-                    float4 dzv[4], xi[4], xj[4];
-                    int si[4], dj[4];
-                    bool ok[4];
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const int r = 4 * (4 * kh + kk) + rs;
-                        dzv[kk] = *reinterpret_cast<const float4*>(stage_buf + r * 32 + ((cg ^ (r & 7)) << 2));
-                        si[kk] = __shfl_sync(0xffffffffu, s_l, r);
-                        dj[kk] = __shfl_sync(0xffffffffu, d_l, r);
-                        ok[kk] = (row0 + r < P) && (col < N);          // N % 4 == 0
-                        if (ok[kk]) {
-                            xj[kk] = ldg4(hj_tab + (int64_t)dj[kk] * N + col);
-                            xi[kk] = ldg4(hi_tab + (int64_t)si[kk] * N + col);
-                        }
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        if (ok[kk]) {
-                            const float4 dz = dzv[kk];
-                            atomicAdd(reinterpret_cast<float4*>(dhi + (int64_t)si[kk] * N + col),
-                                      make_float4(dz.x * xj[kk].x, dz.y * xj[kk].y, dz.z * xj[kk].z, dz.w * xj[kk].w));
-                            atomicAdd(reinterpret_cast<float4*>(dhj + (int64_t)dj[kk] * N + col),
-                                      make_float4(dz.x * xi[kk].x, dz.y * xi[kk].y, dz.z * xi[kk].z, dz.w * xi[kk].w));
-                        }
-                    }
-                }
+                gather(nb, 1, xi1, xj1);
+                scatter(nb, 0, xi0, xj0);
+                if (cc + 32 < COLS_PER_WARP) gather(nb + 32, 0, xi0, xj0);
+                scatter(nb, 1, xi1, xj1);
                 __syncwarp();
             }
             tcgen05_fence_before();
@@ -857,6 +877,11 @@ template <int BN>
 int launch_dz(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* dout, const float* outp, int act, float slope,
               float* G, float* db, const float* hi_tab, const float* hj_tab, const int64_t* src, const int64_t* dst, int64_t P,
               int Hd, int C, float* dhi, float* dhj, cudaStream_t st) {
+    CUtensorMap td, ty;                                   // dOut / out as K-major [P, Hd] operands, boxes {16, 128}
+    int rcm = tc_make_map(&td, dout, Hd, P, Hd, BLOCK_K, BLOCK_M, false);
+    if (rcm) return rcm;
+    rcm = tc_make_map(&ty, outp, Hd, P, Hd, BLOCK_K, BLOCK_M, false);
+    if (rcm) return rcm;
     auto kern = score_bwd_dz_kernel<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -865,7 +890,7 @@ int launch_dz(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* dout,
     }
     const int64_t m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
     const int grid = (int)(m_tiles < MSHA_NUM_SMS ? m_tiles : MSHA_NUM_SMS);
-    kern<<<grid, NUM_THREADS, SCfg<BN>::SMEM_BYTES, st>>>(tbh, tbl, dout, outp, act, slope, G, db, hi_tab, hj_tab, src, dst, P, Hd,
+    kern<<<grid, NUM_THREADS, SCfg<BN>::SMEM_BYTES, st>>>(tbh, tbl, td, ty, act, slope, G, db, hi_tab, hj_tab, src, dst, P, Hd,
                                                          C, dhi, dhj);
     MSHA_LAUNCH_OK();
     return 0;
