@@ -183,30 +183,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(smem_u32(&full_raw[stage]), phase);
                 uint8_t* st = smem + stage * C::STAGE_BYTES;
-                uint4* a_hi = (uint4*)st;
-                uint4* a_lo = (uint4*)(st + C::A_BYTES);
-                uint4* b_hi = (uint4*)(st + 2 * C::A_BYTES);
-                uint4* b_lo = (uint4*)(st + 2 * C::A_BYTES + C::B_BYTES);
-#pragma unroll 4
-                for (int c = tid; c < C::A_BYTES / 16; c += CVT_THREADS) {
-                    uint4 x = a_hi[c], h, l;
-                    h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
-                    l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
-                    l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
-                    l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
-                    l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
-                    a_hi[c] = h; a_lo[c] = l;
-                }
-#pragma unroll 4
-                for (int c = tid; c < C::B_BYTES / 16; c += CVT_THREADS) {
-                    uint4 x = b_hi[c], h, l;
-                    h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
-                    l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
-                    l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
-                    l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
-                    l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
-                    b_hi[c] = h; b_lo[c] = l;
-                }
+                const uint32_t a_hi = smem_u32(st), b_hi = a_hi + 2 * C::A_BYTES;
+                split_tile_inplace(a_hi, a_hi + C::A_BYTES, C::A_BYTES / 16, tid, CVT_THREADS);
+                split_tile_inplace(b_hi, b_hi + C::B_BYTES, C::B_BYTES / 16, tid, CVT_THREADS);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
                 mbar_arrive(smem_u32(&full_cvt[stage]));
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -217,7 +196,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // warp -> TMEM lane quarter q (rows 32q..32q+31 of the tile) and column half `hf`
         const int q = warp & 3, hf = (warp - 8) >> 2;
         constexpr int COLS_PER_WARP = BLOCK_N / 2;
-        float* stage_buf = (float*)(smem + C::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
+        const uint32_t stage_s = smem_u32(smem + C::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
         const bool vec_ok = ((ldc & 3) == 0) && ((((uintptr_t)Cmat) & 15) == 0);
         uint32_t acc = 0, acc_phase = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -274,14 +253,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 // transpose through shared memory (16-byte chunks XOR-swizzled by row) -> coalesced 128 B row stores
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
-                    *reinterpret_cast<float4*>(stage_buf + lane * 32 + ((g ^ (lane & 7)) << 2)) =
-                        make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+                    sts128(stage_s + (uint32_t)(lane * 32 + ((g ^ (lane & 7)) << 2)) * 4u,
+                           make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]));
                 __syncwarp();
                 const int rs = lane >> 3, cg = lane & 7;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int r = 4 * k + rs;
-                    const float4 o = *reinterpret_cast<const float4*>(stage_buf + r * 32 + ((cg ^ (r & 7)) << 2));
+                    const float4 o = lds128(stage_s + (uint32_t)(r * 32 + ((cg ^ (r & 7)) << 2)) * 4u);
                     const int row = row0 + r, col = nb + 4 * cg;
                     if (row < M) {
                         float* cp = Cmat + (int64_t)row * ldc + col;

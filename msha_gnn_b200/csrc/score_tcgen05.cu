@@ -23,7 +23,7 @@ constexpr int UMMA_K = 8;
 constexpr int NUM_THREADS = 512;
 constexpr int PROD_THREADS = 256;             // warps 8-15 of the dW kernel (Z gather producers)
 constexpr int CVT_THREADS = 128;              // warps 4-7 of the dW kernel (TMA tile converters)
-constexpr int FWD_PROD_THREADS = 128;         // forward kernel: warps 4-7 produce the A tile (pair gather),
+constexpr int FWD_PROD_WARPS = 4;              // forward kernel: warps 4-7 produce the A tile (pair gather),
 constexpr int FWD_EPI_WARPS = 8;              //                       warps 8-15 run the store / scatter epilogue
 #ifndef MSHA_DZ_PROD_WARPS
 #define MSHA_DZ_PROD_WARPS 4
@@ -31,9 +31,7 @@ constexpr int FWD_EPI_WARPS = 8;              //                       warps 8-1
 constexpr int DZ_PROD_WARPS = MSHA_DZ_PROD_WARPS;    // dZ kernel: warps 4.. turn the TMA-staged dOut / out tiles into G_hi / G_lo,
 constexpr int DZ_PROD_THREADS = DZ_PROD_WARPS * 32;
 constexpr int DZ_EPI_WARPS = 12 - DZ_PROD_WARPS;     //            the remaining warps scatter (TMEM lane quarter = warp % 4)
-constexpr int DZ_EPI_THREADS = DZ_EPI_WARPS * 32;
 static_assert(DZ_EPI_WARPS == 4 || DZ_EPI_WARPS == 8, "epilogue warps come in groups of four");
-constexpr int FWD_EPI_THREADS = FWD_EPI_WARPS * 32;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;
 
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
@@ -41,23 +39,13 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, 
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float act_grad_out(float y, int act, float slope) {
-    switch (act) {
-        case 1: return y > 0.f ? 1.f : y + 1.f;
-        case 2: return y > 0.f ? 1.f : 0.f;
-        case 3: return y > 0.5f ? y * (1.f - y) : 0.f;
-        case 4: return y > 0.f ? 1.f : slope;
-        case 5: return y * (1.f - y);
-        default: return 1.f;
-    }
-}
-
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS>
 struct SCfg {
-    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;          // 8 KB per hi / lo tile
-    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;          // 8 KB per hi / lo tile (this CTA's 128 rows)
+    static constexpr int B_ROWS = BLOCK_N / CTAS;                  // a CTA of a pair stages half of the B tile
+    static constexpr int B_BYTES = B_ROWS * BLOCK_K * 4;
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
-    static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES < 8 ? (192 * 1024) / STAGE_BYTES : 8;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
     static constexpr int BAR_OFF = EPI_OFF + FWD_EPI_WARPS * EPI_STAGE_BYTES;
@@ -92,25 +80,85 @@ __device__ __forceinline__ void act32(float (&x)[32], int act, float slope) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Shared skeleton of the forward and dZ kernels.  CTAS = 2 runs them as CTA pairs (2-CTA cluster, tcgen05 cta_group::2):
+// the pair computes a 256-row tile, each CTA keeps its own 128 A rows / accumulator rows and only HALF of the B tile
+// (W0 slices come from L2 for every tile, so this halves the dominant shared-memory fill traffic per SM).  The even CTA
+// issues the MMAs and owns the full_a / full_b / tmem_empty barriers; empty / tmem_full are signalled in both CTAs by a
+// multicast commit.
+// ------------------------------------------------------------------------------------------------
+template <int CTAS>
+__device__ __forceinline__ void pair_sync() {
+    if constexpr (CTAS == 2) cluster_sync_all();
+    else __syncthreads();
+}
+// one arrival per warp on a barrier of the MMA-issuing CTA (callers order their own writes first)
+template <int CTAS>
+__device__ __forceinline__ void warp_arrive_leader(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_remote(bar, 0);
+        else mbar_arrive(bar);
+    }
+}
+template <int CTAS>
+__device__ __forceinline__ void wait_leader_bar(uint32_t bar, uint32_t parity) {
+    if constexpr (CTAS == 2) mbar_wait_cluster(bar, parity);
+    else mbar_wait(bar, parity);
+}
+template <int CTAS>
+__device__ __forceinline__ void load_b_slice(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    if constexpr (CTAS == 2) tma_load_2d_pair(dst, map, bar, c0, c1);
+    else tma_load_2d(dst, map, bar, c0, c1);
+}
+// the three MMAs of the 3xTF32 product for one k-block, then release the stage
+template <int BLOCK_N, int CTAS, class S>
+__device__ __forceinline__ void issue_kblock(uint8_t* st, uint32_t tmem_d, bool first, uint32_t empty_bar) {
+    constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M * CTAS, BLOCK_N, false, false);
+    const uint32_t a_hi = smem_u32(st), a_lo = a_hi + S::A_BYTES;
+    const uint32_t b_hi = a_hi + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+        const uint64_t dah = make_smem_desc(a_hi + k * 32, 16, 512, 4);
+        const uint64_t dal = make_smem_desc(a_lo + k * 32, 16, 512, 4);
+        const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 512, 4);
+        const uint64_t dbl = make_smem_desc(b_lo + k * 32, 16, 512, 4);
+        const uint32_t accum = (!first || k > 0) ? 1u : 0u;
+        if constexpr (CTAS == 2) {
+            umma_tf32_pair(tmem_d, dal, dbh, idesc, accum);
+            umma_tf32_pair(tmem_d, dah, dbl, idesc, 1u);
+            umma_tf32_pair(tmem_d, dah, dbh, idesc, 1u);
+        } else {
+            umma_tf32(tmem_d, dal, dbh, idesc, accum);
+            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+        }
+    }
+    if constexpr (CTAS == 2) tcgen05_commit_pair(empty_bar);
+    else tcgen05_commit(empty_bar);
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused forward
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                  const float* __restrict__ hi_tab, const float* __restrict__ hj_tab, const int64_t* __restrict__ src,
                  const int64_t* __restrict__ dst, int64_t P, int C, int N, const float* __restrict__ bias, int act,
                  float slope, float* __restrict__ out, int64_t ldo) {
-    using S = SCfg<BLOCK_N>;
+    using S = SCfg<BLOCK_N, CTAS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + S::BAR_OFF);
     uint64_t* full_a = bars;
     uint64_t* full_b = bars + S::STAGES;
     uint64_t* empty = bars + 2 * S::STAGES;
-    uint64_t* tmem_full = bars + 3 * S::STAGES;
-    uint64_t* tmem_empty = bars + 3 * S::STAGES + 2;
-    uint32_t* tmem_ptr = (uint32_t*)(bars + 3 * S::STAGES + 4);
+    uint64_t* tmem_full = bars + 4 * S::STAGES;
+    uint64_t* tmem_empty = bars + 4 * S::STAGES + 2;
+    uint32_t* tmem_ptr = (uint32_t*)(bars + 4 * S::STAGES + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank = 0;
+    if constexpr (CTAS == 2) rank = cluster_ctarank();
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBh) : "memory");
@@ -118,88 +166,73 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S::STAGES; ++s) {
-            mbar_init(smem_u32(&full_a[s]), FWD_PROD_THREADS);
+            mbar_init(smem_u32(&full_a[s]), CTAS * FWD_PROD_WARPS);
             mbar_init(smem_u32(&full_b[s]), 1);
             mbar_init(smem_u32(&empty[s]), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tmem_full[a]), 1);
-            mbar_init(smem_u32(&tmem_empty[a]), FWD_EPI_THREADS);
+            mbar_init(smem_u32(&tmem_empty[a]), CTAS * FWD_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                     "r"((uint32_t)S::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 2) tmem_alloc<CTAS>(smem_u32(tmem_ptr), (uint32_t)S::TMEM_COLS);
     tcgen05_fence_before();
     __syncthreads();
+    pair_sync<CTAS>();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     const int64_t m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
+    const int64_t pair_tiles = (m_tiles + CTAS - 1) / CTAS;
+    const int64_t tp0 = blockIdx.x / CTAS, tp_step = gridDim.x / CTAS;
     const int total_kb = (C + BLOCK_K - 1) / BLOCK_K;
 
     if (warp == 0) {
-        // ---------------- TMA producer for the (pre-split) weights ----------------
+        // ---------------- TMA producer for this CTA's slice of the (pre-split) weights ----------------
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+            for (int64_t tp = tp0; tp < pair_tiles; tp += tp_step) {
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     uint8_t* st = smem + stage * S::STAGE_BYTES;
                     const uint32_t b_hi = smem_u32(st + 2 * S::A_BYTES), b_lo = b_hi + S::B_BYTES;
                     const uint32_t bar = smem_u32(&full_b[stage]);
-                    mbar_arrive_expect_tx(bar, 2 * S::B_BYTES);
-                    tma_load_2d(b_hi, &tmBh, bar, kb * BLOCK_K, 0);
-                    tma_load_2d(b_lo, &tmBl, bar, kb * BLOCK_K, 0);
+                    if (rank == 0) mbar_arrive_expect_tx(bar, CTAS * 2 * S::B_BYTES);
+                    load_b_slice<CTAS>(b_hi, &tmBh, bar, kb * BLOCK_K, (int)rank * S::B_ROWS);
+                    load_b_slice<CTAS>(b_lo, &tmBl, bar, kb * BLOCK_K, (int)rank * S::B_ROWS);
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, false, false);
+        // ---------------- MMA issuer (even CTA of a pair) ----------------
+        if (lane == 0 && rank == 0) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-                mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+            for (int64_t tp = tp0; tp < pair_tiles; tp += tp_step) {
+                wait_leader_bar<CTAS>(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(smem_u32(&full_b[stage]), phase);
-                    mbar_wait(smem_u32(&full_a[stage]), phase);
+                    wait_leader_bar<CTAS>(smem_u32(&full_a[stage]), phase);
                     tcgen05_fence_after();
-                    uint8_t* st = smem + stage * S::STAGE_BYTES;
-                    const uint32_t a_hi = smem_u32(st), a_lo = a_hi + S::A_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t dah = make_smem_desc(a_hi + k * 32, 16, 512, 4);
-                        const uint64_t dal = make_smem_desc(a_lo + k * 32, 16, 512, 4);
-                        const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 512, 4);
-                        const uint64_t dbl = make_smem_desc(b_lo + k * 32, 16, 512, 4);
-                        umma_tf32(tmem_d, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-                    }
-                    tcgen05_commit(smem_u32(&empty[stage]));
+                    issue_kblock<BLOCK_N, CTAS, S>(smem + stage * S::STAGE_BYTES, tmem_d, kb == 0, smem_u32(&empty[stage]));
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
-                tcgen05_commit(smem_u32(&tmem_full[acc]));
+                if constexpr (CTAS == 2) tcgen05_commit_pair(smem_u32(&tmem_full[acc]));
+                else tcgen05_commit(smem_u32(&tmem_full[acc]));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 4 + FWD_PROD_WARPS) {
         // ---------------- A producers: gather h_i[src], h_j[dst], multiply, split, store swizzled ----------------
         constexpr int RPT = 4, RSTEP = 32;                       // rows per thread, row stride between them
         const int tid = threadIdx.x - 128;
         const int c = tid & 3, rbase = tid >> 2;                 // 16-byte chunk c of rows rbase + 32*i
         uint32_t stage = 0, phase = 0;
-        for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-            const int64_t m0 = t * BLOCK_M;
+        for (int64_t tp = tp0; tp < pair_tiles; tp += tp_step) {
+            const int64_t m0 = (tp * CTAS + rank) * BLOCK_M;
             const float* pa[RPT];
             const float* pb[RPT];
             bool valid[RPT];
@@ -241,25 +274,31 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
                     split_tf32(a[i].z * b[i].z, h.z, l.z);
                     split_tf32(a[i].w * b[i].w, h.w, l.w);
                     const uint32_t off = sw64_offset(rbase + RSTEP * i, c);
-                    *reinterpret_cast<float4*>(st + off) = h;
-                    *reinterpret_cast<float4*>(st + S::A_BYTES + off) = l;
+                    sts128(smem_u32(st) + off, h);
+                    sts128(smem_u32(st) + S::A_BYTES + off, l);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(smem_u32(&full_a[stage]));
+                warp_arrive_leader<CTAS>(smem_u32(&full_a[stage]), lane);
                 if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
                 for (int i = 0; i < RPT; ++i) { a[i] = an[i]; b[i] = bn[i]; }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 4 + FWD_PROD_WARPS) {
         // ---------------- epilogue ----------------
         const int q = warp & 3, hf = (warp - 8) >> 2;
         constexpr int COLS_PER_WARP = BLOCK_N / 2;
-        float* stage_buf = (float*)(smem + S::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
+        const uint32_t stage_s = smem_u32(smem + S::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
         const bool vec_ok = ((ldo & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
         uint32_t acc = 0, acc_phase = 0;
-        for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-            const int64_t row0 = t * BLOCK_M + q * 32;
+        float bias_r[4] = {0.f, 0.f, 0.f, 0.f};                  // this lane's bias of each 32-column chunk of the warp
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int col = hf * COLS_PER_WARP + 32 * u + lane;
+            if (bias != nullptr && 32 * u < COLS_PER_WARP && col < N) bias_r[u] = __ldg(bias + col);
+        }
+        for (int64_t tp = tp0; tp < pair_tiles; tp += tp_step) {
+            const int64_t row0 = (tp * CTAS + rank) * BLOCK_M + q * 32;
             mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
             tcgen05_fence_after();
 #pragma unroll 1
@@ -268,22 +307,21 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + nb, v);
                 if (nb >= N) continue;
-                float bj = 0.f;
-                if (bias != nullptr && nb + lane < N) bj = __ldg(bias + nb + lane);
+                const float bj = cc == 0 ? bias_r[0] : (cc == 32 ? bias_r[1] : (cc == 64 ? bias_r[2] : bias_r[3]));
                 float x[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bj, j);
                 act32(x, act, slope);
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
-                    *reinterpret_cast<float4*>(stage_buf + lane * 32 + ((g ^ (lane & 7)) << 2)) =
-                        make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+                    sts128(stage_s + (uint32_t)(lane * 32 + ((g ^ (lane & 7)) << 2)) * 4u,
+                           make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]));
                 __syncwarp();
                 const int rs = lane >> 3, cg = lane & 7;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int r = 4 * k + rs;
-                    const float4 o = *reinterpret_cast<const float4*>(stage_buf + r * 32 + ((cg ^ (r & 7)) << 2));
+                    const float4 o = lds128(stage_s + (uint32_t)(r * 32 + ((cg ^ (r & 7)) << 2)) * 4u);
                     const int64_t row = row0 + r;
                     const int col = nb + 4 * cg;
                     if (row < P) {
@@ -301,44 +339,47 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
                 __syncwarp();
             }
             tcgen05_fence_before();
-            mbar_arrive(smem_u32(&tmem_empty[acc]));
+            warp_arrive_leader<CTAS>(smem_u32(&tmem_empty[acc]), lane);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tcgen05_fence_before();
     __syncthreads();
+    pair_sync<CTAS>();
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
-                     : "memory");
+        tmem_dealloc<CTAS>(tmem_base, (uint32_t)S::TMEM_COLS);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // fused backward, part 1:  G = dOut * act'(out)  (+ bias gradient),  dZ = G @ W0,  scatter into dh_i / dh_j
-//   A operand: G tile produced by the producer warps from dOut/out (K-major, K = hidden)
-//   B operand: W0^T [C, Hd] pre-split hi/lo by TMA (K-major)
+//   A operand: dOut / out tiles arrive by TMA and are turned into G_hi / G_lo in place (K-major, K = hidden)
+//   B operand: W0^T [C, Hd] pre-split hi/lo by TMA (K-major), one slice per CTA of the pair
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY, int act, float slope,
                     float* __restrict__ G, float* __restrict__ db, const float* __restrict__ hi_tab,
                     const float* __restrict__ hj_tab, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                     int64_t P, int K /*hidden*/, int N /*C*/, float* __restrict__ dhi, float* __restrict__ dhj) {
-    using S = SCfg<BLOCK_N>;
+    using S = SCfg<BLOCK_N, CTAS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + S::BAR_OFF);
     uint64_t* full_a = bars;
     uint64_t* full_b = bars + S::STAGES;
     uint64_t* empty = bars + 2 * S::STAGES;
-    uint64_t* tmem_full = bars + 3 * S::STAGES;
-    uint64_t* tmem_empty = bars + 3 * S::STAGES + 2;
-    uint32_t* tmem_ptr = (uint32_t*)(bars + 3 * S::STAGES + 4);
+    uint64_t* full_raw = bars + 3 * S::STAGES;               // dOut / out tiles of this CTA have landed (local)
+    uint64_t* tmem_full = bars + 4 * S::STAGES;
+    uint64_t* tmem_empty = bars + 4 * S::STAGES + 2;
+    uint32_t* tmem_ptr = (uint32_t*)(bars + 4 * S::STAGES + 4);
     __shared__ float db_sm[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank = 0;
+    if constexpr (CTAS == 2) rank = cluster_ctarank();
 
     if (threadIdx.x < 256) db_sm[threadIdx.x] = 0.f;
     if (warp == 0 && lane == 0) {
@@ -349,78 +390,68 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S::STAGES; ++s) {
-            mbar_init(smem_u32(&full_a[s]), DZ_PROD_THREADS);
+            mbar_init(smem_u32(&full_a[s]), CTAS * DZ_PROD_WARPS);
             mbar_init(smem_u32(&full_b[s]), 1);
             mbar_init(smem_u32(&empty[s]), 1);
+            mbar_init(smem_u32(&full_raw[s]), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tmem_full[a]), 1);
-            mbar_init(smem_u32(&tmem_empty[a]), DZ_EPI_THREADS);
+            mbar_init(smem_u32(&tmem_empty[a]), CTAS * DZ_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                     "r"((uint32_t)S::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 2) tmem_alloc<CTAS>(smem_u32(tmem_ptr), (uint32_t)S::TMEM_COLS);
     tcgen05_fence_before();
     __syncthreads();
+    pair_sync<CTAS>();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     const int64_t m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
+    const int64_t pair_tiles = (m_tiles + CTAS - 1) / CTAS;
+    const int64_t tp0 = blockIdx.x / CTAS, tp_step = gridDim.x / CTAS;
     const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+            for (int64_t tp = tp0; tp < pair_tiles; tp += tp_step) {
+                const int64_t m0 = (tp * CTAS + rank) * BLOCK_M;
+                const int row_c = (int)(m0 < P ? m0 : P);                // a tile past the end reads zeros
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     uint8_t* st = smem + stage * S::STAGE_BYTES;
                     const uint32_t a_d = smem_u32(st), a_y = a_d + S::A_BYTES;
                     const uint32_t b_hi = smem_u32(st + 2 * S::A_BYTES), b_lo = b_hi + S::B_BYTES;
+                    const uint32_t raw = smem_u32(&full_raw[stage]);
+                    mbar_arrive_expect_tx(raw, 2 * S::A_BYTES);
+                    tma_load_2d(a_d, &tmD, raw, kb * BLOCK_K, row_c);           // dOut tile -> becomes G_hi in place
+                    tma_load_2d(a_y, &tmY, raw, kb * BLOCK_K, row_c);           // out  tile -> becomes G_lo in place
                     const uint32_t bar = smem_u32(&full_b[stage]);
-                    mbar_arrive_expect_tx(bar, 2 * S::A_BYTES + 2 * S::B_BYTES);
-                    tma_load_2d(a_d, &tmD, bar, kb * BLOCK_K, (int)(t * BLOCK_M));      // dOut tile -> becomes G_hi in place
-                    tma_load_2d(a_y, &tmY, bar, kb * BLOCK_K, (int)(t * BLOCK_M));      // out  tile -> becomes G_lo in place
-                    tma_load_2d(b_hi, &tmBh, bar, kb * BLOCK_K, 0);
-                    tma_load_2d(b_lo, &tmBl, bar, kb * BLOCK_K, 0);
+                    if (rank == 0) mbar_arrive_expect_tx(bar, CTAS * 2 * S::B_BYTES);
+                    load_b_slice<CTAS>(b_hi, &tmBh, bar, kb * BLOCK_K, (int)rank * S::B_ROWS);
+                    load_b_slice<CTAS>(b_lo, &tmBl, bar, kb * BLOCK_K, (int)rank * S::B_ROWS);
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, false, false);
+        if (lane == 0 && rank == 0) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-                mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+            for (int64_t tp = tp0; tp < pair_tiles; tp += tp_step) {
+                wait_leader_bar<CTAS>(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(smem_u32(&full_b[stage]), phase);
-                    mbar_wait(smem_u32(&full_a[stage]), phase);
+                    wait_leader_bar<CTAS>(smem_u32(&full_a[stage]), phase);
                     tcgen05_fence_after();
-                    uint8_t* st = smem + stage * S::STAGE_BYTES;
-                    const uint32_t a_hi = smem_u32(st), a_lo = a_hi + S::A_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t dah = make_smem_desc(a_hi + k * 32, 16, 512, 4);
-                        const uint64_t dal = make_smem_desc(a_lo + k * 32, 16, 512, 4);
-                        const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 512, 4);
-                        const uint64_t dbl = make_smem_desc(b_lo + k * 32, 16, 512, 4);
-                        umma_tf32(tmem_d, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-                    }
-                    tcgen05_commit(smem_u32(&empty[stage]));
+                    issue_kblock<BLOCK_N, CTAS, S>(smem + stage * S::STAGE_BYTES, tmem_d, kb == 0, smem_u32(&empty[stage]));
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
-                tcgen05_commit(smem_u32(&tmem_full[acc]));
+                if constexpr (CTAS == 2) tcgen05_commit_pair(smem_u32(&tmem_full[acc]));
+                else tcgen05_commit(smem_u32(&tmem_full[acc]));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -445,8 +476,8 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
         float4 csum[16];                                         // bias-gradient partials per k-block (K <= 256)
 #pragma unroll
         for (int j = 0; j < 16; ++j) csum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-            const int64_t m0 = t * BLOCK_M;
+        for (int64_t tp = tp0; tp < pair_tiles; tp += tp_step) {
+            const int64_t m0 = (tp * CTAS + rank) * BLOCK_M;
             uint32_t off[RPT];
             bool pv[RPT];
 #pragma unroll
@@ -459,13 +490,13 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                 if (kb < total_kb) {
                     const int k = kb * BLOCK_K + c * 4;
                     const bool kvalid = k < K;
-                    mbar_wait(smem_u32(&full_b[stage]), phase);          // dOut / out tiles of this stage have landed
+                    mbar_wait(smem_u32(&full_raw[stage]), phase);        // dOut / out tiles of this stage have landed
                     uint8_t* st = smem + stage * S::STAGE_BYTES;
                     float4 d[RPT], y[RPT];
 #pragma unroll
                     for (int i = 0; i < RPT; ++i) {
-                        d[i] = *reinterpret_cast<const float4*>(st + off[i]);
-                        y[i] = *reinterpret_cast<const float4*>(st + S::A_BYTES + off[i]);
+                        d[i] = lds128(smem_u32(st) + off[i]);
+                        y[i] = lds128(smem_u32(st) + S::A_BYTES + off[i]);
                     }
 #pragma unroll
                     for (int i = 0; i < RPT; ++i) {                      // rows beyond P / columns beyond K arrive as zeros
@@ -480,11 +511,11 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                         split_tf32(g.y, h.y, l.y);
                         split_tf32(g.z, h.z, l.z);
                         split_tf32(g.w, h.w, l.w);
-                        *reinterpret_cast<float4*>(st + off[i]) = h;                    // in place: G_hi over the dOut tile
-                        *reinterpret_cast<float4*>(st + S::A_BYTES + off[i]) = l;       //           G_lo over the out tile
+                        sts128(smem_u32(st) + off[i], h);                               // in place: G_hi over the dOut tile
+                        sts128(smem_u32(st) + S::A_BYTES + off[i], l);                  //           G_lo over the out tile
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive(smem_u32(&full_a[stage]));
+                    warp_arrive_leader<CTAS>(smem_u32(&full_a[stage]), lane);
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -520,11 +551,11 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
         const int ew = warp - (4 + DZ_PROD_WARPS);
         const int q = warp & 3, hf = ew >> 2;
         constexpr int COLS_PER_WARP = BLOCK_N / (DZ_EPI_WARPS / 4);
-        float* stage_buf = (float*)(smem + S::EPI_OFF + ew * EPI_STAGE_BYTES);
+        const uint32_t stage_s = smem_u32(smem + S::EPI_OFF + ew * EPI_STAGE_BYTES);
         const int rs = lane >> 3, cg = lane & 7;
         uint32_t acc = 0, acc_phase = 0;
-        for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-            const int64_t row0 = t * BLOCK_M + q * 32;
+        for (int64_t tp = tp0; tp < pair_tiles; tp += tp_step) {
+            const int64_t row0 = (tp * CTAS + rank) * BLOCK_M + q * 32;
             const int64_t prow = row0 + lane;
             int s_l = 0, d_l = 0;
             if (prow < P) {
@@ -550,7 +581,7 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                     const int r = 4 * (4 * kh + kk) + rs;
                     const int si = __shfl_sync(0xffffffffu, s_l, r), dj = __shfl_sync(0xffffffffu, d_l, r);
                     if ((row0 + r < P) && (col < N)) {
-                        const float4 dz = *reinterpret_cast<const float4*>(stage_buf + r * 32 + ((cg ^ (r & 7)) << 2));
+                        const float4 dz = lds128(stage_s + (uint32_t)(r * 32 + ((cg ^ (r & 7)) << 2)) * 4u);
                         atomicAdd(reinterpret_cast<float4*>(dhi + (int64_t)si * N + col),
                                   make_float4(dz.x * xj[kk].x, dz.y * xj[kk].y, dz.z * xj[kk].z, dz.w * xj[kk].w));
                         atomicAdd(reinterpret_cast<float4*>(dhj + (int64_t)dj * N + col),
@@ -569,9 +600,9 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + nb, v);
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
-                    *reinterpret_cast<float4*>(stage_buf + lane * 32 + ((g ^ (lane & 7)) << 2)) =
-                        make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
-                                    __uint_as_float(v[4 * g + 3]));
+                    sts128(stage_s + (uint32_t)(lane * 32 + ((g ^ (lane & 7)) << 2)) * 4u,
+                           make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                       __uint_as_float(v[4 * g + 3])));
                 __syncwarp();
                 gather(nb, 1, xi1, xj1);
                 scatter(nb, 0, xi0, xj0);
@@ -580,19 +611,20 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                 __syncwarp();
             }
             tcgen05_fence_before();
-            mbar_arrive(smem_u32(&tmem_empty[acc]));
+            warp_arrive_leader<CTAS>(smem_u32(&tmem_empty[acc]), lane);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tcgen05_fence_before();
     __syncthreads();
+    pair_sync<CTAS>();
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
-                     : "memory");
+        tmem_dealloc<CTAS>(tmem_base, (uint32_t)S::TMEM_COLS);
     }
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // fused backward, part 2:  dW0[Hd, C] = G^T @ Z,  Z[p,:] = h_i[src[p]] * h_j[dst[p]] regenerated by gather warps.
@@ -704,19 +736,7 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
         for (int64_t ch = c0; ch < c1; ++ch) {
             mbar_wait(smem_u32(&full_raw[stage]), phase);
             uint8_t* st = smem + stage * W::STAGE_BYTES;
-            uint4* a_hi = (uint4*)st;
-            uint4* a_lo = (uint4*)(st + W::TILE_BYTES);
-            const int n16 = a_chunks * 2048 / 16;
-#pragma unroll 4
-            for (int c = tid; c < n16; c += CVT_THREADS) {
-                uint4 x = a_hi[c], h, l;
-                h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
-                l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
-                l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
-                l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
-                l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
-                a_hi[c] = h; a_lo[c] = l;
-            }
+            split_tile_inplace(smem_u32(st), smem_u32(st) + W::TILE_BYTES, a_chunks * 2048 / 16, tid, CVT_THREADS);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(smem_u32(&full_cvt[stage]));
             if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
@@ -758,8 +778,8 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
                 split_tf32(za[i].w * zb[i].w, h.w, l.w);
                 const int col = j * 4 + 64 * i;                  // channel of this 16-byte chunk
                 const uint32_t off = (col >> 5) * 2048 + sw128b32_offset(kk, (col & 31) >> 2);
-                *reinterpret_cast<float4*>(st + off) = h;
-                *reinterpret_cast<float4*>(st + W::TILE_BYTES + off) = l;
+                sts128(smem_u32(st) + off, h);
+                sts128(smem_u32(st) + W::TILE_BYTES + off, l);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(smem_u32(&full_b[stage]));
@@ -817,22 +837,47 @@ __global__ void split_weights_kernel(const float* __restrict__ w, float* __restr
     lo[i] = l;
 }
 
+#ifndef MSHA_SCORE_CTAS
+#define MSHA_SCORE_CTAS 2
+#endif
+constexpr int SCORE_CTAS = MSHA_SCORE_CTAS;   // 2: forward / dZ kernels run as CTA pairs (cta_group::2); 1: single CTAs
+
+// persistent launch: one CTA (or CTA pair) per SM, tiles strided over the grid
+template <class Kern, class... Args>
+int launch_tiles(Kern kern, int smem_bytes, int64_t m_tiles, cudaStream_t st, Args... args) {
+    const int64_t pair_tiles = (m_tiles + SCORE_CTAS - 1) / SCORE_CTAS;
+    const int max_pairs = MSHA_NUM_SMS / SCORE_CTAS;
+    const int grid = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs) * SCORE_CTAS;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SCORE_CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MSHA_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
 template <int BN>
 int launch_fwd(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* hi_tab, const float* hj_tab, const int64_t* src,
                const int64_t* dst, int64_t P, int C, int N, const float* bias, int act, float slope, float* out, int64_t ldo,
                cudaStream_t st) {
-    auto kern = score_fwd_kernel<BN>;
+    using S = SCfg<BN, SCORE_CTAS>;
+    auto kern = score_fwd_kernel<BN, SCORE_CTAS>;
     static bool attr_set = false;
     if (!attr_set) {
-        MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg<BN>::SMEM_BYTES));
+        MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
         attr_set = true;
     }
-    const int64_t m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
-    const int grid = (int)(m_tiles < MSHA_NUM_SMS ? m_tiles : MSHA_NUM_SMS);
-    kern<<<grid, NUM_THREADS, SCfg<BN>::SMEM_BYTES, st>>>(tbh, tbl, hi_tab, hj_tab, src, dst, P, C, N, bias, act, slope, out,
-                                                         ldo);
-    MSHA_LAUNCH_OK();
-    return 0;
+    return launch_tiles(kern, S::SMEM_BYTES, (P + BLOCK_M - 1) / BLOCK_M, st, tbh, tbl, hi_tab, hj_tab, src, dst, P, C, N, bias,
+                        act, slope, out, ldo);
 }
 
 }  // namespace
@@ -863,9 +908,9 @@ MSHA_API int msha_score_mlp_fwd(const float* hi_tab, const float* hj_tab, const 
     MSHA_LAUNCH_OK();
     const int BN = Hd > 128 ? 256 : (Hd > 64 ? 128 : 64);
     CUtensorMap tbh, tbl;
-    int rc = tc_make_map(&tbh, w_hi, C, Hd, C, BLOCK_K, BN, false);
+    int rc = tc_make_map(&tbh, w_hi, C, Hd, C, BLOCK_K, BN / SCORE_CTAS, false);   // one box per CTA of a pair
     if (rc) return rc;
-    rc = tc_make_map(&tbl, w_lo, C, Hd, C, BLOCK_K, BN, false);
+    rc = tc_make_map(&tbl, w_lo, C, Hd, C, BLOCK_K, BN / SCORE_CTAS, false);
     if (rc) return rc;
     if (BN == 256) return launch_fwd<256>(tbh, tbl, hi_tab, hj_tab, src, dst, P, (int)C, (int)Hd, b0, act, slope, out, ldo, st);
     if (BN == 128) return launch_fwd<128>(tbh, tbl, hi_tab, hj_tab, src, dst, P, (int)C, (int)Hd, b0, act, slope, out, ldo, st);
@@ -882,18 +927,15 @@ int launch_dz(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* dout,
     if (rcm) return rcm;
     rcm = tc_make_map(&ty, outp, Hd, P, Hd, BLOCK_K, BLOCK_M, false);
     if (rcm) return rcm;
-    auto kern = score_bwd_dz_kernel<BN>;
+    using S = SCfg<BN, SCORE_CTAS>;
+    auto kern = score_bwd_dz_kernel<BN, SCORE_CTAS>;
     static bool attr_set = false;
     if (!attr_set) {
-        MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg<BN>::SMEM_BYTES));
+        MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
         attr_set = true;
     }
-    const int64_t m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
-    const int grid = (int)(m_tiles < MSHA_NUM_SMS ? m_tiles : MSHA_NUM_SMS);
-    kern<<<grid, NUM_THREADS, SCfg<BN>::SMEM_BYTES, st>>>(tbh, tbl, td, ty, act, slope, G, db, hi_tab, hj_tab, src, dst, P, Hd,
-                                                         C, dhi, dhj);
-    MSHA_LAUNCH_OK();
-    return 0;
+    return launch_tiles(kern, S::SMEM_BYTES, (P + BLOCK_M - 1) / BLOCK_M, st, tbh, tbl, td, ty, act, slope, G, db, hi_tab,
+                        hj_tab, src, dst, P, Hd, C, dhi, dhj);
 }
 }  // namespace
 
@@ -920,9 +962,9 @@ MSHA_API int msha_score_mlp_bwd(const float* dout, const float* out, const float
     // ---- part 1: G, db0, dZ = G @ W0, scatter
     const int BN = C > 128 ? 256 : (C > 64 ? 128 : 64);
     CUtensorMap tbh, tbl, tg;
-    int rc = tc_make_map(&tbh, wt_hi, Hd, C, Hd, BLOCK_K, BN, false);     // B operand: [N = C rows, K = Hd] K-major
+    int rc = tc_make_map(&tbh, wt_hi, Hd, C, Hd, BLOCK_K, BN / SCORE_CTAS, false);     // B operand: [N = C rows, K = Hd] K-major
     if (rc) return rc;
-    rc = tc_make_map(&tbl, wt_lo, Hd, C, Hd, BLOCK_K, BN, false);
+    rc = tc_make_map(&tbl, wt_lo, Hd, C, Hd, BLOCK_K, BN / SCORE_CTAS, false);
     if (rc) return rc;
     if (BN == 256) rc = launch_dz<256>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, st);
     else if (BN == 128) rc = launch_dz<128>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, st);

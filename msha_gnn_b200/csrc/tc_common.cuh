@@ -52,6 +52,79 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the even CTA of a 2-CTA cluster issues the MMAs for both, each CTA holds its
+// own 128 accumulator rows in TMEM and half of the B tile in shared memory ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  Default (.release.cta) semantics on
+// purpose: a cluster-scope release costs MEMBAR.ALL.GPU, which drains every load / store the thread still has in flight.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta)
+        : "memory");
+}
+// wait on a local barrier whose arrivals may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > SPIN_LIMIT) __trap();
+    } while (!done);
+}
+// TMA load whose completion bytes are counted on the leader CTA's barrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+// commit: one arrival on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <int CTAS>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    if constexpr (CTAS == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+}
+template <int CTAS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    if constexpr (CTAS == 2)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -134,10 +207,52 @@ inline int tc_make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_
     return 0;
 }
 
+// Explicit shared-state-space vector accesses.  Pointers carved out of the dynamic shared buffer are generic to the
+// compiler, which then emits LD.E / ST.E (long-scoreboard latency, no reordering against global stores or atomics).
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // split x into hi (exact in tf32) and lo = x - hi
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
     lo = x - hi;
+}
+
+// In-place hi/lo split of a TMA-staged fp32 tile: n16 16-byte chunks at `hi` become the tf32-exact parts, the
+// remainders go to the same offsets at `lo`.  Loads are batched four deep ahead of the dependent stores.
+__device__ __forceinline__ void split_tile_inplace(uint32_t hi, uint32_t lo, int n16, int tid, int nthreads) {
+    int c = tid;
+    for (; c + 3 * nthreads < n16; c += 4 * nthreads) {
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = lds128(hi + (uint32_t)(c + u * nthreads) * 16u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float4 h, l;
+            split_tf32(x[u].x, h.x, l.x);
+            split_tf32(x[u].y, h.y, l.y);
+            split_tf32(x[u].z, h.z, l.z);
+            split_tf32(x[u].w, h.w, l.w);
+            sts128(hi + (uint32_t)(c + u * nthreads) * 16u, h);
+            sts128(lo + (uint32_t)(c + u * nthreads) * 16u, l);
+        }
+    }
+    for (; c < n16; c += nthreads) {
+        const float4 x = lds128(hi + (uint32_t)c * 16u);
+        float4 h, l;
+        split_tf32(x.x, h.x, l.x);
+        split_tf32(x.y, h.y, l.y);
+        split_tf32(x.z, h.z, l.z);
+        split_tf32(x.w, h.w, l.w);
+        sts128(hi + (uint32_t)c * 16u, h);
+        sts128(lo + (uint32_t)c * 16u, l);
+    }
 }
 
 }  // namespace
