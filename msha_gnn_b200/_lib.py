@@ -49,9 +49,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     obj_dir = os.path.join(_PKG_DIR, "build")
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [HEADER]
+    stamp = os.path.join(obj_dir, "flags.txt")
+    same_flags = os.path.isfile(stamp) and open(stamp).read() == " ".join(flags)
     for src in sources():
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
+        if (not force and same_flags and os.path.isfile(obj)
+                and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in [src] + headers)):
+            continue                                   # object is newer than its source and every header
         cmd = [nvcc, *flags, "-I", os.path.join(_ROOT, "include"), "-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
@@ -60,6 +66,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{out.decode(errors='replace')}")
+    with open(stamp, "w") as f:
+        f.write(" ".join(flags))
     cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart", "-lcuda"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:

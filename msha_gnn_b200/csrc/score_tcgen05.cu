@@ -9,8 +9,10 @@
 //   score_bwd_dw  dW0 = G^T @ Z with Z regenerated from the gathers (MN-major operands, whole K range per CTA in TMEM).
 //
 // Same warp-specialised skeleton as gemm_tcgen05.cu (TMA thread, MMA thread, TMEM allocator; mbarrier rings;
-// double-buffered TMEM accumulators) with 8 producer warps (the gathers / streaming reads are software-pipelined one
-// k-block ahead in registers) and 4 epilogue warps.
+// double-buffered TMEM accumulators).  score_fwd and score_bwd_dz run as CTA pairs (tcgen05 cta_group::2: 256-row
+// tiles, half of the W0 slice staged per CTA) with 4 producer warps and 8 epilogue warps per CTA; score_bwd_dw keeps the
+// whole 256 x 256 accumulator of one CTA in TMEM.  What bounds them (shared-memory bandwidth of the three MMAs per
+// k-step, L2 fill of the W0 slices, epilogue latency) is measured in profiles/r01_tensor_kernel_ablations.txt.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>
@@ -23,8 +25,10 @@ constexpr int UMMA_K = 8;
 constexpr int NUM_THREADS = 512;
 constexpr int PROD_THREADS = 256;             // warps 8-15 of the dW kernel (Z gather producers)
 constexpr int CVT_THREADS = 128;              // warps 4-7 of the dW kernel (TMA tile converters)
-constexpr int FWD_PROD_WARPS = 4;              // forward kernel: warps 4-7 produce the A tile (pair gather),
-constexpr int FWD_EPI_WARPS = 8;              //                       warps 8-15 run the store / scatter epilogue
+constexpr int FWD_PROD_WARPS = 4;              // forward kernel: warps 4-7 produce the A tile (pair gather, 4 rows per thread),
+constexpr int FWD_EPI_WARPS = 8;               //                 warps 8-15 run the store epilogue (4 epilogue warps: 3.9 ms)
+constexpr int FWD_THREADS = (4 + FWD_PROD_WARPS + FWD_EPI_WARPS) * 32;
+constexpr int MAX_EPI_WARPS = 8;
 #ifndef MSHA_DZ_PROD_WARPS
 #define MSHA_DZ_PROD_WARPS 4
 #endif
@@ -48,34 +52,38 @@ struct SCfg {
     static constexpr int STAGES = (192 * 1024) / STAGE_BYTES < 8 ? (192 * 1024) / STAGE_BYTES : 8;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BAR_OFF = EPI_OFF + FWD_EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int BAR_OFF = EPI_OFF + MAX_EPI_WARPS * EPI_STAGE_BYTES;
     static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 512;
 };
 
-// Apply activation to 32 values (switch hoisted out of the element loop).
-__device__ __forceinline__ void act32(float (&x)[32], int act, float slope) {
+// Activation of one 16-byte chunk (the branch on `act` is warp-uniform).
+__device__ __forceinline__ float fast_sigmoid(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
+}
+__device__ __forceinline__ float act1(float x, int act, float slope) {
     switch (act) {
-        case 1:
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] : expm1f(x[j]);
+        case 1: return x > 0.f ? x : expm1f(x);
+        case 2: return fmaxf(x, 0.f);
+        case 3: return fast_sigmoid(fmaxf(x, 0.f));
+        case 4: return x > 0.f ? x : x * slope;
+        case 5: return fast_sigmoid(x);
+        default: return x;
+    }
+}
+__device__ __forceinline__ void act4(float4& o, int act, float slope) {
+    switch (act) {
+        case 3:                                                   // the scorer's relu -> sigmoid
+            o.x = fast_sigmoid(fmaxf(o.x, 0.f)); o.y = fast_sigmoid(fmaxf(o.y, 0.f));
+            o.z = fast_sigmoid(fmaxf(o.z, 0.f)); o.w = fast_sigmoid(fmaxf(o.w, 0.f));
             break;
-        case 2:
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        case 0: break;
+        default:
+            o.x = act1(o.x, act, slope); o.y = act1(o.y, act, slope);
+            o.z = act1(o.z, act, slope); o.w = act1(o.w, act, slope);
             break;
-        case 3:
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __fdividef(1.f, 1.f + __expf(-fmaxf(x[j], 0.f)));
-            break;
-        case 4:
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * slope;
-            break;
-        case 5:
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __fdividef(1.f, 1.f + __expf(-x[j]));
-            break;
-        default: break;
     }
 }
 
@@ -141,7 +149,7 @@ __device__ __forceinline__ void issue_kblock(uint8_t* st, uint32_t tmem_d, bool 
 // fused forward
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK_N, int CTAS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                  const float* __restrict__ hi_tab, const float* __restrict__ hj_tab, const int64_t* __restrict__ src,
                  const int64_t* __restrict__ dst, int64_t P, int C, int N, const float* __restrict__ bias, int act,
@@ -286,53 +294,66 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant
         }
     } else if (warp >= 4 + FWD_PROD_WARPS) {
         // ---------------- epilogue ----------------
-        const int q = warp & 3, hf = (warp - 8) >> 2;
-        constexpr int COLS_PER_WARP = BLOCK_N / 2;
-        const uint32_t stage_s = smem_u32(smem + S::EPI_OFF + (warp - 8) * EPI_STAGE_BYTES);
+        const int ew = warp - (4 + FWD_PROD_WARPS);
+        const int q = warp & 3, hf = ew >> 2;
+        constexpr int COLS_PER_WARP = BLOCK_N / (FWD_EPI_WARPS / 4);
+        const uint32_t stage_s = smem_u32(smem + S::EPI_OFF + ew * EPI_STAGE_BYTES);
         const bool vec_ok = ((ldo & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
         uint32_t acc = 0, acc_phase = 0;
-        float bias_r[4] = {0.f, 0.f, 0.f, 0.f};                  // this lane's bias of each 32-column chunk of the warp
+        const int rs = lane >> 3, cg = lane & 7;                 // after the transpose: rows 4k + rs, 16-byte column chunk cg
+        constexpr int NCH = COLS_PER_WARP / 32;
+        float4 bias_r[NCH];                                      // bias of this thread's 4 columns in each chunk of the warp
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int col = hf * COLS_PER_WARP + 32 * u + lane;
-            if (bias != nullptr && 32 * u < COLS_PER_WARP && col < N) bias_r[u] = __ldg(bias + col);
+        for (int u = 0; u < NCH; ++u) {
+            const int col = hf * COLS_PER_WARP + 32 * u + 4 * cg;
+            float bv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (bias != nullptr) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (col + e < N) bv[e] = __ldg(bias + col + e);
+            }
+            bias_r[u] = make_float4(bv[0], bv[1], bv[2], bv[3]);
         }
         for (int64_t tp = tp0; tp < pair_tiles; tp += tp_step) {
             const int64_t row0 = (tp * CTAS + rank) * BLOCK_M + q * 32;
             mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
             tcgen05_fence_after();
-#pragma unroll 1
-            for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
-                const int nb = hf * COLS_PER_WARP + cc;
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) {
+                const int nb = hf * COLS_PER_WARP + 32 * u;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + nb, v);
                 if (nb >= N) continue;
-                const float bj = cc == 0 ? bias_r[0] : (cc == 32 ? bias_r[1] : (cc == 64 ? bias_r[2] : bias_r[3]));
-                float x[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bj, j);
-                act32(x, act, slope);
+                // transpose through shared memory (16-byte chunks XOR-swizzled by row); bias + activation run on the
+                // transposed side, where a thread's four columns (and so its bias) are the same for every row
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
                     sts128(stage_s + (uint32_t)(lane * 32 + ((g ^ (lane & 7)) << 2)) * 4u,
-                           make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]));
+                           make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                       __uint_as_float(v[4 * g + 3])));
                 __syncwarp();
-                const int rs = lane >> 3, cg = lane & 7;
+                const float4 bj = bias_r[u];
+                const int col = nb + 4 * cg;
+                float4 o[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int r = 4 * k + rs;
-                    const float4 o = lds128(stage_s + (uint32_t)(r * 32 + ((cg ^ (r & 7)) << 2)) * 4u);
-                    const int64_t row = row0 + r;
-                    const int col = nb + 4 * cg;
+                    o[k] = lds128(stage_s + (uint32_t)(r * 32 + ((cg ^ (r & 7)) << 2)) * 4u);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    o[k].x += bj.x; o[k].y += bj.y; o[k].z += bj.z; o[k].w += bj.w;
+                    act4(o[k], act, slope);
+                    const int64_t row = row0 + 4 * k + rs;
                     if (row < P) {
                         float* cp = out + row * ldo + col;
                         if (vec_ok && col + 4 <= N) {
-                            *reinterpret_cast<float4*>(cp) = o;
+                            *reinterpret_cast<float4*>(cp) = o[k];
                         } else {
-                            if (col + 0 < N) cp[0] = o.x;
-                            if (col + 1 < N) cp[1] = o.y;
-                            if (col + 2 < N) cp[2] = o.z;
-                            if (col + 3 < N) cp[3] = o.w;
+                            if (col + 0 < N) cp[0] = o[k].x;
+                            if (col + 1 < N) cp[1] = o[k].y;
+                            if (col + 2 < N) cp[2] = o[k].z;
+                            if (col + 3 < N) cp[3] = o[k].w;
                         }
                     }
                 }
@@ -844,13 +865,13 @@ constexpr int SCORE_CTAS = MSHA_SCORE_CTAS;   // 2: forward / dZ kernels run as 
 
 // persistent launch: one CTA (or CTA pair) per SM, tiles strided over the grid
 template <class Kern, class... Args>
-int launch_tiles(Kern kern, int smem_bytes, int64_t m_tiles, cudaStream_t st, Args... args) {
+int launch_tiles(Kern kern, int threads, int smem_bytes, int64_t m_tiles, cudaStream_t st, Args... args) {
     const int64_t pair_tiles = (m_tiles + SCORE_CTAS - 1) / SCORE_CTAS;
     const int max_pairs = MSHA_NUM_SMS / SCORE_CTAS;
     const int grid = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs) * SCORE_CTAS;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = (size_t)smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -876,7 +897,7 @@ int launch_fwd(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* hi_t
         MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
         attr_set = true;
     }
-    return launch_tiles(kern, S::SMEM_BYTES, (P + BLOCK_M - 1) / BLOCK_M, st, tbh, tbl, hi_tab, hj_tab, src, dst, P, C, N, bias,
+    return launch_tiles(kern, FWD_THREADS, S::SMEM_BYTES, (P + BLOCK_M - 1) / BLOCK_M, st, tbh, tbl, hi_tab, hj_tab, src, dst, P, C, N, bias,
                         act, slope, out, ldo);
 }
 
@@ -934,7 +955,7 @@ int launch_dz(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* dout,
         MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
         attr_set = true;
     }
-    return launch_tiles(kern, S::SMEM_BYTES, (P + BLOCK_M - 1) / BLOCK_M, st, tbh, tbl, td, ty, act, slope, G, db, hi_tab,
+    return launch_tiles(kern, NUM_THREADS, S::SMEM_BYTES, (P + BLOCK_M - 1) / BLOCK_M, st, tbh, tbl, td, ty, act, slope, G, db, hi_tab,
                         hj_tab, src, dst, P, Hd, C, dhi, dhj);
 }
 }  // namespace
