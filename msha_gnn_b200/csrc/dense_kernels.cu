@@ -629,20 +629,21 @@ __global__ void nll_fwd_stage2(const double* __restrict__ partial, int n, int64_
 }
 __global__ void nll_bwd_kernel(const int64_t* __restrict__ target, const float* __restrict__ gout, int64_t P, int C,
                                float* __restrict__ dlogp) {
-    // one warp per row chunk: stream zeros, patch the picked column
+    // one warp per row: stream zeros (write-once data, streaming stores), patch the picked column
     const float g = -(*gout) / (float)P;
-    const int64_t total4 = P * C / 4;              // C % 4 == 0 fast path handled by the caller
-    float4* d4 = reinterpret_cast<float4*>(dlogp);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = i * 4;
-        const int64_t p = e / C;
-        const int c = (int)(e - p * C);
-        const int t = (int)target[p];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= c && t < c + 4) {
-            if (t == c) v.x = g; else if (t == c + 1) v.y = g; else if (t == c + 2) v.z = g; else v.w = g;
+    const int lane = threadIdx.x & 31, c4n = C >> 2;        // C % 4 == 0 fast path handled by the caller
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp; p < P; p += nwarps) {
+        const int t = (int)__ldg(target + p);
+        float4* d4 = reinterpret_cast<float4*>(dlogp + p * C);
+        for (int c4 = lane; c4 < c4n; c4 += 32) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((t >> 2) == c4) {
+                const int r = t & 3;
+                if (r == 0) v.x = g; else if (r == 1) v.y = g; else if (r == 2) v.z = g; else v.w = g;
+            }
+            __stcs(d4 + c4, v);
         }
-        d4[i] = v;
     }
 }
 __global__ void nll_bwd_scalar_kernel(const int64_t* __restrict__ target, const float* __restrict__ gout, int64_t P, int C,

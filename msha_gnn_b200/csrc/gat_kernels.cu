@@ -308,7 +308,10 @@ __global__ void gat_fwd_rescale_kernel(HubArgs hub, const float* __restrict__ pa
 // ---------------------------------------------------------------------------------------------
 // EB: edges whose feature gathers are in flight together; MINB: resident CTAs per SM the register budget targets.
 // <4, 2> suits dense rows (long gather streams), <2, 3> sparse power-law rows (latency hidden by occupancy).
-template <int VW, int VPL, int EB, int MINB>
+// LPH_T > 0 (VW == 4, no dT/fT term): lanes per head known at compile time -- the per-edge dot products of EB edges are
+// reduced together by a transposing butterfly (EB/2 + EB/4 + ... shuffles for EB edges instead of log2(LPH) each) and
+// every (edge, head) sum is stored once, by the lane that ends up owning it.
+template <int VW, int VPL, int EB, int MINB, int LPH_T = 0>
 __global__ void __launch_bounds__(GAT_THREADS, MINB)
 gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_rows,
                     const float* __restrict__ s_nbr, const float* __restrict__ s_self, float slope,
@@ -375,9 +378,83 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
         const bool valid = e < end;
         const int c = valid ? col[e] : 0;
         const int j = c < 0 ? ~c : c;
+        const int cnt = min(32, end - e0);
+        if constexpr (LPH_T > 0) {
+            static_assert(LPH_T == 0 || VW == 4, "fast path is for 128-bit vectors");
+            constexpr int KPH = LPH_T > 32 ? LPH_T / 32 : 1;        // vectors of one lane that belong to the same head
+            constexpr int NG = VPL / KPH;                            // heads a lane contributes to
+            constexpr int G = LPH_T > 32 ? 32 : LPH_T;               // lanes to reduce across
+            constexpr int LOGG = G == 32 ? 5 : (G == 16 ? 4 : (G == 8 ? 3 : (G == 4 ? 2 : (G == 2 ? 1 : 0))));
+            constexpr int LOGE = EB == 8 ? 3 : (EB == 4 ? 2 : (EB == 2 ? 1 : 0));
+            constexpr int T = LOGG < LOGE ? LOGG : LOGE;              // transposing steps
+            static_assert(VPL % KPH == 0 && (1 << LOGG) == G && (1 << LOGE) == EB, "fast path layout");
+            int estart = 0;                                          // first edge (of a batch) whose sum this lane ends up with
+#pragma unroll
+            for (int sidx = 0; sidx < T; ++sidx)
+                if (lane & (G >> (sidx + 1))) estart += EB >> (sidx + 1);
+            const bool writer = (lane & ((G >> T) - 1)) == 0;
+            for (int t0 = 0; t0 < cnt; t0 += EB) {
+                float x[EB][VPL][VW];
+#pragma unroll
+                for (int u = 0; u < EB; ++u) {
+                    const int jt = __shfl_sync(FULL_MASK, j, (t0 + u) & 31);
+                    const float* f = feat + (int64_t)jt * C;
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) {
+                        if (t0 + u < cnt) {
+                            VecT<VW>::load(f + (lane + 32 * k) * VW, x[u][k]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < VW; ++q) x[u][k][q] = 0.f;
+                        }
+                    }
+                }
+                float pr[NG][EB];
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+#pragma unroll
+                    for (int u = 0; u < EB; ++u) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int kk = 0; kk < KPH; ++kk)
+#pragma unroll
+                            for (int q = 0; q < VW; ++q) acc = fmaf(x[u][g * KPH + kk][q], dz[g * KPH + kk][q], acc);
+                        pr[g][u] = acc;
+                    }
+                int n = EB;
+#pragma unroll
+                for (int sidx = 0; sidx < T; ++sidx) {
+                    const int o = G >> (sidx + 1);
+                    const bool up = (lane & o) != 0;
+                    n >>= 1;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g)
+#pragma unroll
+                        for (int i = 0; i < (EB >> (sidx + 1)); ++i) {
+                            const float send = up ? pr[g][i] : pr[g][i + n];
+                            const float keep = up ? pr[g][i + n] : pr[g][i];
+                            pr[g][i] = keep + __shfl_xor_sync(FULL_MASK, send, o);
+                        }
+                }
+#pragma unroll
+                for (int sidx = T; sidx < LOGG; ++sidx) {
+                    const int o = G >> (sidx + 1);
+#pragma unroll
+                    for (int g = 0; g < NG; ++g)
+#pragma unroll
+                        for (int i = 0; i < (EB >> T); ++i) pr[g][i] += __shfl_xor_sync(FULL_MASK, pr[g][i], o);
+                }
+                if (writer) {
+#pragma unroll
+                    for (int g = 0; g < NG; ++g)
+#pragma unroll
+                        for (int i = 0; i < (EB >> T); ++i)
+                            sm_d[(t0 + estart + i) * H + (lane + 32 * g * KPH) / LPH_T] = pr[g][i];
+                }
+            }
+        } else {
         for (int q = lane; q < 32 * H; q += 32) sm_d[q] = 0.f;
         __syncwarp();
-        const int cnt = min(32, end - e0);
         for (int t0 = 0; t0 < cnt; t0 += EB) {
             float x[EB][VPL][VW], y[EB][VPL][VW];
 #pragma unroll
@@ -423,6 +500,7 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
                     }
                 }
             }
+        }
         }
         __syncwarp();
         if (hp2) {
@@ -802,21 +880,34 @@ MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_
                                                                          alpha, feat, dout, out, act, dz_out, dT, fT,    \
                                                                          dalpha_extra, dlse, H, D, dlogit, ds_self,      \
                                                                          drop, hub, mode, r_buf)
+    // 256 channels in 128-bit vectors, no second (dT, fT) term: compile-time lanes-per-head variants
+    const int lph = (vw == 4 && vpl == 2 && dT == nullptr && H * D == 256) ? D / 4 : 0;
+#define CALL_FAST(LPH)                                                                                                   \
+    gat_bwd_rows_kernel<4, 2, 8, 2, LPH><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, slope, \
+                                                                          alpha, feat, dout, out, act, dz_out, dT, fT,    \
+                                                                          dalpha_extra, dlse, H, D, dlogit, ds_self,      \
+                                                                          drop, hub, mode, r_buf)
+#define LAUNCH_ROWS()                                   \
+    if (lph == 8) { CALL_FAST(8); }                     \
+    else if (lph == 64) { CALL_FAST(64); }              \
+    else { DISPATCH_LAYOUT(vw, vpl, CALL) }
     unsigned grid = (unsigned)msha_cdiv(n_rows, GAT_WARPS);
     int mode = 0;
-    DISPATCH_LAYOUT(vw, vpl, CALL)
+    LAUNCH_ROWS()
     MSHA_LAUNCH_OK();
     if (hub.n_segs > 0) {
         grid = (unsigned)msha_cdiv(hub.n_segs, GAT_WARPS);
         mode = 1;
-        DISPATCH_LAYOUT(vw, vpl, CALL)
+        LAUNCH_ROWS()
         MSHA_LAUNCH_OK();
         if (s_nbr != nullptr) {
             mode = 2;
-            DISPATCH_LAYOUT(vw, vpl, CALL)
+            LAUNCH_ROWS()
             MSHA_LAUNCH_OK();
         }
     }
+#undef LAUNCH_ROWS
+#undef CALL_FAST
 #undef CALL
     return 0;
 }

@@ -8,6 +8,7 @@ Ours.py:54,67; HGANE.py:38-39) and the O(N^2) Python builders ``dataset.py:260-2
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 
 import torch
@@ -18,7 +19,8 @@ from .ops import call, ptr, workspace, _stream
 _L = ops._lib
 
 
-SEG_LIMIT = 1024     # rows / columns with more entries are processed as segments of this many slots (hub handling)
+# rows / columns with more entries are processed as segments of this many slots (hub handling)
+SEG_LIMIT = int(os.environ.get("MSHA_SEG_LIMIT", "1024"))
 
 
 class _HubStruct(ctypes.Structure):
