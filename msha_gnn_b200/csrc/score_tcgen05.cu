@@ -661,23 +661,29 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
 // fused backward, part 2:  dW0[Hd, C] = G^T @ Z,  Z[p,:] = h_i[src[p]] * h_j[dst[p]] regenerated by gather warps.
 //   A operand: G [K = pairs, M = Hd]  MN-major, TMA (128B-atom-32B swizzle) + converter warps (hi / lo)
 //   B operand: Z [K = pairs, N = C]   MN-major, written hi / lo by the gather warps in the same swizzle
-//   each CTA owns a contiguous range of pairs and keeps the whole 256 x 256 accumulator in TMEM (512 columns);
-//   partial results are added to dW0 with atomics at the end.
+//   A CTA (CTAS = 1) or CTA pair (CTAS = 2) owns a contiguous range of pairs and keeps the whole 256 x 256 accumulator
+//   in TMEM; partial results are added to dW0 with atomics at the end.  In a pair each CTA stages 128 of the Hd rows
+//   of G and 128 of the C columns of Z -- half the shared-memory traffic per SM for the same tensor work.
 // ------------------------------------------------------------------------------------------------
+template <int CTAS>
 struct WCfg {
-    static constexpr int MN = 256;                                  // padded Hd and C
-    static constexpr int TILE_BYTES = MN * BLOCK_K * 4;             // 16 KB per hi / lo tile
+    static constexpr int ROWS = 256 / CTAS;                         // Hd rows of G / C columns of Z staged per CTA
+    static constexpr int BK = 16 * CTAS;                            // pairs per stage (a pair needs 32 to amortise its hand-offs)
+    static constexpr int CHUNK_BYTES = BK * 128;                    // one 32-wide MN chunk: BK K-rows of 128 B
+    static constexpr int TILE_BYTES = ROWS * BK * 4;                // 16 KB per hi / lo tile
     static constexpr int STAGE_BYTES = 4 * TILE_BYTES;              // A_hi, A_lo, B_hi, B_lo
     static constexpr int STAGES = 3;
+    static constexpr int TMEM_COLS = 512 / CTAS;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 512;
 };
 
+template <int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __restrict__ hi_tab,
                     const float* __restrict__ hj_tab, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                     int64_t P, int Hd, int C, float* __restrict__ dW) {
-    using W = WCfg;
+    using W = WCfg<CTAS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + W::BAR_OFF);
@@ -688,36 +694,36 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
     uint64_t* acc_full = bars + 4 * W::STAGES;
     uint32_t* tmem_ptr = (uint32_t*)(bars + 4 * W::STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank = 0;
+    if constexpr (CTAS == 2) rank = cluster_ctarank();
 
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmG) : "memory");
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < W::STAGES; ++s) {
             mbar_init(smem_u32(&full_raw[s]), 1);
-            mbar_init(smem_u32(&full_cvt[s]), CVT_THREADS);
-            mbar_init(smem_u32(&full_b[s]), PROD_THREADS);
+            mbar_init(smem_u32(&full_cvt[s]), CTAS * (CVT_THREADS / 32));
+            mbar_init(smem_u32(&full_b[s]), CTAS * (PROD_THREADS / 32));
             mbar_init(smem_u32(&empty[s]), 1);
         }
         mbar_init(smem_u32(acc_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 2) tmem_alloc<CTAS>(smem_u32(tmem_ptr), (uint32_t)W::TMEM_COLS);
     tcgen05_fence_before();
     __syncthreads();
+    pair_sync<CTAS>();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    // contiguous range of 16-pair chunks owned by this CTA
-    const int64_t n_chunks = (P + BLOCK_K - 1) / BLOCK_K;
-    const int64_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
-    const int64_t c0 = (int64_t)blockIdx.x * per;
+    // contiguous range of BK-pair chunks owned by this CTA (pair)
+    const int64_t n_chunks = (P + W::BK - 1) / W::BK;
+    const int64_t n_owner = gridDim.x / CTAS;
+    const int64_t per = (n_chunks + n_owner - 1) / n_owner;
+    const int64_t c0 = (int64_t)(blockIdx.x / CTAS) * per;
     const int64_t c1 = c0 + per < n_chunks ? c0 + per : n_chunks;
-    const int m_tiles = (Hd + 127) / 128;
+    const int m_tiles = CTAS == 2 ? 1 : (Hd + 127) / 128;
     const int a_chunks = m_tiles * 4;                     // 32-wide MN chunks of G actually loaded
+    const int row_base = (int)rank * W::ROWS;             // first Hd row (A) / C column (B) staged by this CTA
 
     if (warp == 0) {
         if (lane == 0) {
@@ -726,18 +732,19 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
                 mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                 const uint32_t a_dst = smem_u32(smem + stage * W::STAGE_BYTES);
                 const uint32_t bar = smem_u32(&full_raw[stage]);
-                mbar_arrive_expect_tx(bar, (uint32_t)a_chunks * 2048u);
-                for (int i = 0; i < a_chunks; ++i) tma_load_2d(a_dst + i * 2048, &tmG, bar, 32 * i, (int)(ch * BLOCK_K));
+                mbar_arrive_expect_tx(bar, (uint32_t)a_chunks * W::CHUNK_BYTES);
+                for (int i = 0; i < a_chunks; ++i)
+                    tma_load_2d(a_dst + i * W::CHUNK_BYTES, &tmG, bar, row_base + 32 * i, (int)(ch * W::BK));
                 if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(128, 256, true, true);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(128 * CTAS, 256, true, true);
             uint32_t stage = 0, phase = 0;
             for (int64_t ch = c0; ch < c1; ++ch) {
-                mbar_wait(smem_u32(&full_cvt[stage]), phase);
-                mbar_wait(smem_u32(&full_b[stage]), phase);
+                wait_leader_bar<CTAS>(smem_u32(&full_cvt[stage]), phase);
+                wait_leader_bar<CTAS>(smem_u32(&full_b[stage]), phase);
                 tcgen05_fence_after();
                 uint8_t* st = smem + stage * W::STAGE_BYTES;
                 const uint32_t a_hi = smem_u32(st), a_lo = a_hi + W::TILE_BYTES;
@@ -745,20 +752,29 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
                 for (int mt = 0; mt < m_tiles; ++mt) {
                     const uint32_t tmem_d = tmem_base + mt * 256;
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t dah = make_smem_desc(a_hi + mt * 8192 + k * 1024, 2048, 512, 1);
-                        const uint64_t dal = make_smem_desc(a_lo + mt * 8192 + k * 1024, 2048, 512, 1);
-                        const uint64_t dbh = make_smem_desc(b_hi + k * 1024, 2048, 512, 1);
-                        const uint64_t dbl = make_smem_desc(b_lo + k * 1024, 2048, 512, 1);
-                        umma_tf32(tmem_d, dal, dbh, idesc, (ch > c0 || k > 0) ? 1u : 0u);
-                        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                    for (int k = 0; k < W::BK / UMMA_K; ++k) {
+                        const uint64_t dah = make_smem_desc(a_hi + mt * 4 * W::CHUNK_BYTES + k * 1024, W::CHUNK_BYTES, 512, 1);
+                        const uint64_t dal = make_smem_desc(a_lo + mt * 4 * W::CHUNK_BYTES + k * 1024, W::CHUNK_BYTES, 512, 1);
+                        const uint64_t dbh = make_smem_desc(b_hi + k * 1024, W::CHUNK_BYTES, 512, 1);
+                        const uint64_t dbl = make_smem_desc(b_lo + k * 1024, W::CHUNK_BYTES, 512, 1);
+                        const uint32_t accum = (ch > c0 || k > 0) ? 1u : 0u;
+                        if constexpr (CTAS == 2) {
+                            umma_tf32_pair(tmem_d, dal, dbh, idesc, accum);
+                            umma_tf32_pair(tmem_d, dah, dbl, idesc, 1u);
+                            umma_tf32_pair(tmem_d, dah, dbh, idesc, 1u);
+                        } else {
+                            umma_tf32(tmem_d, dal, dbh, idesc, accum);
+                            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                            umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                        }
                     }
                 }
-                tcgen05_commit(smem_u32(&empty[stage]));
+                if constexpr (CTAS == 2) tcgen05_commit_pair(smem_u32(&empty[stage]));
+                else tcgen05_commit(smem_u32(&empty[stage]));
                 if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
             }
-            tcgen05_commit(smem_u32(acc_full));
+            if constexpr (CTAS == 2) tcgen05_commit_pair(smem_u32(acc_full));
+            else tcgen05_commit(smem_u32(acc_full));
         }
     } else if (warp >= 4 && warp < 8) {
         // ---------------- converters for the TMA-loaded G tile ----------------
@@ -767,25 +783,27 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
         for (int64_t ch = c0; ch < c1; ++ch) {
             mbar_wait(smem_u32(&full_raw[stage]), phase);
             uint8_t* st = smem + stage * W::STAGE_BYTES;
-            split_tile_inplace(smem_u32(st), smem_u32(st) + W::TILE_BYTES, a_chunks * 2048 / 16, tid, CVT_THREADS);
+            split_tile_inplace(smem_u32(st), smem_u32(st) + W::TILE_BYTES, a_chunks * W::CHUNK_BYTES / 16, tid, CVT_THREADS);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(smem_u32(&full_cvt[stage]));
+            warp_arrive_leader<CTAS>(smem_u32(&full_cvt[stage]), lane);
             if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 8) {
-        // ---------------- Z producers (8 warps): 16 pairs x C channels per stage, MN-major 128B-atom-32B swizzle ----------------
+        // ---------------- Z producers (8 warps): BK pairs x this CTA's channels per stage, MN-major 128B-atom-32B swizzle ----
+        constexpr int TPP = PROD_THREADS / W::BK;                // threads per pair (16 / 8)
+        constexpr int NI = W::ROWS / (4 * TPP);                  // 16-byte chunks per thread and table (4)
         const int tid = threadIdx.x - 256;
-        const int kk = tid >> 4, j = tid & 15;                   // pair kk of the chunk; 16-byte column j (+16 per step)
+        const int kk = tid / TPP, j = tid % TPP;                 // pair kk of the chunk; 16-byte column j (+TPP per step)
         uint32_t stage = 0, phase = 0;
-        float4 za[4], zb[4], na[4], nb4[4];
-        auto load = [&](int64_t ch, float4 (&x)[4], float4 (&y)[4]) {
-            const int64_t p = ch * BLOCK_K + kk;
+        float4 za[NI], zb[NI], na[NI], nb4[NI];
+        auto load = [&](int64_t ch, float4 (&x)[NI], float4 (&y)[NI]) {
+            const int64_t p = ch * W::BK + kk;
             const bool pvalid = (ch < c1) && (p < P);
             const int64_t si = pvalid ? (src ? src[p] : p) : 0;
             const int64_t dj = pvalid ? (dst ? dst[p] : p) : 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int col = j * 4 + 64 * i;
+            for (int i = 0; i < NI; ++i) {
+                const int col = row_base + j * 4 + 4 * TPP * i;
                 if (pvalid && col < C) {
                     x[i] = ldg4(hi_tab + si * C + col);
                     y[i] = ldg4(hj_tab + dj * C + col);
@@ -799,24 +817,24 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
         for (int64_t ch = c0; ch < c1; ++ch) {
             load(ch + 1, na, nb4);
             mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
-            uint8_t* st = smem + stage * W::STAGE_BYTES + 2 * W::TILE_BYTES;
+            const uint32_t st = smem_u32(smem + stage * W::STAGE_BYTES + 2 * W::TILE_BYTES);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < NI; ++i) {
                 float4 h, l;
                 split_tf32(za[i].x * zb[i].x, h.x, l.x);
                 split_tf32(za[i].y * zb[i].y, h.y, l.y);
                 split_tf32(za[i].z * zb[i].z, h.z, l.z);
                 split_tf32(za[i].w * zb[i].w, h.w, l.w);
-                const int col = j * 4 + 64 * i;                  // channel of this 16-byte chunk
-                const uint32_t off = (col >> 5) * 2048 + sw128b32_offset(kk, (col & 31) >> 2);
-                sts128(smem_u32(st) + off, h);
-                sts128(smem_u32(st) + W::TILE_BYTES + off, l);
+                const int col = j * 4 + 4 * TPP * i;             // local channel of this 16-byte chunk
+                const uint32_t off = (col >> 5) * W::CHUNK_BYTES + sw128b32_offset(kk, (col & 31) >> 2);
+                sts128(st + off, h);
+                sts128(st + W::TILE_BYTES + off, l);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(smem_u32(&full_b[stage]));
+            warp_arrive_leader<CTAS>(smem_u32(&full_b[stage]), lane);
             if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { za[i] = na[i]; zb[i] = nb4[i]; }
+            for (int i = 0; i < NI; ++i) { za[i] = na[i]; zb[i] = nb4[i]; }
         }
     }
     // ---------------- epilogue (warps 8-15): TMEM -> atomicAdd into dW0 ----------------
@@ -825,7 +843,7 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
         mbar_wait(smem_u32(acc_full), 0);
         tcgen05_fence_after();
         for (int mt = 0; mt < m_tiles; ++mt) {
-            const int row = mt * 128 + q * 32 + lane;
+            const int row = (CTAS == 2 ? (int)rank * 128 : mt * 128) + q * 32 + lane;
 #pragma unroll 1
             for (int cc = 0; cc < 128; cc += 32) {
                 const int nb = hf * 128 + cc;
@@ -841,9 +859,10 @@ score_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmG, const float* __rest
     }
     tcgen05_fence_before();
     __syncthreads();
+    pair_sync<CTAS>();
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        tmem_dealloc<CTAS>(tmem_base, (uint32_t)W::TMEM_COLS);
     }
 }
 
@@ -1002,16 +1021,43 @@ MSHA_API int msha_score_mlp_bwd(const float* dout, const float* out, const float
     else rc = launch_dz<64>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, st);
     if (rc) return rc;
     // ---- part 2: dW0 = G^T @ Z
-    rc = tc_make_map(&tg, G, Hd, P, Hd, 32, BLOCK_K, true);               // A operand: G stored [K = P, M = Hd] MN-major
+    const bool dw_pairs = SCORE_CTAS == 2 && Hd > 128;   // CTA pairs split the Hd rows of G: pointless for Hd <= 128
+    const int dw_bk = dw_pairs ? WCfg<2>::BK : WCfg<1>::BK;
+    rc = tc_make_map(&tg, G, Hd, P, Hd, 32, dw_bk, true);                 // A operand: G stored [K = P, M = Hd] MN-major
     if (rc) return rc;
+    const int64_t n_chunks = (P + dw_bk - 1) / dw_bk;
+    if (dw_pairs) {
+        auto kern = score_bwd_dw_kernel<2>;
+        static bool attr_set2 = false;
+        if (!attr_set2) {
+            MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<2>::SMEM_BYTES));
+            attr_set2 = true;
+        }
+        const int max_pairs = MSHA_NUM_SMS / 2;
+        const int n_pairs = (int)(n_chunks < max_pairs ? n_chunks : max_pairs);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_pairs * 2);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = (size_t)WCfg<2>::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MSHA_CUDA(cudaLaunchKernelEx(&cfg, kern, tg, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dW0));
+        MSHA_LAUNCH_OK();
+        return 0;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        MSHA_CUDA(cudaFuncSetAttribute(score_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg::SMEM_BYTES));
+        MSHA_CUDA(cudaFuncSetAttribute(score_bwd_dw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<1>::SMEM_BYTES));
         attr_set = true;
     }
-    const int64_t n_chunks = (P + BLOCK_K - 1) / BLOCK_K;
     const int grid = (int)(n_chunks < MSHA_NUM_SMS ? n_chunks : MSHA_NUM_SMS);
-    score_bwd_dw_kernel<<<grid, NUM_THREADS, WCfg::SMEM_BYTES, st>>>(tg, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dW0);
+    score_bwd_dw_kernel<1><<<grid, NUM_THREADS, WCfg<1>::SMEM_BYTES, st>>>(tg, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dW0);
     MSHA_LAUNCH_OK();
     return 0;
 }

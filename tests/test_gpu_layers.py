@@ -338,7 +338,7 @@ def test_nll_readout_kernel_matches_torch():
 
 @pytest.mark.parametrize("fused_bwd", [True, False])
 @pytest.mark.parametrize("P,C,Hd,Nn", [(1000, 256, 256, 300), (4097, 64, 128, 50), (129, 32, 40, 17), (70000, 256, 256, 4267),
-                                      (5000, 128, 200, 64), (33, 8, 4, 5)])
+                                      (5000, 128, 200, 64), (33, 8, 4, 5), (1, 16, 8, 3), (37889, 256, 256, 1000)])
 def test_fused_scorer_vs_oracle(P, C, Hd, Nn, fused_bwd, monkeypatch):
     monkeypatch.setattr(Fn, "FUSED_SCORE_BWD", fused_bwd)
     g = torch.Generator().manual_seed(P)
