@@ -19,8 +19,21 @@ from .ops import call, ptr, workspace, _stream
 _L = ops._lib
 
 
-# rows / columns with more entries are processed as segments of this many slots (hub handling)
-SEG_LIMIT = int(os.environ.get("MSHA_SEG_LIMIT", "1024"))
+# rows / columns with more entries are processed as segments of this many slots (hub handling); the default adapts to
+# the graph so that small graphs with a few very long rows / columns still spread over the whole GPU
+SEG_LIMIT = int(os.environ.get("MSHA_SEG_LIMIT", "0"))
+SEG_LIMIT_MAX, SEG_LIMIT_MIN = 1024, 64
+
+
+def default_seg_limit(nnz: int) -> int:
+    """Segment length: ~16 warps of work per SM if the whole structure were hubs, a power of two in [64, 1024]."""
+    if SEG_LIMIT:
+        return SEG_LIMIT
+    target = max(1, nnz // (148 * 16))
+    lim = SEG_LIMIT_MIN
+    while lim < target and lim < SEG_LIMIT_MAX:
+        lim *= 2
+    return lim
 
 
 class _HubStruct(ctypes.Structure):
@@ -34,7 +47,7 @@ class Hub:
     """Segment decomposition of the rows (columns) with more than ``seg_limit`` entries; ``ptr`` is 0 when none."""
 
     def __init__(self, ptr_arr: torch.Tensor, seg_limit: int = None):
-        seg_limit = SEG_LIMIT if seg_limit is None else seg_limit
+        seg_limit = default_seg_limit(int(ptr_arr[-1])) if seg_limit is None else seg_limit
         deg = (ptr_arr[1:] - ptr_arr[:-1]).long()
         ids = torch.nonzero(deg > seg_limit).flatten()
         self.n_hub = int(ids.numel())

@@ -18,7 +18,13 @@ TC_MIN_WORK = 1 << 18                                    # below this many MACs 
 launch_count = 0    # number of C-ABI compute calls issued (bench.py reports kernel launches from it)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device (raw handle: this sits on every C-ABI call)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -41,11 +47,18 @@ def ptr(t, dtype=torch.float32, name="tensor"):
     return p
 
 
+_fn_cache = {}
+
+
 def call(fname, *args):
     global launch_count
     launch_count += 1
-    rc = getattr(_lib.lib(), fname)(*args)
-    _lib.check(rc, fname)
+    fn = _fn_cache.get(fname)
+    if fn is None:
+        fn = _fn_cache[fname] = getattr(_lib.lib(), fname)
+    rc = fn(*args)
+    if rc:
+        _lib.check(rc, fname)
 
 
 def workspace(nbytes: int, device):
