@@ -65,12 +65,37 @@ class Partition:
         return slice(self.rank * self.n_max, self.rank * self.n_max + self.n_local)
 
 
+class GradSink:
+    """Early start of a reduce-scatter: the op that produces the gradient of a gathered tensor calls ``start(g)`` the
+    moment ``g`` is complete; the collective then runs on NCCL's stream while that op finishes its other outputs, and
+    ``_AllGatherRows.backward`` only waits for it."""
+
+    def __init__(self, part: Partition, group=None):
+        self.part, self.group, self.work, self.out, self.src = part, group, None, None, None
+
+    def start(self, g: torch.Tensor):
+        part = self.part
+        if part.world == 1 or not g.is_cuda or dist.get_backend(self.group) == "gloo":
+            return
+        self.src = g                                      # keep the buffer alive until the collective has read it
+        self.out = g.new_empty((part.n_max, g.shape[1]))
+        self.work = dist.reduce_scatter_tensor(self.out, g, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def take(self, g: torch.Tensor):
+        """Result of the started collective if it was started on exactly this gradient, else None."""
+        if self.work is None or self.src is None or self.src.data_ptr() != g.data_ptr():
+            return None
+        self.work.wait()                                  # current stream waits for NCCL's stream
+        out, self.work, self.src, self.out = self.out, None, None, None
+        return out
+
+
 class _AllGatherRows(torch.autograd.Function):
     """[n_local, C] -> [world * n_max, C]; backward: reduce-scatter (sum) of the gathered gradient."""
 
     @staticmethod
-    def forward(ctx, x, part: Partition, group):
-        ctx.part, ctx.group = part, group
+    def forward(ctx, x, part: Partition, group, sink=None):
+        ctx.part, ctx.group, ctx.sink = part, group, sink
         C = x.shape[1]
         padded = x
         if part.n_local != part.n_max:
@@ -88,18 +113,21 @@ class _AllGatherRows(torch.autograd.Function):
         part, group = ctx.part, ctx.group
         g = g.contiguous()
         if part.world == 1:
-            return g[: part.n_local], None, None
+            return g[: part.n_local], None, None, None
+        early = ctx.sink.take(g) if ctx.sink is not None else None
+        if early is not None:
+            return early[: part.n_local], None, None, None
         out = g.new_empty((part.n_max, g.shape[1]))
         if dist.get_backend(group) == "gloo":            # gloo has no reduce_scatter: all-reduce + slice (tests only)
             dist.all_reduce(g, group=group)
             out.copy_(g[part.rank * part.n_max:(part.rank + 1) * part.n_max])
         else:
             dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=group)
-        return out[: part.n_local], None, None
+        return out[: part.n_local], None, None, None
 
 
-def all_gather_rows(x, part: Partition, group=None):
-    return _AllGatherRows.apply(x, part, group)
+def all_gather_rows(x, part: Partition, group=None, sink: GradSink = None):
+    return _AllGatherRows.apply(x, part, group, sink)
 
 
 def allreduce_gradients(params, group=None, world=None):
@@ -127,20 +155,22 @@ def partition_graph(rows: torch.Tensor, cols: torch.Tensor, part: Partition) -> 
     return Graph.from_coo(rows.to(torch.int64) - part.lo, part.to_padded(cols), part.n_local, part.n_padded)
 
 
-def gat_encode(convs, x_local, pgraph: Graph, part: Partition, group=None, training=True):
-    """Partitioned forward of a stack of ``GATConv`` layers (same arithmetic as ``GATConv.forward``): per layer one
-    all-gather of [Wh | s_nbr] in the forward and one reduce-scatter of its gradient in the backward."""
+def gat_encode(convs, x_local, pgraph: Graph, part: Partition, group=None, training=True, overlap=True):
+    """Partitioned forward of a stack of ``GATConv`` layers (same arithmetic as ``GATConv.forward``): per layer an
+    all-gather of Wh and of s_nbr in the forward and the reduce-scatter of their gradients in the backward."""
     h = x_local
     for conv in convs:
         H, D = conv.heads, conv.out_features
         Wh = Fn.linear(h, conv.W)                                              # local rows only
         s_nbr, s_self = Fn.node_scores(Wh, conv.a_nbr, conv.a_self, H, D)
-        gathered = all_gather_rows(torch.cat([Wh, s_nbr], dim=1), part, group)  # one collective for both tensors
-        Wh_g = gathered[:, : H * D].contiguous()
-        s_nbr_g = gathered[:, H * D:].contiguous()
+        # two collectives (features, then the H scores per node) straight into the buffers the kernels read: packing
+        # them into one message costs two extra passes over the gathered N x C matrix in each direction
+        sink = GradSink(part, group) if overlap else None     # backward: reduce-scatter of d Wh_g under the row pass
+        Wh_g = all_gather_rows(Wh, part, group, sink)
+        s_nbr_g = all_gather_rows(s_nbr, part, group)
         fuse_elu = conv.activation == "elu" and conv.concat
         out, _ = Fn.attention_block(pgraph, s_nbr_g, s_self, Wh_g, heads=H, act=ACT_ELU if fuse_elu else ACT_NONE,
-                                    dropout_p=conv.dropout, training=training)
+                                    dropout_p=conv.dropout, training=training, grad_sink=sink)
         if not conv.concat:
             out = out.view(out.shape[0], H, D).mean(dim=1)
             if conv.activation == "elu":

@@ -196,7 +196,8 @@ def node_scores(feat, a1, a2=None, H=1, D=None):
 # ------------------------------------------------------------------------------------------------
 class _AttentionBlock(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, s_nbr, s_self, feat_nbr, feat_self, graph: Graph, H, D, act, p, seed, want_cols, want_lse):
+    def forward(ctx, s_nbr, s_self, feat_nbr, feat_self, graph: Graph, H, D, act, p, seed, want_cols, want_lse,
+                grad_sink=None):
         s_nbr, s_self, feat_nbr = _c(s_nbr), _c(s_self), _c(feat_nbr)
         rp, col = graph.attention_csr()
         N, M = graph.n_rows, graph.n_cols
@@ -221,7 +222,7 @@ class _AttentionBlock(torch.autograd.Function):
             call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(feat_self), H, D,
                  ptr(out_cols), 0, None, None, p, seed, graph.hub_cols().ptr, _stream())
         ctx.graph, ctx.H, ctx.D, ctx.act, ctx.p, ctx.seed = graph, H, D, act, p, seed
-        ctx.want_cols, ctx.want_lse = want_cols, want_lse
+        ctx.want_cols, ctx.want_lse, ctx.grad_sink = want_cols, want_lse, grad_sink
         ctx.save_for_backward(s_nbr, s_self, feat_nbr, feat_self if want_cols else None, alpha,
                               out if act != ACT_NONE else None)
         ctx.set_materialize_grads(False)
@@ -256,13 +257,30 @@ class _AttentionBlock(torch.autograd.Function):
         r_buf = torch.empty((N, H), dtype=torch.float32, device=dev) if hub.n_segs else None
         extra = _c(d_alpha) if d_alpha is not None else None
         dlse = _c(d_lse) if d_lse is not None else None
+        dfeat_nbr = torch.empty((M, C), dtype=torch.float32, device=dev)
+        ds_nbr = torch.empty((M, H), dtype=torch.float32, device=dev)
+        sink = ctx.grad_sink if d_cols is None else None
+        if sink is not None:
+            # Partitioned graphs (dist.gat_encode): d feat_nbr is the big message of the backward.  Produce it first
+            # -- it needs only alpha and dZ -- and hand it to the sink, which starts its reduce-scatter; the row pass
+            # and the d s_nbr column sums then run while the collective is in flight.
+            if dz is not None:
+                call("msha_act_bwd", ptr(d_rows), ptr(out), ptr(dz), N * C, act, LRELU_SLOPE, _stream())
+            dzz = dz if dz is not None else d_rows
+            call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(dzz), H, D,
+                 ptr(dfeat_nbr), 0, None, None, p, seed, graph.hub_cols().ptr, _stream())
+            sink.start(dfeat_nbr)
+            call("msha_gat_bwd_rows", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr), ptr(s_self), LRELU_SLOPE, ptr(alpha),
+                 ptr(feat_nbr), ptr(dzz), None, ACT_NONE, None, None, None, ptr(extra), ptr(dlse), H, D, ptr(dlogit),
+                 ptr(ds_self), p, seed, hub.ptr, ptr(r_buf), int(alpha.shape[0] // max(N, 1)), _stream())
+            call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, None, None, H, D,
+                 None, 0, ptr(dlogit), ptr(ds_nbr), p, seed, graph.hub_cols().ptr, _stream())
+            return ds_nbr, ds_self, dfeat_nbr, None, None, None, None, None, None, None, None, None, None
         call("msha_gat_bwd_rows", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr), ptr(s_self), LRELU_SLOPE, ptr(alpha),
              ptr(feat_nbr), ptr(d_rows), ptr(out), act, ptr(dz), ptr(d_cols), ptr(feat_self) if d_cols is not None else None,
              ptr(extra), ptr(dlse), H, D, ptr(dlogit), ptr(ds_self), p, seed, hub.ptr, ptr(r_buf),
              int(alpha.shape[0] // max(N, 1)), _stream())
         dzz = dz if dz is not None else d_rows
-        dfeat_nbr = torch.empty((M, C), dtype=torch.float32, device=dev)
-        ds_nbr = torch.empty((M, H), dtype=torch.float32, device=dev)
         call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(dzz), H, D,
              ptr(dfeat_nbr), 0, ptr(dlogit), ptr(ds_nbr), p, seed, graph.hub_cols().ptr, _stream())
         dfeat_self = None
@@ -271,19 +289,21 @@ class _AttentionBlock(torch.autograd.Function):
             scr = _hub_scratch(hub, H, D, dev)
             call("msha_gat_fwd", ptr(rp, I32), ptr(col, I32), N, None, None, ptr(d_cols), H, D, LRELU_SLOPE, ptr(alpha),
                  None, ptr(dfeat_self), ACT_NONE, None, p, seed, hub.ptr, ptr(scr), _stream())
-        return ds_nbr, ds_self, dfeat_nbr, dfeat_self, None, None, None, None, None, None, None, None
+        return ds_nbr, ds_self, dfeat_nbr, dfeat_self, None, None, None, None, None, None, None, None, None
 
 
 def attention_block(graph: Graph, s_nbr, s_self, feat_nbr, feat_self=None, heads=1, act=ACT_NONE, dropout_p=0.0,
-                    training=True, want_cols=False, want_lse=False):
+                    training=True, want_cols=False, want_lse=False, grad_sink=None):
     """Returns (out_rows, [out_cols,] alpha [, lse]); alpha is [E_att, H], the pre-dropout attention over the
     attention CSR (differentiable: gradients flowing into it join the softmax backward); lse is the row-wise
-    log-sum-exp of the logits ([N, H], -inf for rows without edges)."""
+    log-sum-exp of the logits ([N, H], -inf for rows without edges).  ``grad_sink`` (optional, ``.start(tensor)``) is
+    handed d feat_nbr as soon as it exists in the backward (dist.py starts its reduce-scatter there)."""
     C = feat_nbr.shape[1]
     D = C // heads
     p = float(dropout_p) if training else 0.0
     seed = ops.next_seed() if p > 0 else 0
-    return _AttentionBlock.apply(s_nbr, s_self, feat_nbr, feat_self, graph, heads, D, act, p, seed, want_cols, want_lse)
+    return _AttentionBlock.apply(s_nbr, s_self, feat_nbr, feat_self, graph, heads, D, act, p, seed, want_cols, want_lse,
+                                 grad_sink)
 
 
 # ------------------------------------------------------------------------------------------------

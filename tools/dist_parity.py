@@ -1,0 +1,76 @@
+"""torchrun --nproc-per-node N tools/dist_parity.py : partitioned GAT encode + pair scoring over NCCL (with and without
+the early reduce-scatter of d Wh) against the whole-graph result on one GPU -- outputs, input and parameter gradients.
+
+Two constructions.  "positive": non-negative features / weights and a positive scorer bias keep every relu / LeakyReLU
+pre-activation away from 0, so the comparison measures arithmetic only (tolerance 1e-4; the attention vectors' gradients
+are excluded: with all logits on one LeakyReLU branch softmax shift-invariance makes them exactly 0 / pure cancellation).
+"signed": ordinary random parameters; a handful of the 77 M pre-activations lie within fp32 round-off of 0 and fall on
+either side in the two summation orders, which moves gradients by ~1e-3 of their norm (the reference has the same
+sensitivity) -- tolerance 5e-3, all parameters included."""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import msha_gnn_b200 as mg
+from msha_gnn_b200 import dist as md
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+rng = np.random.default_rng(7)
+N, F, H, d, P = 20011, 64, 8, 32, 300_000
+deg = np.minimum(1 + (rng.pareto(1.2, N) * 8).astype(np.int64), 3000)          # power-law rows: hub segments on every rank
+rows = np.repeat(np.arange(N), deg); cols = rng.integers(0, N, rows.size)
+key = np.unique(rows * N + cols); rows, cols = key // N, key % N
+src, dst = rng.integers(0, N, P), rng.integers(0, N, P)
+src_d, dst_d = torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev)
+G = torch.from_numpy(rng.standard_normal((P, 256)).astype(np.float32)).to(dev)
+g_full = mg.Graph.from_coo(torch.from_numpy(rows).to(dev), torch.from_numpy(cols).to(dev), N, N)
+part = md.Partition(N, world, rank)
+keep = (rows >= part.lo) & (rows < part.hi)
+pg = md.partition_graph(torch.from_numpy(rows[keep]).to(dev), torch.from_numpy(cols[keep]).to(dev), part)
+lo, hi = (P * rank) // world, (P * (rank + 1)) // world
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+ok = True
+for construction, tol in (("positive", 1e-4), ("signed", 5e-3)):
+    torch.manual_seed(3)
+    model = mg.GATLinkModel(F, H * d, H, 2, 256, dropout=0.0).to(dev)
+    if construction == "positive":
+        with torch.no_grad():
+            for p_ in model.convs.parameters():
+                p_.abs_()
+            model.predictor.lins[0].weight.abs_().mul_(1e-4)
+            model.predictor.lins[0].bias.fill_(0.5)
+    x_full = torch.from_numpy(rng.random((N, F)).astype(np.float32) * 0.3).to(dev)
+    xf = x_full.clone().requires_grad_(True)
+    out_ref = model(xf, g_full, src_d, dst_d)
+    (out_ref * G).sum().backward()
+    gref = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}   # the last Linear is never applied
+    gx_ref = xf.grad.clone()
+    model.zero_grad(set_to_none=True)
+    for overlap in (True, False):
+        xl = x_full[part.lo:part.hi].clone().requires_grad_(True)
+        h = md.gat_encode(model.convs, xl, pg, part, overlap=overlap)
+        out = md.score_pairs(model.predictor, h, src_d[lo:hi], dst_d[lo:hi], part)
+        (out * G[lo:hi]).sum().backward()
+        md.allreduce_gradients([p for p in model.parameters() if p.grad is not None], world=world)
+        errs = {"out": rel(out.detach(), out_ref.detach()[lo:hi]), "dx": rel(xl.grad, gx_ref[part.lo:part.hi])}
+        for n, p in model.named_parameters():
+            if n in gref:
+                errs["d" + n] = rel(p.grad, gref[n])
+        checked = {k: v for k, v in errs.items() if not (construction == "positive" and (".a_nbr" in k or ".a_self" in k))}
+        worst = torch.tensor([max(checked.values())], device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"{construction:8s} overlap={overlap} world={world} hub_rows={pg.hub_rows().n_hub} worst checked rel err "
+                  f"{float(worst):.3e} (tol {tol:g})", {k: f"{v:.1e}" for k, v in errs.items()}, flush=True)
+        ok = ok and float(worst) < tol
+        model.zero_grad(set_to_none=True)
+dist.destroy_process_group()
+if rank == 0:
+    print("PARITY OK" if ok else "PARITY FAILED", flush=True)
+sys.exit(0 if ok else 1)
