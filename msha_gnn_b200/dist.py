@@ -15,6 +15,8 @@ tensors under the gloo backend for the tests.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -155,9 +157,16 @@ def partition_graph(rows: torch.Tensor, cols: torch.Tensor, part: Partition) -> 
     return Graph.from_coo(rows.to(torch.int64) - part.lo, part.to_padded(cols), part.n_local, part.n_padded)
 
 
-def gat_encode(convs, x_local, pgraph: Graph, part: Partition, group=None, training=True, overlap=True):
+# Early reduce-scatter of d Wh under the attention row pass (GradSink).  Off by default: measured on B200 x2 / x8 (R-MAT,
+# profiles/README.md) the collective's CTAs and the row pass compete for the same SMs -- no gain with a host sync per
+# step (24.5 vs 24.5 ms at N = 2, 70 vs 73 ms at N = 8) and a loss when the host runs ahead (29 vs 25 ms at N = 2).
+OVERLAP_DEFAULT = os.environ.get("MSHA_DIST_OVERLAP", "0") != "0"
+
+
+def gat_encode(convs, x_local, pgraph: Graph, part: Partition, group=None, training=True, overlap=None):
     """Partitioned forward of a stack of ``GATConv`` layers (same arithmetic as ``GATConv.forward``): per layer an
     all-gather of Wh and of s_nbr in the forward and the reduce-scatter of their gradients in the backward."""
+    overlap = OVERLAP_DEFAULT if overlap is None else overlap
     h = x_local
     for conv in convs:
         H, D = conv.heads, conv.out_features
