@@ -16,7 +16,9 @@ from conftest import rel_err
 DEV = "cuda:0"
 
 
-def test_world1_partition_equals_plain_conv():
+@pytest.mark.parametrize("overlap", [False, True])
+def test_world1_partition_equals_plain_conv(overlap):
+    """overlap=True runs the split backward (d Wh first, handed to the GradSink, then row pass and d s_nbr sums)."""
     rng = np.random.default_rng(0)
     N, Fin, H, d = 200, 32, 4, 16
     adj = (rng.random((N, N)) < 0.1).astype(np.float32)
@@ -30,7 +32,7 @@ def test_world1_partition_equals_plain_conv():
     part = Partition(N, 1, 0)
     pg = partition_graph(torch.from_numpy(r).to(DEV), torch.from_numpy(c).to(DEV), part)
     x2 = x.detach().clone().requires_grad_(True)
-    out = gat_encode(convs, x2, pg, part)
+    out = gat_encode(convs, x2, pg, part, overlap=overlap)
     assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
     ref.square().sum().backward()
     gref = x.grad.clone()
