@@ -314,14 +314,42 @@ def run_ours(args):
     launches = lib.msha_launch_count() - l0
     ms_dev = ev0.elapsed_time(ev1) / args.steps
     # ---- end-to-end timing: pinned host batch -> device every step, loss back to the host
+    # The pinned batch of step i+1 is copied on a second stream while step i computes (two device buffers, an event per
+    # buffer) -- every step's host->device copy and its loss read-back stay inside the timed region.
+    copy_stream = torch.cuda.Stream()
+    bufs = [torch.empty_like(pos_dev), torch.empty_like(pos_dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        b = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])              # the step that last read this buffer has finished
+            bufs[b].copy_(pos_host, non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def host_fed_step(i, seed_it):
+        b = i & 1
+        torch.cuda.current_stream().wait_event(ready[b])
+        if i + 1 < host_fed_total[0]:
+            prefetch(i + 1)
+        loss_ = step(seed_it, bufs[b])
+        consumed[b].record()
+        return float(loss_.item())
+
+    host_fed_total = [2]
+    for b in range(2):
+        consumed[b].record()
+    prefetch(0)
     for it in range(2):                # untimed: the first host-fed steps allocate the per-step staging tensors
-        float(step(20_000 + it, pos_host.to(dev, non_blocking=True)).item())
+        host_fed_step(it, 20_000 + it)
     barrier()
+    host_fed_total[0] = args.steps
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
+    prefetch(0)
     for it in range(args.steps):
-        pos = pos_host.to(dev, non_blocking=True)
-        loss_host = float(step(args.warmup + args.steps + it, pos).item())
+        loss_host = host_fed_step(it, args.warmup + args.steps + it)
     ev3.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -416,7 +444,8 @@ def run_ours(args):
                    "l2_policy": "per-step working set (>= 4*P*pred_hidden bytes of scores) exceeds the 126 MB L2; no explicit flush"},
         "pairs_per_sec": P_global / (ms_dev / 1e3),
         "e2e": {"value": total_edges / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(pos_host.numel() * 8), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(pos_host.numel() * 8), "d2h_bytes_per_step": 4,
+                "input_pipeline": "pinned batch of step i+1 copied on a second stream while step i computes; loss.item() every step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
