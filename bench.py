@@ -280,12 +280,18 @@ def run_ours(args):
         src = torch.cat([pos[0], nsrc + part.lo])
         dst = torch.cat([pos[1], ndst])
         opt.zero_grad(set_to_none=True)
-        if world == 1:
-            out = model(x, graph, src, dst)                                      # (P, pred_hidden) sigmoid scores
+        if args.unfused_loss:
+            if world == 1:
+                out = model(x, graph, src, dst)                                  # (P, pred_hidden) sigmoid scores
+            else:
+                h = mdist.gat_encode(model.convs, x, graph, part)
+                out = mdist.score_pairs(model.predictor, h, src, dst, part)
+            loss = mg.functional.nll_loss(out, labels)                           # LLP.py:235 read-out shape
+        elif world == 1:
+            loss = model.loss(x, graph, src, dst, labels)                        # same read-out, d scores generated in-kernel
         else:
             h = mdist.gat_encode(model.convs, x, graph, part)
-            out = mdist.score_pairs(model.predictor, h, src, dst, part)
-        loss = mg.functional.nll_loss(out, labels)                               # LLP.py:235 read-out shape
+            loss = mdist.score_pairs(model.predictor, h, src, dst, part, target=labels)
         loss.backward()
         if world > 1:
             mdist.allreduce_gradients(params, world=world)
@@ -383,7 +389,7 @@ def run_ours(args):
         gemm_flops = sum(2.0 * sh[0] * sh[1] * sh[2] for f, a, b, sh in kt.records if f.startswith("msha_gemm") and len(sh) >= 3) / 2
         C_, Hd_ = wl["hidden"], wl["pred_hidden"]
         tensor_flops = {"msha_gemm_tf32x3": gemm_flops, "msha_score_mlp_fwd": 2.0 * P * C_ * Hd_,
-                        "msha_score_mlp_bwd": 4.0 * P * C_ * Hd_}
+                        "msha_score_mlp_bwd": 4.0 * P * C_ * Hd_, "msha_score_mlp_nll_bwd": 4.0 * P * C_ * Hd_}
         _, bf16_peak, _ = load_peaks()
         tf32_peak = bf16_peak / 2.0              # kind::tf32 runs at half the bf16 rate; bf16 peak = measured cuBLAS number
         for k in kernels:
@@ -698,6 +704,8 @@ def main():
     ap.add_argument("--workload", default="ddi", choices=list(WORKLOADS) + ["flow", "flow-ours"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused-loss", action="store_true",
+                    help="separate nll_loss op: the dense d scores tensor is written and re-read (default: fused into the scorer backward)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3

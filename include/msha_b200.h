@@ -191,6 +191,13 @@ int msha_score_mlp_fwd(const float* hi_tab, const float* hj_tab, const int64_t* 
 int msha_score_mlp_bwd(const float* dout, const float* out, const float* hi_tab, const float* hj_tab, const int64_t* src,
                        const int64_t* dst, int64_t P, int64_t C, const float* W0, int64_t Hd, int act, float slope,
                        float* G, float* dhi, float* dhj, float* dW0, float* db0, void* ws, size_t ws_bytes, void* stream);
+/* Same backward with the F.nll_loss read-out (LLP.py:235: loss = -mean_p out[p, target[p]]) folded in: dOut is never
+ * materialised -- the producers of kernel (1) generate dOut[p, c] = (c == target[p]) ? -gout[0] / P : 0 on the fly.
+ * gout: float[1] on the device (upstream gradient of the scalar loss).  Out-of-range targets contribute nothing. */
+int msha_score_mlp_nll_bwd(const int64_t* target, const float* gout, const float* out, const float* hi_tab,
+                           const float* hj_tab, const int64_t* src, const int64_t* dst, int64_t P, int64_t C,
+                           const float* W0, int64_t Hd, int act, float slope, float* G, float* dhi, float* dhj,
+                           float* dW0, float* db0, void* ws, size_t ws_bytes, void* stream);
 /* builder-defined sampler (the reference's --ns_rate flags are dead code, LLP.py:26-29) */
 int msha_negative_sample(uint64_t seed, int64_t P, int64_t n_src, int64_t n_dst, int64_t* src, int64_t* dst,
                          void* stream);

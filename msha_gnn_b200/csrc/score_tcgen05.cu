@@ -385,7 +385,9 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY, int act, float slope,
                     float* __restrict__ G, float* __restrict__ db, const float* __restrict__ hi_tab,
                     const float* __restrict__ hj_tab, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
-                    int64_t P, int K /*hidden*/, int N /*C*/, float* __restrict__ dhi, float* __restrict__ dhj) {
+                    int64_t P, int K /*hidden*/, int N /*C*/, float* __restrict__ dhi, float* __restrict__ dhj,
+                    const int64_t* __restrict__ nll_target, const float* __restrict__ nll_gout) {
+    // nll_target != NULL: dOut is not read -- it is -gout/P in column target[p] of row p and 0 elsewhere (nll read-out)
     using S = SCfg<BLOCK_N, CTAS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -446,8 +448,8 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                     const uint32_t a_d = smem_u32(st), a_y = a_d + S::A_BYTES;
                     const uint32_t b_hi = smem_u32(st + 2 * S::A_BYTES), b_lo = b_hi + S::B_BYTES;
                     const uint32_t raw = smem_u32(&full_raw[stage]);
-                    mbar_arrive_expect_tx(raw, 2 * S::A_BYTES);
-                    tma_load_2d(a_d, &tmD, raw, kb * BLOCK_K, row_c);           // dOut tile -> becomes G_hi in place
+                    mbar_arrive_expect_tx(raw, (nll_target ? 1 : 2) * S::A_BYTES);
+                    if (!nll_target) tma_load_2d(a_d, &tmD, raw, kb * BLOCK_K, row_c);   // dOut tile -> becomes G_hi in place
                     tma_load_2d(a_y, &tmY, raw, kb * BLOCK_K, row_c);           // out  tile -> becomes G_lo in place
                     const uint32_t bar = smem_u32(&full_b[stage]);
                     if (rank == 0) mbar_arrive_expect_tx(bar, CTAS * 2 * S::B_BYTES);
@@ -494,6 +496,7 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
             default: break;
         }
         auto dact = [&](float yv) { return yv > thr ? fmaf(yv, fmaf(a2, yv, a1), a0) : fmaf(b1, yv, b0); };
+        const float nll_g = nll_target ? -__ldg(nll_gout) / (float)P : 0.f;
         float4 csum[16];                                         // bias-gradient partials per k-block (K <= 256)
 #pragma unroll
         for (int j = 0; j < 16; ++j) csum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -501,10 +504,16 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
             const int64_t m0 = (tp * CTAS + rank) * BLOCK_M;
             uint32_t off[RPT];
             bool pv[RPT];
+            int lab[RPT];                                        // nll read-out: the one column of the row that carries a gradient
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
                 off[i] = sw64_offset(rbase + RSTEP * i, c);
                 pv[i] = m0 + rbase + RSTEP * i < P;
+                lab[i] = -1;
+                if (nll_target && pv[i]) {
+                    const int64_t tg = nll_target[m0 + rbase + RSTEP * i];
+                    lab[i] = (tg >= 0 && tg < K) ? (int)tg : -1;
+                }
             }
 #pragma unroll
             for (int kb = 0; kb < 16; ++kb) {
@@ -516,7 +525,13 @@ score_bwd_dz_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                     float4 d[RPT], y[RPT];
 #pragma unroll
                     for (int i = 0; i < RPT; ++i) {
-                        d[i] = lds128(smem_u32(st) + off[i]);
+                        if (nll_target) {
+                            const int dk = lab[i] - k;               // 0..3: the labelled column lies in this 16-byte chunk
+                            d[i] = make_float4(dk == 0 ? nll_g : 0.f, dk == 1 ? nll_g : 0.f, dk == 2 ? nll_g : 0.f,
+                                               dk == 3 ? nll_g : 0.f);
+                        } else {
+                            d[i] = lds128(smem_u32(st) + off[i]);
+                        }
                         y[i] = lds128(smem_u32(st) + S::A_BYTES + off[i]);
                     }
 #pragma unroll
@@ -971,9 +986,9 @@ namespace {
 template <int BN>
 int launch_dz(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* dout, const float* outp, int act, float slope,
               float* G, float* db, const float* hi_tab, const float* hj_tab, const int64_t* src, const int64_t* dst, int64_t P,
-              int Hd, int C, float* dhi, float* dhj, cudaStream_t st) {
+              int Hd, int C, float* dhi, float* dhj, const int64_t* nll_target, const float* nll_gout, cudaStream_t st) {
     CUtensorMap td, ty;                                   // dOut / out as K-major [P, Hd] operands, boxes {16, 128}
-    int rcm = tc_make_map(&td, dout, Hd, P, Hd, BLOCK_K, BLOCK_M, false);
+    int rcm = tc_make_map(&td, dout ? dout : outp, Hd, P, Hd, BLOCK_K, BLOCK_M, false);   // unused in the nll variant
     if (rcm) return rcm;
     rcm = tc_make_map(&ty, outp, Hd, P, Hd, BLOCK_K, BLOCK_M, false);
     if (rcm) return rcm;
@@ -985,22 +1000,24 @@ int launch_dz(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* dout,
         attr_set = true;
     }
     return launch_tiles(kern, NUM_THREADS, S::SMEM_BYTES, (P + BLOCK_M - 1) / BLOCK_M, st, tbh, tbl, td, ty, act, slope, G, db, hi_tab,
-                        hj_tab, src, dst, P, Hd, C, dhi, dhj);
+                        hj_tab, src, dst, P, Hd, C, dhi, dhj, nll_target, nll_gout);
 }
 }  // namespace
 
 // Backward of msha_score_mlp_fwd.  dout/out: [P, Hd] contiguous.  G: [P, Hd] scratch (receives dOut*act'(out)).
 // dhi/dhj [n, C] must hold the running gradients (atomically accumulated); dW0 [Hd, C] and db0 [Hd] are overwritten.
 // Needs Hd % 4 == 0 in addition to msha_score_mlp_supported.
-MSHA_API int msha_score_mlp_bwd(const float* dout, const float* out, const float* hi_tab, const float* hj_tab,
-                                const int64_t* src, const int64_t* dst, int64_t P, int64_t C, const float* W0, int64_t Hd,
-                                int act, float slope, float* G, float* dhi, float* dhj, float* dW0, float* db0, void* ws,
-                                size_t ws_bytes, void* stream) {
+static int score_mlp_bwd_impl(const float* dout, const int64_t* nll_target, const float* nll_gout, const float* out,
+                              const float* hi_tab, const float* hj_tab, const int64_t* src, const int64_t* dst, int64_t P,
+                              int64_t C, const float* W0, int64_t Hd, int act, float slope, float* G, float* dhi, float* dhj,
+                              float* dW0, float* db0, void* ws, size_t ws_bytes, void* stream) {
     MSHA_REQUIRE(msha_score_mlp_supported(hi_tab, hj_tab, W0, C, Hd) == 0 && (Hd & 3) == 0 && C <= 256,
                  "score_mlp_bwd: unsupported shape/alignment (need C <= 256, Hd <= 256, both multiples of 4)");
     MSHA_REQUIRE(ws_bytes >= msha_score_mlp_workspace_bytes(C, Hd), "score_mlp_bwd: workspace too small");
     MSHA_REQUIRE(((uintptr_t)dout & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)G & 15) == 0,
                  "score_mlp_bwd: dout/out/G must be 16-byte aligned");
+    MSHA_REQUIRE((dout != nullptr) != (nll_target != nullptr), "score_mlp_bwd: exactly one of dout / nll target");
+    MSHA_REQUIRE(nll_target == nullptr || nll_gout != nullptr, "score_mlp_nll_bwd: gout required");
     if (P == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     float* wt_hi = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255) + 2 * C * Hd;
@@ -1016,9 +1033,9 @@ MSHA_API int msha_score_mlp_bwd(const float* dout, const float* out, const float
     if (rc) return rc;
     rc = tc_make_map(&tbl, wt_lo, Hd, C, Hd, BLOCK_K, BN / SCORE_CTAS, false);
     if (rc) return rc;
-    if (BN == 256) rc = launch_dz<256>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, st);
-    else if (BN == 128) rc = launch_dz<128>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, st);
-    else rc = launch_dz<64>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, st);
+    if (BN == 256) rc = launch_dz<256>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, nll_target, nll_gout, st);
+    else if (BN == 128) rc = launch_dz<128>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, nll_target, nll_gout, st);
+    else rc = launch_dz<64>(tbh, tbl, dout, out, act, slope, G, db0, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dhi, dhj, nll_target, nll_gout, st);
     if (rc) return rc;
     // ---- part 2: dW0 = G^T @ Z
     const bool dw_pairs = SCORE_CTAS == 2 && Hd > 128;   // CTA pairs split the Hd rows of G: pointless for Hd <= 128
@@ -1060,4 +1077,24 @@ MSHA_API int msha_score_mlp_bwd(const float* dout, const float* out, const float
     score_bwd_dw_kernel<1><<<grid, NUM_THREADS, WCfg<1>::SMEM_BYTES, st>>>(tg, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dW0);
     MSHA_LAUNCH_OK();
     return 0;
+}
+
+MSHA_API int msha_score_mlp_bwd(const float* dout, const float* out, const float* hi_tab, const float* hj_tab,
+                                const int64_t* src, const int64_t* dst, int64_t P, int64_t C, const float* W0, int64_t Hd,
+                                int act, float slope, float* G, float* dhi, float* dhj, float* dW0, float* db0, void* ws,
+                                size_t ws_bytes, void* stream) {
+    MSHA_REQUIRE(dout != nullptr, "score_mlp_bwd: dout is NULL");
+    return score_mlp_bwd_impl(dout, nullptr, nullptr, out, hi_tab, hj_tab, src, dst, P, C, W0, Hd, act, slope, G, dhi, dhj, dW0,
+                              db0, ws, ws_bytes, stream);
+}
+
+// Backward of the scorer with the nll read-out folded in (loss = -mean_p out[p, target[p]], LLP.py:235): dOut is generated
+// by the producer warps, never stored.
+MSHA_API int msha_score_mlp_nll_bwd(const int64_t* target, const float* gout, const float* out, const float* hi_tab,
+                                    const float* hj_tab, const int64_t* src, const int64_t* dst, int64_t P, int64_t C,
+                                    const float* W0, int64_t Hd, int act, float slope, float* G, float* dhi, float* dhj,
+                                    float* dW0, float* db0, void* ws, size_t ws_bytes, void* stream) {
+    MSHA_REQUIRE(target != nullptr && gout != nullptr, "score_mlp_nll_bwd: target / gout is NULL");
+    return score_mlp_bwd_impl(nullptr, target, gout, out, hi_tab, hj_tab, src, dst, P, C, W0, Hd, act, slope, G, dhi, dhj, dW0,
+                              db0, ws, ws_bytes, stream);
 }

@@ -188,8 +188,11 @@ def gat_encode(convs, x_local, pgraph: Graph, part: Partition, group=None, train
     return h
 
 
-def score_pairs(predictor, h_local, src_global, dst_global, part: Partition, group=None):
+def score_pairs(predictor, h_local, src_global, dst_global, part: Partition, group=None, target=None):
     """Data-parallel link scoring: this rank scores its own pair shard against the all-gathered embeddings;
-    the backward reduce-scatters d h to the owning ranks."""
+    the backward reduce-scatters d h to the owning ranks.  With ``target`` the rank's mean nll read-out is returned
+    instead of the scores (fused scorer + loss backward)."""
     h_g = all_gather_rows(h_local, part, group)
+    if target is not None:
+        return predictor.nll_loss_pairs(h_g, h_g, part.to_padded(src_global), part.to_padded(dst_global), target)
     return predictor.forward_pairs(h_g, h_g, part.to_padded(src_global), part.to_padded(dst_global))

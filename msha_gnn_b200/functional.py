@@ -605,6 +605,62 @@ class _ScoreMLP(torch.autograd.Function):
 FUSED_SCORE_BWD = True     # False: unfused backward (act', gather, two GEMMs, scatter) -- kept for validation
 
 
+class _ScoreMLPNll(torch.autograd.Function):
+    """Fused scorer + nll read-out: ``F.nll_loss(act((h_i[src]*h_j[dst]) @ W0.T + b0), target)`` (LLP.py:233-235).
+    Forward = the scorer kernel + the read-out reduction; the backward never materialises d out -- the producer warps of
+    the dZ kernel generate it from ``target`` (it is -g/P in one column per row)."""
+
+    @staticmethod
+    def forward(ctx, hi, hj, src, dst, W0, b0, target, act):
+        hi, hj, W0 = _c(hi), _c(hj), _c(W0)
+        P = src.numel() if src is not None else hi.shape[0]
+        Hd, C = W0.shape
+        dev = hi.device
+        out = torch.empty((P, Hd), dtype=torch.float32, device=dev)
+        lib = ops._lib.lib()
+        ws = workspace(lib.msha_score_mlp_workspace_bytes(C, Hd), dev)
+        call("msha_score_mlp_fwd", ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C, ptr(W0),
+             ptr(b0) if b0 is not None else None, Hd, act, LRELU_SLOPE, ptr(out), Hd, ws.data_ptr(), ws.numel(), _stream())
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        status = torch.empty(1, dtype=torch.int32, device=dev)
+        ws2 = workspace(lib.msha_nll_workspace_bytes(), dev)
+        call("msha_nll_loss_fwd", ptr(out), ptr(target, torch.int64), P, Hd, loss.data_ptr(), ptr(status, I32),
+             ws2.data_ptr(), ws2.numel(), _stream())
+        ctx.act, ctx.has_bias = act, b0 is not None
+        ctx.save_for_backward(hi, hj, src, dst, W0, out, target)
+        ctx.mark_non_differentiable(out)
+        return loss, out
+
+    @staticmethod
+    def backward(ctx, gloss, _gout_unused):
+        hi, hj, src, dst, W0, out, target = ctx.saved_tensors
+        P, Hd = out.shape
+        C = W0.shape[1]
+        lib = ops._lib.lib()
+        g = torch.empty_like(out)
+        dhi, dhj = torch.zeros_like(hi), torch.zeros_like(hj)
+        dW = torch.empty_like(W0)
+        db = torch.empty(Hd, dtype=torch.float32, device=out.device)
+        ws = workspace(lib.msha_score_mlp_workspace_bytes(C, Hd), out.device)
+        gl = _c(gloss.reshape(1).float())
+        call("msha_score_mlp_nll_bwd", ptr(target, torch.int64), ptr(gl), ptr(out), ptr(hi), ptr(hj), ptr(src, torch.int64),
+             ptr(dst, torch.int64), P, C, ptr(W0), Hd, ctx.act, LRELU_SLOPE, ptr(g), ptr(dhi), ptr(dhj), ptr(dW), ptr(db),
+             ws.data_ptr(), ws.numel(), _stream())
+        return dhi, dhj, None, None, dW, (db if ctx.has_bias else None), None, None
+
+
+def score_mlp_nll_supported(hi, hj, W0):
+    Hd, C = W0.shape
+    return FUSED_SCORE_BWD and score_mlp_supported(hi, hj, W0) and Hd % 4 == 0 and C <= 256
+
+
+def score_mlp_nll(hi, hj, src, dst, W0, b0, target, act=ACT_SIGMOID_RELU):
+    """-> (loss, scores): mean nll read-out of the fused scorer; ``scores`` is returned for metrics (not differentiable)."""
+    if target.dtype != torch.int64:
+        target = target.long()
+    return _ScoreMLPNll.apply(hi, hj, src, dst, W0, b0, target.contiguous(), act)
+
+
 def score_mlp_supported(hi, hj, W0):
     lib = ops._lib.lib()
     return (hi.is_cuda and hi.dtype == torch.float32 and hi.is_contiguous() and hj.is_contiguous() and W0.is_contiguous()

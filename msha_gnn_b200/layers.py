@@ -378,6 +378,19 @@ class LinkPredictor(nn.Module):
         """Fused pair-gather entry: scores pairs (src[p], dst[p]) of the embedding tables h_i / h_j."""
         return self._score(h_i, h_j, src, dst)
 
+    def nll_loss_pairs(self, h_i, h_j, src, dst, target):
+        """``F.nll_loss(self.forward_pairs(h_i, h_j, src, dst), target)`` (the read-out of LLP.py:233-235) with the loss
+        folded into the fused scorer: d scores is generated inside the backward kernel instead of being streamed through
+        HBM.  Falls back to the two separate ops whenever the fused scorer does not apply."""
+        if self.predictor == 'mlp':
+            hidden = list(self.lins)[:-1]
+            drop_on = self.training and self.dropout > 0
+            if (self.fused and len(hidden) == 1 and not drop_on
+                    and Fn.score_mlp_nll_supported(h_i, h_j, hidden[0].weight)):
+                loss, _ = Fn.score_mlp_nll(h_i, h_j, src, dst, hidden[0].weight, hidden[0].bias, target, ACT_SIGMOID_RELU)
+                return loss
+        return Fn.nll_loss(self._score(h_i, h_j, src, dst), target)
+
     def _score(self, hi, hj, src, dst):
         if self.predictor == 'mlp':
             hidden = list(self.lins)[:-1]
@@ -496,3 +509,8 @@ class GATLinkModel(nn.Module):
     def forward(self, x, graph, src, dst):
         h = self.encode(x, graph)
         return self.predictor.forward_pairs(h, h, src, dst)
+
+    def loss(self, x, graph, src, dst, labels):
+        """nll read-out of the pair scores (LLP.py:233-235) with the fused scorer + loss backward."""
+        h = self.encode(x, graph)
+        return self.predictor.nll_loss_pairs(h, h, src, dst, labels)

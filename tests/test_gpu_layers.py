@@ -376,3 +376,26 @@ def test_fused_scorer_vs_oracle(P, C, Hd, Nn, fused_bwd, monkeypatch):
     assert rel_err(_np(h.grad), hd.grad.numpy()) < TOL
     assert rel_err(_np(lp.lins[0].weight.grad), W[0].grad.numpy()) < TOL
     assert rel_err(_np(lp.lins[0].bias.grad), b[0].grad.numpy()) < TOL
+
+
+@pytest.mark.parametrize("P,C,Hd,Nn", [(1000, 256, 256, 300), (4097, 64, 128, 50), (70001, 256, 256, 4267), (33, 8, 4, 5)])
+def test_fused_scorer_nll_matches_separate_ops(P, C, Hd, Nn):
+    """nll read-out folded into the scorer backward (d scores generated in the dZ producers) == scorer + nll_loss ops."""
+    g = torch.Generator().manual_seed(P + 1)
+    lp = mg.LinkPredictor("mlp", C, Hd, 1, 2, 0.0).to(DEV)
+    h = (torch.randn(Nn, C, generator=g) * 0.5).to(DEV)
+    src = torch.randint(0, Nn, (P,), generator=g).to(DEV)
+    dst = torch.randint(0, Nn, (P,), generator=g).to(DEV)
+    tgt = torch.randint(0, min(Hd, 2), (P,), generator=g).to(DEV)
+    h1 = h.clone().requires_grad_(True)
+    loss1 = 3.0 * Fn.nll_loss(lp.forward_pairs(h1, h1, src, dst), tgt)
+    loss1.backward()
+    ref = [h1.grad.clone(), lp.lins[0].weight.grad.clone(), lp.lins[0].bias.grad.clone()]
+    lp.zero_grad(set_to_none=True)
+    h2 = h.clone().requires_grad_(True)
+    loss2 = 3.0 * lp.nll_loss_pairs(h2, h2, src, dst, tgt)
+    loss2.backward()
+    assert abs(float(loss1) - float(loss2)) <= 1e-6 * max(1.0, abs(float(loss1)))
+    got = [h2.grad, lp.lins[0].weight.grad, lp.lins[0].bias.grad]
+    for a, b in zip(got, ref):
+        assert rel_err(_np(a), _np(b)) < 1e-5
