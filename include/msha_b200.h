@@ -203,6 +203,34 @@ int msha_negative_sample(uint64_t seed, int64_t P, int64_t n_src, int64_t n_dst,
                          void* stream);
 int msha_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* keep, void* stream);
 
+/* ==== callers either side of the path ==== */
+
+/* ---- 8f-1 LLP distillation read-outs.  KD_cosine(s, t) = 1 - mean_p cos(s[idx_s[p]], t[idx_t[p]]) replaces
+ *      `1 - cosine_similarity(h[source_index], t_h[source_index].detach(), dim=-1).mean()` (LLP.py:34-35,236) with the
+ *      row gathers fused (idx NULL -> row p); torch semantics: each norm clamped at eps = 1e-8.  cos: float[P] saved for
+ *      the backward; loss / gout: float[1] on the device; ds / dt are accumulated into, either may be NULL. ---- */
+size_t msha_loss_workspace_bytes(void);
+int msha_kd_cosine_fwd(const float* s, const float* t, const int64_t* idx_s, const int64_t* idx_t, int64_t P, int64_t C,
+                       int64_t n_s, int64_t n_t, float eps, float* cosv, float* loss, int32_t* status, void* ws,
+                       size_t ws_bytes, void* stream);
+int msha_kd_cosine_bwd(const float* s, const float* t, const int64_t* idx_s, const int64_t* idx_t, int64_t P, int64_t C,
+                       int64_t n_s, int64_t n_t, float eps, const float* cosv, const float* gout, float* ds, float* dt,
+                       void* stream);
+/* torch.nn.MSELoss() (mean over all n elements), LLP.py:221,237; da / db are overwritten, either may be NULL */
+int msha_mse_loss_fwd(const float* a, const float* b, int64_t n, float* loss, void* ws, size_t ws_bytes, void* stream);
+int msha_mse_loss_bwd(const float* a, const float* b, int64_t n, const float* gout, float* da, float* db, void* stream);
+
+/* ---- 8f-3 GraphSAGE baseline: out[b, :] = adj[src[b], :] * x[b, :] (SGAE.py:53) over the CSR of adj (val NULL -> 1);
+ *      the map is diagonal: the same call with x = d out is the backward ---- */
+int msha_csr_rows_mul(const int32_t* rowptr, const int32_t* col, const float* val, const int64_t* src, int64_t B,
+                      int64_t n_rows, int64_t M, const float* x, float* out, void* stream);
+
+/* ---- 8f-4 attention export: per item (CSR row, or CSC column through perm) the maximum of the per-edge attention
+ *      w[slot * H + head] (head < 0: mean over heads), the smallest slot attaining it (-1: empty item) and the number of
+ *      ties -- replaces argwhere(row == max(row)) over the dense (N, M) / (N, N) dumps, Explainer.py:25-30 ---- */
+int msha_segment_argmax(const int32_t* ptr, const int32_t* perm, const float* w, int H, int head, int64_t n_items,
+                        float* vmax, int32_t* first, int32_t* ties, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,12 +10,15 @@ from .graph import Graph, as_graph                   # noqa: F401
 from .intra import GroupLists                        # noqa: F401
 from .layers import (GAT, GATConv, GATLinkModel, GraphAttentionLayer, GraphConvolution, HGANELayer, LinkPredictor,   # noqa: F401
                      Ours, OursLayer, OursLayer2, OursLayer3, Teacher_LinkPredictor, ablation1, ablation2,
-                     ablation3, dense_attention, last_attention)
+                     ablation3, dense_attention, last_attention, MLP, KD_cosine, llp_distill_loss, GCN, GraphSAGE,
+                     export_attention)
+from .data import HigherDataset, read_flow_files, normalize_adjacency_matrix   # noqa: F401
 from . import functional                             # noqa: F401
 
 __all__ = ["Graph", "as_graph", "GroupLists", "GAT", "GATConv", "GATLinkModel", "GraphAttentionLayer",
            "GraphConvolution", "HGANELayer", "LinkPredictor", "Teacher_LinkPredictor", "Ours", "OursLayer", "OursLayer2",
-           "OursLayer3", "ablation1", "ablation2", "ablation3", "functional"]
+           "OursLayer3", "ablation1", "ablation2", "ablation3", "functional", "MLP", "KD_cosine", "llp_distill_loss", "GCN",
+           "GraphSAGE", "export_attention", "HigherDataset", "read_flow_files", "normalize_adjacency_matrix"]
 
 
 def build(force: bool = False):

@@ -704,3 +704,164 @@ def negative_sample(seed: int, n_pairs: int, n_src: int, n_dst: int, device):
     dst = torch.empty(n_pairs, dtype=torch.int64, device=device)
     call("msha_negative_sample", seed, n_pairs, n_src, n_dst, ptr(src, torch.int64), ptr(dst, torch.int64), _stream())
     return src, dst
+
+
+# ------------------------------------------------------------------------------------------------
+# row SpMM over the canonical CSR with stored values: out[i] = sum_j w[e(i,j)] feat[j]
+# (GCN's second layer `adj.t().transpose(0, 1) @ support` == adj @ support, model.py:37,60)
+# ------------------------------------------------------------------------------------------------
+class _Spmm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, w, graph: Graph):
+        feat, w = _c(feat), _c(w)
+        C = feat.shape[1]
+        out = torch.empty((graph.n_rows, C), dtype=torch.float32, device=feat.device)
+        hub = graph.hub_rows_plain()
+        scr = _hub_scratch(hub, 1, C, feat.device)
+        call("msha_gat_fwd", ptr(graph.rowptr, I32), ptr(graph.col, I32), graph.n_rows, None, None, ptr(feat), 1, C,
+             LRELU_SLOPE, ptr(w), None, ptr(out), ACT_NONE, None, 0.0, 0, hub.ptr, ptr(scr), _stream())
+        ctx.graph = graph
+        ctx.save_for_backward(w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (w,) = ctx.saved_tensors
+        g = ctx.graph
+        dout = _c(dout)
+        colptr, rowidx, perm = g.transpose_structure()
+        C = dout.shape[1]
+        dfeat = torch.empty((g.n_cols, C), dtype=torch.float32, device=dout.device)
+        call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), g.n_cols, ptr(w), ptr(dout), 1, C,
+             ptr(dfeat), 0, None, None, 0.0, 0, g.hub_cols_plain().ptr, _stream())
+        return dfeat, None, None
+
+
+def spmm(graph: Graph, w, feat):
+    return _Spmm.apply(feat, w.view(-1, 1), graph)
+
+
+# ------------------------------------------------------------------------------------------------
+# LLP distillation read-outs                                                   LLP.py:34-35,221,236-237
+# ------------------------------------------------------------------------------------------------
+class _KDCosine(torch.autograd.Function):
+    """1 - mean_p cos(s[idx_s[p]], t[idx_t[p]]) with the row gathers fused (idx None -> row p)."""
+
+    @staticmethod
+    def forward(ctx, s, t, idx_s, idx_t, eps):
+        s, t = _c(s), _c(t)
+        if s.dim() != 2 or t.dim() != 2 or s.shape[1] != t.shape[1]:
+            raise ValueError("kd_cosine: s and t must be (rows, C) with the same C")
+        P = idx_s.numel() if idx_s is not None else (idx_t.numel() if idx_t is not None else s.shape[0])
+        for idx, tab in ((idx_s, s), (idx_t, t)):
+            if idx is not None and idx.numel() != P:
+                raise ValueError("kd_cosine: index vectors must have the same length")
+            if idx is None and tab.shape[0] != P:
+                raise ValueError("kd_cosine: un-indexed operand must have one row per pair")
+        cosv = torch.empty(P, dtype=torch.float32, device=s.device)
+        loss = torch.empty((), dtype=torch.float32, device=s.device)
+        status = torch.empty(1, dtype=torch.int32, device=s.device)
+        lib = ops._lib.lib()
+        ws = workspace(lib.msha_loss_workspace_bytes(), s.device)
+        call("msha_kd_cosine_fwd", ptr(s), ptr(t), ptr(idx_s, torch.int64), ptr(idx_t, torch.int64), P, s.shape[1],
+             s.shape[0], t.shape[0], eps, ptr(cosv), loss.data_ptr(), ptr(status, I32), ws.data_ptr(), ws.numel(), _stream())
+        ctx.eps = eps
+        ctx.save_for_backward(s, t, idx_s, idx_t, cosv)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        s, t, idx_s, idx_t, cosv = ctx.saved_tensors
+        ds = torch.zeros_like(s) if ctx.needs_input_grad[0] else None
+        dt = torch.zeros_like(t) if ctx.needs_input_grad[1] else None
+        call("msha_kd_cosine_bwd", ptr(s), ptr(t), ptr(idx_s, torch.int64), ptr(idx_t, torch.int64), cosv.numel(), s.shape[1],
+             s.shape[0], t.shape[0], ctx.eps, ptr(cosv), _c(g).data_ptr(), ptr(ds), ptr(dt), _stream())
+        return ds, dt, None, None, None
+
+
+def _index(idx):
+    if idx is None:
+        return None
+    return (idx if idx.dtype == torch.int64 else idx.long()).contiguous()
+
+
+def kd_cosine(s, t, idx_s=None, idx_t=None, eps=1e-8):
+    """``KD_cosine`` (LLP.py:34-35): ``1 - cosine_similarity(s[idx_s], t[idx_t].detach(), dim=-1).mean()``; the teacher
+    operand is detached like the reference's."""
+    return _KDCosine.apply(s, t.detach(), _index(idx_s), _index(idx_t), float(eps))
+
+
+class _MseLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        if a.shape != b.shape:
+            raise ValueError(f"mse_loss: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+        a, b = _c(a), _c(b)
+        loss = torch.empty((), dtype=torch.float32, device=a.device)
+        lib = ops._lib.lib()
+        ws = workspace(lib.msha_loss_workspace_bytes(), a.device)
+        call("msha_mse_loss_fwd", ptr(a), ptr(b), a.numel(), loss.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        ctx.save_for_backward(a, b)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        call("msha_mse_loss_bwd", ptr(a), ptr(b), a.numel(), _c(g).data_ptr(), ptr(da), ptr(db), _stream())
+        return da, db
+
+
+def mse_loss(a, b):
+    """``torch.nn.MSELoss()(a, b)`` (mean over every element, LLP.py:221,237)."""
+    return _MseLoss.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# GraphSAGE baseline: adj[source_index] * x                                              SGAE.py:53
+# ------------------------------------------------------------------------------------------------
+class _CsrRowsMul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, graph: Graph, w, src):
+        x = _c(x)
+        B, M = x.shape
+        if M != graph.n_cols:
+            raise RuntimeError(f"adj[source_index] * x: x has {M} columns, the adjacency {graph.n_cols}")
+        out = torch.empty_like(x)
+        call("msha_csr_rows_mul", ptr(graph.rowptr, I32), ptr(graph.col, I32), ptr(w), ptr(src, torch.int64), B,
+             graph.n_rows, M, ptr(x), ptr(out), _stream())
+        ctx.graph = graph
+        ctx.save_for_backward(w, src)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        w, src = ctx.saved_tensors
+        g = ctx.graph
+        dout = _c(dout)
+        dx = torch.empty_like(dout)
+        call("msha_csr_rows_mul", ptr(g.rowptr, I32), ptr(g.col, I32), ptr(w), ptr(src, torch.int64), dout.shape[0],
+             g.n_rows, dout.shape[1], ptr(dout), ptr(dx), _stream())
+        return dx, None, None, None
+
+
+def csr_rows_mul(graph: Graph, x, src=None, values=None):
+    """``adj[src] * x`` for a (B, M) block ``x`` (rows of ``adj`` selected by ``src``; values default to the stored ones)."""
+    w = graph.val if values is None else values
+    return _CsrRowsMul.apply(x, graph, _c(w), _index(src))
+
+
+# ------------------------------------------------------------------------------------------------
+# attention export                                                   train.py:284-321, Explainer.py:25-30
+# ------------------------------------------------------------------------------------------------
+def segment_argmax(ptr_arr, w, heads=1, head=-1, perm=None):
+    """Per item of a CSR / CSC pointer array: (max, smallest slot attaining it or -1, tie count) of the per-edge weights."""
+    w = _c(w.detach())
+    n = ptr_arr.numel() - 1
+    vmax = torch.empty(n, dtype=torch.float32, device=w.device)
+    first = torch.empty(n, dtype=I32, device=w.device)
+    ties = torch.empty(n, dtype=I32, device=w.device)
+    call("msha_segment_argmax", ptr(ptr_arr, I32), ptr(perm, I32), ptr(w), heads, head, n, ptr(vmax), ptr(first, I32),
+         ptr(ties, I32), _stream())
+    return vmax, first, ties

@@ -65,10 +65,13 @@ def _gal_heads(x, layers, graph, training):
 # a-2  GAT                                                      GAT.py:38-58, LLP.py:148-168
 # =================================================================================================
 class GAT(nn.Module):
+    owns_features = True      # GAT.py:41-42 registers `features`; LLP.py:151-152 has that line commented out
+
     def __init__(self, n_features, n_classes, n_heads, dropout, gdp, N):
         super().__init__()
-        gdp_values = _gdp_column(gdp)
-        self.features = nn.Parameter(torch.cat((torch.rand([N, n_features])[:, :-1], gdp_values), dim=1))
+        if self.owns_features:
+            gdp_values = _gdp_column(gdp)
+            self.features = nn.Parameter(torch.cat((torch.rand([N, n_features])[:, :-1], gdp_values), dim=1))
         self.n_classes = n_classes
         self.n_heads = n_heads
         self.dropout = dropout
@@ -80,6 +83,8 @@ class GAT(nn.Module):
     def forward(self, *args):
         """``forward(adj)`` (GAT.py:53) or ``forward(input, adj)`` (LLP.py:163)."""
         if len(args) == 1:
+            if not self.owns_features:
+                raise TypeError("LLP.GAT.forward takes (input, adj)")
             x_in, adj = self.features, args[0]
         elif len(args) == 2:
             x_in, adj = args
@@ -91,6 +96,12 @@ class GAT(nn.Module):
         x = Fn.dropout(x, self.dropout, self.training)                         # GAT.py:56
         x = self.out_att(x, graph)                                             # inner ELU GAT.py:35
         return Fn.log_softmax(x, pre_elu=True)                                 # outer ELU + log_softmax GAT.py:57-58
+
+
+class LLPGAT(GAT):
+    """``LLP.GAT`` (LLP.py:148-168): same layers, no ``features`` parameter (no ``torch.rand`` draw at construction, no
+    such ``state_dict`` key), ``forward(input, adj)`` only.  ``msha_gnn_b200.llp.GAT`` is this class."""
+    owns_features = False
 
 
 # =================================================================================================
@@ -444,13 +455,15 @@ class GraphConvolution(nn.Module):
         if self.bias is not None:
             self.bias.data.uniform_(-stdv, stdv)
 
-    def forward(self, input, adj, values=None):
+    def forward(self, input, adj, values=None, transposed=False):
         """``adj.T @ (input @ W) + bias`` (model.py:36-39).  ``adj`` dense/Graph; its stored values weight
-        the edges (pass ``values`` to override, e.g. ``graph.normalized_values()``)."""
+        the edges (pass ``values`` to override, e.g. ``graph.normalized_values()``).  ``transposed=True`` evaluates the
+        layer on ``adj.t()`` -- ``adj @ (input @ W) + bias``, GCN's second layer (model.py:61) -- over the same graph
+        instead of building a second one from the transposed dense matrix."""
         graph = as_graph(adj)
         support = Fn.linear(input, self.weight)
         w = graph.val if values is None else values
-        out = Fn.spmm_t(graph, w, support)
+        out = Fn.spmm(graph, w, support) if transposed else Fn.spmm_t(graph, w, support)
         return out + self.bias if self.bias is not None else out
 
     def __repr__(self):
@@ -514,3 +527,162 @@ class GATLinkModel(nn.Module):
         """nll read-out of the pair scores (LLP.py:233-235) with the fused scorer + loss backward."""
         h = self.encode(x, graph)
         return self.predictor.nll_loss_pairs(h, h, src, dst, labels)
+
+
+# =================================================================================================
+# SURVEY.md section 8f-1: the LLP student (LLP.py:36-84) and its distillation step (LLP.py:217-248)
+# =================================================================================================
+class MLP(nn.Module):
+    """``LLP.MLP`` (LLP.py:36-84): Linear (+ norm) + ReLU + dropout per hidden layer, plain Linear last.  Each
+    ``relu(layer(h))`` is one tensor-core GEMM with the bias and ReLU in its epilogue."""
+
+    def __init__(self, num_layers, input_dim, hidden_dim, output_dim, dropout_ratio, norm_type="none"):
+        super().__init__()
+        self.num_layers = num_layers
+        self.norm_type = norm_type
+        self.dropout = nn.Dropout(dropout_ratio)
+        self.layers = nn.ModuleList()
+        self.norms = nn.ModuleList()
+        if num_layers == 1:
+            self.layers.append(nn.Linear(input_dim, output_dim))
+        else:
+            self.layers.append(nn.Linear(input_dim, hidden_dim))
+            self._add_norm(hidden_dim)
+            for _ in range(num_layers - 2):
+                self.layers.append(nn.Linear(hidden_dim, hidden_dim))
+                self._add_norm(hidden_dim)
+            self.layers.append(nn.Linear(hidden_dim, output_dim))
+
+    def _add_norm(self, dim):
+        if self.norm_type == "batch":
+            self.norms.append(nn.BatchNorm1d(dim))
+        elif self.norm_type == "layer":
+            self.norms.append(nn.LayerNorm(dim))
+
+    def reset_parameters(self):
+        for layer in self.layers:
+            layer.reset_parameters()
+
+    def forward(self, feats):
+        h = feats
+        p = self.dropout.p
+        for l, layer in enumerate(self.layers):
+            last = l == self.num_layers - 1
+            if last:
+                h = Fn.linear_bias_act(h, layer.weight, layer.bias, ACT_NONE)          # LLP.py:78
+            elif self.norm_type == "none":
+                h = Fn.linear_bias_act(h, layer.weight, layer.bias, ACT_RELU)          # LLP.py:78,82 fused
+                h = Fn.dropout(h, p, self.training)                                     # LLP.py:83
+            else:
+                # norm_type 'batch' / 'layer' is never selected by the reference's call site (LLP.py:291 keeps the default
+                # "none"); the normalisation itself stays a torch module, the Linear / ReLU / dropout are this library's
+                h = Fn.linear_bias_act(h, layer.weight, layer.bias, ACT_NONE)
+                h = self.norms[l](h)
+                h = Fn._Act.apply(h, ACT_RELU)
+                h = Fn.dropout(h, p, self.training)
+        return h
+
+
+def KD_cosine(s, t):
+    """``LLP.KD_cosine`` (LLP.py:34-35) on already gathered rows."""
+    return Fn.kd_cosine(s, t)
+
+
+def llp_distill_loss(model, predictor, teacher_model, teacher_predictor, features, adj_inter, source_index,
+                     recipient_index, True_label=10.0, KD_f=0.1, KD_p=100.0):
+    """The loss of one LLP training step (LLP.py:230-237), every gather fused into its consumer:
+
+        h = model(features); t_h = teacher_model(features, adj_inter)
+        output = predictor(h[source_index], h[recipient_index])          -> fused pair-gather scorer
+        label_loss = F.nll_loss(output, recipient_index)
+        t_out = teacher_predictor(t_h[source_index], t_h[recipient_index]).detach()
+        loss = True_label * label_loss + KD_f * KD_cosine(h[source_index], t_h[source_index]) + KD_p * mse(output, t_out)
+
+    Returns ``(loss, parts)`` with the three un-weighted terms.  The teacher branch carries no gradient: LLP.py:297 hands
+    only the student's and the predictor's parameters to the optimiser and detaches both teacher outputs."""
+    h = model(features)
+    with torch.no_grad():
+        t_h = teacher_model(features, adj_inter)
+        t_out = teacher_predictor.forward_pairs(t_h, t_h, source_index, recipient_index)
+    output = predictor.forward_pairs(h, h, source_index, recipient_index)
+    if output.dim() == 2 and output.shape[1] == 1:
+        output = output.squeeze(1)                                              # .squeeze() LLP.py:233
+    label_loss = Fn.nll_loss(output, recipient_index)                           # LLP.py:235
+    kd_f = Fn.kd_cosine(h, t_h, source_index, source_index)                     # LLP.py:236
+    kd_p = Fn.mse_loss(output, t_out.reshape(output.shape))                     # LLP.py:237
+    loss = True_label * label_loss + KD_f * kd_f + KD_p * kd_p
+    return loss, {"label_loss": label_loss, "KD_cosine": kd_f, "mse_loss": kd_p}
+
+
+# =================================================================================================
+# SURVEY.md section 8f-3: the remaining baselines -- GCN (model.py:48-64) and GraphSAGE (SGAE.py:41-56)
+# =================================================================================================
+class GCN(nn.Module):
+    def __init__(self, nfeat, nhid, nclass, dropout, gdp, N):
+        super().__init__()
+        gdp_values = _gdp_column(gdp)
+        self.features = nn.Parameter(torch.cat((torch.rand([N, nfeat])[:, :], gdp_values), dim=1))   # model.py:52
+        self.gc1 = GraphConvolution(nfeat + 1, nhid)
+        self.gc2 = GraphConvolution(nhid, nhid)
+        self.gc3 = GraphConvolution(nhid, nclass)        # allocated, never applied (model.py:62-63)
+        self.dropout = dropout
+
+    def forward(self, adj):
+        graph = as_graph(adj)
+        x = Fn._Act.apply(self.gc1(self.features, graph), ACT_RELU)             # (M, nhid)  model.py:59
+        x = Fn.dropout(x, self.dropout, self.training)                          # model.py:60
+        x = Fn._Act.apply(self.gc2(x, graph, transposed=True), ACT_RELU)        # gc2(x, adj.t()) -> (N, nhid)  model.py:61
+        return Fn.log_softmax(x, pre_elu=False)                                 # model.py:64
+
+
+class GraphSAGE(nn.Module):
+    """SGAE.py:41-56.  ``Scount`` is a module-level global there (SGAE.py:46); here it is a constructor argument."""
+
+    def __init__(self, in_features, hidden_features, out_features, gdp, Scount=None):
+        super().__init__()
+        gdp_values = _gdp_column(gdp)
+        Scount = gdp_values.shape[0] if Scount is None else Scount
+        self.Sfeatures = nn.Parameter(torch.cat((torch.rand([Scount, in_features])[:, :-1], gdp_values), dim=1))
+        self.linear1 = nn.Linear(in_features, hidden_features)
+        self.linear2 = nn.Linear(hidden_features, out_features)
+
+    def forward(self, source_index, adj, values=None):
+        graph = as_graph(adj)
+        x = self.Sfeatures.index_select(0, source_index)                                        # SGAE.py:51
+        x = Fn.linear_bias_act(x, self.linear1.weight, self.linear1.bias, ACT_RELU)             # SGAE.py:52
+        x = Fn.csr_rows_mul(graph, x, source_index, values)                                     # SGAE.py:53
+        x = Fn.linear_bias_act(x, self.linear2.weight, self.linear2.bias, ACT_RELU)             # SGAE.py:54
+        return Fn.log_softmax(x, pre_elu=False)                                                 # SGAE.py:55
+
+
+# =================================================================================================
+# SURVEY.md section 8f-4: attention export without the dense (N, M) / (N, N) dumps
+# (train.py:284-321 fills Coeff12 / Coeff3 / Coeff4, Explainer.py:25-30 takes argwhere(row == max(row)))
+# =================================================================================================
+def export_attention(graph: Graph, alpha, heads=1, head=-1):
+    """Sparse form of ``Coeff12`` and of what the explainer extracts from it.
+
+    Returns a dict: ``edge_index`` (2, E) int64 and ``alpha`` (E,) -- the attention of ``head`` (mean over heads for
+    ``head < 0``) in canonical row-major order; ``row_max`` / ``row_argmax`` / ``row_ties`` per source row (``interAttS``:
+    the recipient a source attends to most, smallest column on ties, and how many columns tie); ``col_max`` /
+    ``col_argmax`` / ``col_ties`` per recipient column (``interAttR``).  ``argmax`` is -1 for an empty row / column."""
+    rp, col = graph.attention_csr()
+    colptr, rowidx, perm = graph.attention_csc()
+    a = alpha.detach()
+    vmax_r, first_r, ties_r = Fn.segment_argmax(rp, a, heads, head)
+    vmax_c, first_c, ties_c = Fn.segment_argmax(colptr, a, heads, head, perm=perm)
+    cols = torch.where(col < 0, ~col, col).long()
+    deg = (rp[1:] - rp[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(graph.n_rows, device=a.device), deg)
+    vals = a.view(-1, heads)
+    vals = vals[:, head] if head >= 0 else vals.mean(dim=1)
+    neg_r = torch.full((graph.n_rows,), -1, dtype=torch.int64, device=a.device)
+    neg_c = torch.full((graph.n_cols,), -1, dtype=torch.int64, device=a.device)
+    if cols.numel():
+        row_arg = torch.where(first_r >= 0, cols[first_r.clamp(min=0).long()], neg_r)
+        col_arg = torch.where(first_c >= 0, rowidx.long()[first_c.clamp(min=0).long()], neg_c)
+    else:
+        row_arg, col_arg = neg_r, neg_c
+    return {"edge_index": torch.stack([rows, cols]), "alpha": vals,
+            "row_max": vmax_r, "row_argmax": row_arg, "row_ties": ties_r,
+            "col_max": vmax_c, "col_argmax": col_arg, "col_ties": ties_c}

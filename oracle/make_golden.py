@@ -285,6 +285,161 @@ def case_generic_gat(save):
                              W=np.stack(Ws), a=np.stack(As)))
 
 
+def case_dataset(save):
+    """dataset.HigherDataset.intra_adjacent / inter_adjacent (dataset.py:260-296) on a small synthetic year: the class
+    body is executed verbatim (AST), an instance is made without running the hard-coded-path __init__, and ``open`` is
+    shadowed inside the class' globals so the ``inter<year>.json`` dump of dataset.py:293-294 goes to a null sink."""
+    import contextlib
+    import csv
+    import io
+    import json
+    from torch.utils.data import Dataset
+
+    @contextlib.contextmanager
+    def null_open(*a, **k):
+        yield io.StringIO()
+
+    cls = ref_import.extract_classes("dataset.py", ["HigherDataset"], extra_globals=dict(
+        Dataset=Dataset, json=json, csv=csv, year="0000", open=null_open))["HigherDataset"]
+    rng = np.random.default_rng(901)
+    N, M, R = 57, 6, 400
+    city = rng.integers(0, 9, N)
+    province = city // 3                                   # cities nest in provinces, like the real tables
+    source = rng.integers(0, N, R)
+    source[source == 11] = 12                              # node 11 has no record (isolated inter row)
+    recipient = rng.integers(0, M - 1, R)                  # column M-1 never occurs (empty column)
+    ds = object.__new__(cls)
+    ds.graph_dict = {str(i): [int(i % 7), int(city[i]), int(province[i])] for i in range(N)}   # values[1], values[2]
+    ds.N, ds.M, ds.count = N, M, R
+    ds.source, ds.recipient = source.tolist(), recipient.tolist()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                    # torch.tensor(tensor) copy-construct warning, dataset.py:277
+        city_adj, prov_adj = ds.intra_adjacent()
+        inter = ds.inter_adjacent()
+    gdp = rng.random(N)
+    save("dataset", dict(source=source, recipient=recipient, city=city, province=province, gdp=gdp,
+                         inter=_np(inter), city_adj=_np(city_adj), province_adj=_np(prov_adj),
+                         n_recipients=np.int64(M)))
+
+
+def _named_grads(out_scalar, mods):
+    named = [(f"{tag}.{n}", p) for tag, m in mods for n, p in m.named_parameters()]
+    gs = torch.autograd.grad(out_scalar, [p for _, p in named], allow_unused=True)
+    return {"g." + n: _np(torch.zeros_like(p) if g is None else g) for (n, p), g in zip(named, gs)}
+
+
+def case_llp(save):
+    """One LLP training-step loss (LLP.py:230-237) from the reference's own MLP / LinkPredictor / GAT(input, adj) /
+    Teacher_LinkPredictor / KD_cosine, dropout 0; plus a 3-layer MLP on its own and KD_cosine / MSELoss on raw rows."""
+    L = ref_import.llp_classes()
+    Mo = ref_import.import_module("model")
+    gen = torch.Generator().manual_seed(1001)
+    N, M, P = 41, 8, 30                                   # hidden_channels == Rcount (LLP.py:291-293)
+    torch.manual_seed(91)
+    model = L["MLP"](2, M, M, M, 0.0)
+    predictor = L["LinkPredictor"]("mlp", M, M, 1, 2, 0.0)
+    teacher = L["GAT"](n_features=M, n_classes=M, n_heads=2, dropout=0.0, gdp=None, N=N)
+    teacher_pred = L["Teacher_LinkPredictor"]("mlp", M, M, 1, 2, 0.0)
+    adj = _rand_adj(N, M, 0.3, gen, iso_rows=(4,), counts=True)
+    adj[:, 0] += 1.0                                      # no empty column -> finite normalisation
+    adj_n = Mo.normalize_adjacency_matrix(adj)
+    features = torch.rand(N, M, generator=gen)
+    si = torch.randint(0, N, (P,), generator=gen)
+    ri = torch.randint(0, M, (P,), generator=gen)
+    mse_loss = torch.nn.MSELoss()
+    h = model(features)
+    t_h = teacher(features, adj_n)
+    output = predictor(h[si], h[ri]).squeeze()
+    label_loss = torch.nn.functional.nll_loss(output, ri)
+    t_out = teacher_pred(t_h[si], t_h[ri]).squeeze().detach()
+    kd_f = L["KD_cosine"](h[si], t_h[si])
+    kd_p = mse_loss(output, t_out)
+    loss = 10.0 * label_loss + 0.1 * kd_f + 100.0 * kd_p
+    mods = (("model", model), ("predictor", predictor))
+    dd = dict(adj=_np(adj), adj_norm=_np(adj_n), features=_np(features), src=_np(si), rec=_np(ri), loss=_np(loss),
+              label_loss=_np(label_loss), kd_f=_np(kd_f), kd_p=_np(kd_p), h=_np(h), t_h=_np(t_h), output=_np(output),
+              t_out=_np(t_out), **_named_grads(loss, mods))
+    for tag, m in mods + (("teacher", teacher), ("teacher_pred", teacher_pred)):
+        dd.update(_state(m, prefix=f"p.{tag}."))
+    save("llp_step", dd)
+
+    torch.manual_seed(92)
+    mlp = L["MLP"](3, 12, 20, 7, 0.0)
+    x = torch.randn(33, 12, generator=gen, requires_grad=True)
+    out = mlp(x)
+    G = torch.randn(out.shape, generator=gen)
+    params = list(mlp.named_parameters())
+    grads = _grads(out, G, [x] + [p for _, p in params])
+    dd = dict(x=_np(x), G=_np(G), out=_np(out), gx=_np(grads[0]), **_state(mlp))
+    for (n, _), g in zip(params, grads[1:]):
+        dd["g." + n] = _np(g)
+    save("mlp3", dd)
+
+    # KD_cosine / MSELoss on raw operands: duplicate indices, a zero row on each side, C not a multiple of 4
+    for tag, C in (("c12", 12), ("c7", 7)):
+        s = torch.randn(19, C, generator=gen)
+        t = torch.randn(23, C, generator=gen)
+        s[3] = 0.0
+        t[5] = 0.0
+        s.requires_grad_(True)
+        t.requires_grad_(True)
+        i_s = torch.randint(0, 19, (40,), generator=gen)
+        i_t = torch.randint(0, 23, (40,), generator=gen)
+        i_s[0], i_t[0] = 3, 1                             # zero student row
+        i_s[1], i_t[1] = 2, 5                             # zero teacher row
+        cos = L["KD_cosine"](s[i_s], t[i_t])
+        (gs,) = torch.autograd.grad(cos, [s])
+        full = 1 - torch.nn.functional.cosine_similarity(s[i_s], t[i_t], dim=-1).mean()   # teacher not detached
+        gs_full, gt_full = torch.autograd.grad(full, [s, t])
+        a = torch.randn(17, C, generator=gen, requires_grad=True)
+        b = torch.randn(17, C, generator=gen, requires_grad=True)
+        mse = mse_loss(a, b)
+        ga, gb = torch.autograd.grad(mse, [a, b])
+        save("kd_losses_" + tag, dict(s=_np(s), t=_np(t), idx_s=_np(i_s), idx_t=_np(i_t), kd=_np(cos), gs=_np(gs),
+                                      gs_full=_np(gs_full), gt_full=_np(gt_full), a=_np(a), b=_np(b), mse=_np(mse),
+                                      ga=_np(ga), gb=_np(gb)))
+
+
+def case_baselines(save):
+    """model.GCN (model.py:48-64) and SGAE.GraphSAGE (SGAE.py:41-56), dropout 0."""
+    Mo = ref_import.import_module("model")
+    gen = torch.Generator().manual_seed(1101)
+    N, M, nfeat, nhid = 31, 9, 6, 5
+    gdp = {str(i): float(v) for i, v in enumerate(torch.rand(N, generator=gen))}
+    torch.manual_seed(93)
+    gcn = Mo.GCN(nfeat, nhid, M, 0.0, gdp, N)
+    adj = _rand_adj(N, M, 0.3, gen, iso_rows=(6,), counts=True)
+    adj[:, 0] += 1.0
+    adj[6, 0] = 0.0                                       # keep row 6 isolated
+    adj_n = Mo.normalize_adjacency_matrix(adj)
+    gcn.train()
+    out = gcn(adj_n)
+    G = torch.randn(out.shape, generator=gen)
+    params = list(gcn.named_parameters())
+    grads = _grads(out, G, [p for _, p in params])
+    dd = dict(adj=_np(adj), adj_norm=_np(adj_n), G=_np(G), out=_np(out), **_state(gcn))
+    for (n, _), g in zip(params, grads):
+        dd["g." + n] = _np(g)
+    save("gcn_model", dd)
+
+    S = ref_import.sgae_classes(N)
+    torch.manual_seed(94)
+    sage = S["GraphSAGE"](7, M, 5, gdp)
+    src = torch.randint(0, N, (20,), generator=gen)
+    src[0] = 6                                            # an isolated source: its row of adj is all zero
+    sage.train()
+    out = sage(src, adj_n)
+    G = torch.randn(out.shape, generator=gen)
+    params = list(sage.named_parameters())
+    grads = _grads(out, G, [p for _, p in params])
+    dd = dict(adj=_np(adj), adj_norm=_np(adj_n), src=_np(src), G=_np(G), out=_np(out), gdp=np.array(list(gdp.values())),
+              **_state(sage))
+    for (n, _), g in zip(params, grads):
+        dd["g." + n] = _np(g)
+    save("graphsage", dd)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
 
@@ -295,7 +450,7 @@ def main():
 
     torch.set_num_threads(1)
     for fn in (case_gal, case_gat, case_ours_layers, case_ours_record, case_msha_models, case_hgane,
-               case_linkpred, case_gcn, case_generic_gat):
+               case_linkpred, case_gcn, case_generic_gat, case_dataset, case_llp, case_baselines):
         fn(save)
 
 

@@ -427,6 +427,95 @@ def graph_convolution(x, weight, bias, rowptr, col, val, n_cols):
 
 
 # --------------------------------------------------------------------------------------
+# LLP student + distillation step, GCN / GraphSAGE baselines, attention export
+# --------------------------------------------------------------------------------------
+def mlp(x, weights, biases):
+    """``LLP.MLP.forward`` with ``norm_type='none'`` in eval / dropout 0 (LLP.py:75-84): relu on all but the last."""
+    h = _t(x)
+    for k, (W, b) in enumerate(zip(weights, biases)):
+        h = h @ _t(W).t() + _t(b)
+        if k != len(weights) - 1:
+            h = F.relu(h)
+    return h
+
+
+def kd_cosine(s, t, idx_s=None, idx_t=None, eps=1e-8, detach_teacher=True):
+    """``KD_cosine`` (LLP.py:34-35) = ``1 - cosine_similarity(s, t.detach(), dim=-1).mean()``; torch divides each
+    vector by ``max(||.||, eps)`` (clamped outside autograd) before the dot product."""
+    s, t = _t(s), _t(t)
+    if detach_teacher:
+        t = t.detach()
+    if idx_s is not None:
+        s = s[torch.as_tensor(np.asarray(idx_s), dtype=torch.int64)]
+    if idx_t is not None:
+        t = t[torch.as_tensor(np.asarray(idx_t), dtype=torch.int64)]
+    ns = torch.linalg.vector_norm(s, 2, dim=-1, keepdim=True)
+    nt = torch.linalg.vector_norm(t, 2, dim=-1, keepdim=True)
+    ns = ns + (ns.detach().clamp_min(eps) - ns.detach())          # value clamped, gradient of the norm kept
+    nt = nt + (nt.detach().clamp_min(eps) - nt.detach())
+    return 1 - ((s / ns) * (t / nt)).sum(-1).mean()
+
+
+def mse_loss(a, b):
+    """``torch.nn.MSELoss()`` (LLP.py:221,237): mean over every element."""
+    return ((_t(a) - _t(b)) ** 2).mean()
+
+
+def llp_step_loss(features, student, predictor, teacher_heads, teacher_out, teacher_pred, rowptr, col, src, rec,
+                  True_label=10.0, KD_f=0.1, KD_p=100.0):
+    """Loss of one LLP step (LLP.py:230-237), dropout 0.  ``student`` / ``predictor`` / ``teacher_pred`` are
+    ``(weights, biases)`` lists, ``teacher_heads`` a list of ``(W, a)``, ``teacher_out`` one ``(W, a)``."""
+    src = torch.as_tensor(np.asarray(src), dtype=torch.int64)
+    rec = torch.as_tensor(np.asarray(rec), dtype=torch.int64)
+    feats = _t(features)
+    h = mlp(feats, *student)
+    x = torch.cat([graph_attention_layer(feats, W, a, rowptr, col) for W, a in teacher_heads], dim=1)   # LLP.py:165
+    t_h = F.log_softmax(F.elu(graph_attention_layer(x, teacher_out[0], teacher_out[1], rowptr, col)), dim=1)
+    output = link_predictor(h[src], h[rec], *predictor)
+    label_loss = -(output[torch.arange(src.numel()), rec]).mean()                                      # LLP.py:235
+    t_out = link_predictor(t_h[src], t_h[rec], *teacher_pred).detach()
+    kd_f = kd_cosine(h[src], t_h[src])
+    kd_p = mse_loss(output, t_out)
+    return True_label * label_loss + KD_f * kd_f + KD_p * kd_p, dict(label_loss=label_loss, kd_f=kd_f, kd_p=kd_p,
+                                                                     h=h, t_h=t_h, output=output, t_out=t_out)
+
+
+def spmm_rows(x, rowptr, col, val, n_rows):
+    """``adj @ x`` with adj as value CSR (GCN's second layer ``gc2(x, adj.t())``, model.py:37,61)."""
+    x = _t(x)
+    r = _rows_of(rowptr)
+    c = torch.as_tensor(np.asarray(col), dtype=torch.int64)
+    return torch.zeros(n_rows, x.shape[1], dtype=x.dtype).index_add(0, r, _t(val)[:, None] * x[c])
+
+
+def gcn_model(features, p, rowptr, col, val, n_rows, n_cols):
+    """``GCN.forward`` (model.py:58-64), dropout 0: relu(gc1(features, adj)) -> relu(gc2(., adj.t())) -> log_softmax."""
+    x = F.relu(graph_convolution(features, p["gc1.weight"], p["gc1.bias"], rowptr, col, val, n_cols))
+    x = F.relu(spmm_rows(x @ _t(p["gc2.weight"]), rowptr, col, val, n_rows) + _t(p["gc2.bias"]))
+    return F.log_softmax(x, dim=1)
+
+
+def graphsage_model(p, src, rowptr, col, val, n_cols):
+    """``GraphSAGE.forward`` (SGAE.py:49-56): relu(linear1(S[src])) * adj[src] -> relu(linear2) -> log_softmax."""
+    src = np.asarray(src, dtype=np.int64)
+    x = _t(p["Sfeatures"])[torch.as_tensor(src)]
+    x = F.relu(x @ _t(p["linear1.weight"]).t() + _t(p["linear1.bias"]))
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    rows = torch.zeros(src.size, n_cols, dtype=x.dtype)
+    v = _t(val)
+    for b, r in enumerate(src):                                      # adj[source_index], SGAE.py:53
+        e0, e1 = int(rowptr[r]), int(rowptr[r + 1])
+        rows[b, torch.as_tensor(np.asarray(col[e0:e1]), dtype=torch.int64)] = v[e0:e1]
+    x = F.relu((rows * x) @ _t(p["linear2.weight"]).t() + _t(p["linear2.bias"]))
+    return F.log_softmax(x, dim=1)
+
+
+def explainer_argmax(dense: np.ndarray):
+    """``[np.argwhere(row == np.max(row)).flatten().tolist() for row in Coeff]`` (Explainer.py:25-30)."""
+    return [np.argwhere(row == np.max(row)).flatten().tolist() for row in np.asarray(dense)]
+
+
+# --------------------------------------------------------------------------------------
 # a-8  loss read-out                                                          train.py:229
 # --------------------------------------------------------------------------------------
 def nll_readout(logp, src, rec):

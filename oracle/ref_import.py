@@ -40,13 +40,13 @@ def import_module(name: str):
 
 
 def extract_classes(filename: str, class_names, extra_globals=None):
-    """Execute only the named ``class`` statements of a reference file (verbatim source)."""
+    """Execute only the named top-level ``class`` / ``def`` statements of a reference file (verbatim source)."""
     _ensure_path()
     path = os.path.join(REF_ROOT, filename)
     with open(path, "r", encoding="utf-8", errors="replace") as f:
         src = f.read()
     tree = ast.parse(src, filename=path)
-    wanted = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in class_names]
+    wanted = [n for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.name in class_names]
     missing = set(class_names) - {n.name for n in wanted}
     if missing:
         raise RuntimeError(f"{filename}: classes not found: {sorted(missing)}")
@@ -62,9 +62,16 @@ def extract_classes(filename: str, class_names, extra_globals=None):
 
 
 def llp_classes():
-    """LinkPredictor / Teacher_LinkPredictor / MLP / GAT(input, adj) from LLP.py:36-198."""
+    """LinkPredictor / Teacher_LinkPredictor / MLP / GAT(input, adj) / KD_cosine from LLP.py:34-198."""
+    from torch.nn.functional import cosine_similarity          # LLP.py:3
     return extract_classes(
-        "LLP.py", ["MLP", "LinkPredictor", "GraphAttentionLayer", "GAT", "Teacher_LinkPredictor"])
+        "LLP.py", ["KD_cosine", "MLP", "LinkPredictor", "GraphAttentionLayer", "GAT", "Teacher_LinkPredictor"],
+        extra_globals={"cosine_similarity": cosine_similarity})
+
+
+def sgae_classes(Scount: int):
+    """GraphSAGE from SGAE.py:41-56; ``Scount`` is a module-level global there (SGAE.py:46,70)."""
+    return extract_classes("SGAE.py", ["GraphSAGE"], extra_globals={"Scount": Scount})
 
 
 def ours_classes():

@@ -270,3 +270,115 @@ def test_negative_sampler_and_dropout_stream():
     keep = O.dropout_keep_mask(7, 200000, 0.5)
     assert abs(keep.mean() - 0.5) < 0.01
     assert O.dropout_keep_mask(7, 100, 0.0).all()
+
+
+# ------------------------------------------------------------------ SURVEY 8f rows (LLP student, baselines, export)
+def _lins(p, prefix, names=("lins",)):
+    ws, bs = [], []
+    k = 0
+    while f"{prefix}{names[0]}.{k}.weight" in p:
+        ws.append(p[f"{prefix}{names[0]}.{k}.weight"])
+        bs.append(p[f"{prefix}{names[0]}.{k}.bias"])
+        k += 1
+    return ws, bs
+
+
+def test_llp_step_loss():
+    g = load_golden("llp_step")
+    p = params_of(g)
+    rowptr, col, _ = O.csr_from_dense(g["adj_norm"])
+    heads = [(p[f"teacher.attention_{k}.W"], p[f"teacher.attention_{k}.a"]) for k in range(2)]
+    student = tuple([_leaf(w) for w in x] for x in _lins(p, "model.", ("layers",)))
+    pred = tuple([_leaf(w) for w in x] for x in _lins(p, "predictor."))
+    loss, parts = O.llp_step_loss(g["features"], student, pred, heads, (p["teacher.out_att.W"], p["teacher.out_att.a"]),
+                                  _lins(p, "teacher_pred."), rowptr, col, g["src"], g["rec"])
+    for k in ("label_loss", "kd_f", "kd_p", "h", "t_h", "output", "t_out"):
+        assert rel_err(parts[k].detach().numpy(), g[k]) < TOL, k
+    # the weighted sum cancels (10 * label_loss ~ -7, 100 * mse ~ +7): compare against the size of its terms
+    scale = 10.0 * abs(float(g["label_loss"])) + 0.1 * abs(float(g["kd_f"])) + 100.0 * abs(float(g["kd_p"]))
+    assert abs(float(loss) - float(g["loss"])) < TOL * scale
+    loss.backward()
+    for tag, (ws, bs), nm in (("model", student, "layers"), ("predictor", pred, "lins")):
+        for k, (w, b) in enumerate(zip(ws, bs)):
+            for leaf, kind in ((w, "weight"), (b, "bias")):
+                ref = g[f"g.{tag}.{nm}.{k}.{kind}"]
+                got = np.zeros_like(ref) if leaf.grad is None else leaf.grad.numpy()
+                if np.abs(ref).max() < 1e-7:
+                    assert np.abs(got).max() < 1e-7
+                else:
+                    assert rel_err(got, ref) < 5e-5, (tag, k, kind, rel_err(got, ref))
+
+
+def test_mlp3():
+    g = load_golden("mlp3")
+    p = params_of(g)
+    ws, bs = _lins(p, "", ("layers",))
+    x = _leaf(g["x"])
+    wl, bl = [_leaf(w) for w in ws], [_leaf(b) for b in bs]
+    out = O.mlp(x, wl, bl)
+    assert rel_err(out.detach().numpy(), g["out"]) < TOL
+    grads = _grad(out, g["G"], [x] + wl + bl)
+    assert rel_err(grads[0].numpy(), g["gx"]) < TOL
+    for k in range(3):
+        assert rel_err(grads[1 + k].numpy(), g[f"g.layers.{k}.weight"]) < TOL
+        assert rel_err(grads[4 + k].numpy(), g[f"g.layers.{k}.bias"]) < TOL
+
+
+@pytest.mark.parametrize("tag", ["c12", "c7"])
+def test_kd_losses(tag):
+    g = load_golden("kd_losses_" + tag)
+    s, t = _leaf(g["s"]), _leaf(g["t"])
+    kd = O.kd_cosine(s, t, g["idx_s"], g["idx_t"])
+    assert rel_err(kd.detach().numpy(), g["kd"]) < TOL
+    (gs,) = torch.autograd.grad(kd, [s])
+    zero_row = 3                                              # its gradient is t / (eps |t|): ~1e8, checked apart
+    keep = np.arange(g["s"].shape[0]) != zero_row
+    assert rel_err(gs.numpy()[keep], g["gs"][keep]) < TOL
+    assert rel_err(gs.numpy()[zero_row], g["gs"][zero_row]) < TOL
+    full = O.kd_cosine(s, t, g["idx_s"], g["idx_t"], detach_teacher=False)
+    gs2, gt2 = torch.autograd.grad(full, [s, t])
+    assert rel_err(gs2.numpy()[keep], g["gs_full"][keep]) < TOL
+    keep_t = np.arange(g["t"].shape[0]) != 5
+    assert rel_err(gt2.numpy()[keep_t], g["gt_full"][keep_t]) < TOL
+    assert rel_err(gt2.numpy()[5], g["gt_full"][5]) < TOL
+    a, b = _leaf(g["a"]), _leaf(g["b"])
+    mse = O.mse_loss(a, b)
+    assert rel_err(mse.detach().numpy(), g["mse"]) < TOL
+    ga, gb = torch.autograd.grad(mse, [a, b])
+    assert rel_err(ga.numpy(), g["ga"]) < TOL and rel_err(gb.numpy(), g["gb"]) < TOL
+
+
+def test_gcn_model():
+    g = load_golden("gcn_model")
+    p = {k: _leaf(v) for k, v in params_of(g).items()}
+    N, M = g["adj"].shape
+    rowptr, col, _ = O.csr_from_dense(g["adj"])
+    val = O.normalize_csr_values(O.csr_from_dense(g["adj"])[2], col, M)
+    np.testing.assert_allclose(val, g["adj_norm"][g["adj"] > 0], rtol=1e-6)
+    out = O.gcn_model(p["features"], p, rowptr, col, val, N, M)
+    assert rel_err(out.detach().numpy(), g["out"]) < TOL
+    names = ["features", "gc1.weight", "gc1.bias", "gc2.weight", "gc2.bias"]
+    grads = _grad(out, g["G"], [p[n] for n in names])
+    for n, gr in zip(names, grads):
+        assert rel_err(gr.numpy(), g["g." + n]) < TOL, n
+    assert np.abs(g["g.gc3.weight"]).max() == 0               # allocated, never applied (model.py:62-63)
+
+
+def test_graphsage_model():
+    g = load_golden("graphsage")
+    p = {k: _leaf(v) for k, v in params_of(g).items()}
+    N, M = g["adj"].shape
+    rowptr, col, v0 = O.csr_from_dense(g["adj"])
+    val = O.normalize_csr_values(v0, col, M)
+    out = O.graphsage_model(p, g["src"], rowptr, col, val, M)
+    assert rel_err(out.detach().numpy(), g["out"]) < TOL
+    names = list(p)
+    grads = _grad(out, g["G"], [p[n] for n in names])
+    for n, gr in zip(names, grads):
+        assert rel_err(gr.numpy(), g["g." + n]) < TOL, n
+
+
+def test_explainer_argmax():
+    dense = np.array([[0.2, 0.5, 0.5, 0.0], [0.0, 0.0, 0.0, 0.0], [0.1, 0.0, 0.0, 0.9]], dtype=np.float32)
+    assert O.explainer_argmax(dense) == [[1, 2], [0, 1, 2, 3], [3]]
+    assert O.explainer_argmax(dense.T) == [[0], [0], [0], [2]]
