@@ -569,6 +569,146 @@ def run_flow(args):
     print(json.dumps(out))
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[1]: GAT.py 2-layer 8-head GAT + LinkPredictor MLP scorer on the 2015-2018 yearly graphs
+# (SURVEY.md section 8d cfg 2: real node-table sizes, synthetic flows shaped like 2015)
+# ------------------------------------------------------------------------------------------------
+YEARLY = {"2015": (39179, 233887), "2016": (48032, 286700), "2017": (49700, 296700), "2018": (50015, 298600)}
+
+
+def yearly_cpu_baseline(src, dst, N, M, H, B, reps=2):
+    """GAT.forward (GAT.py:53-58) + LinkPredictor (LLP.py:104-115) + nll, fwd + bwd, oracle port in fp32 on the 2015 graph."""
+    from oracle import msha_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    rowptr, col, _ = O.csr_from_coo(src, dst, N, M)
+    g = torch.Generator().manual_seed(0)
+    dt = torch.float32
+
+    def P(*shape):
+        return (torch.rand(*shape, generator=g, dtype=dt) - 0.5).requires_grad_(True)
+    heads = [(P(M, M), P(2 * M, 1)) for _ in range(H)]
+    out_p = (P(M * H, M), P(2 * M, 1))
+    feats = torch.rand(N, M, generator=g, dtype=dt)
+    lw, lb = [P(M, M), P(1, M)], [P(M), P(1)]
+    orig_t = O._t
+    O._t = lambda a, d_=dt: orig_t(a, d_)
+    try:
+        ts = []
+        for _ in range(reps + 1):
+            s_i = torch.randint(0, N, (B,), generator=g)
+            r_i = torch.randint(0, M, (B,), generator=g)
+            t0 = time.perf_counter()
+            h = O.gat_model(feats, heads, out_p, rowptr, col)
+            out = O.link_predictor(h[s_i], h[r_i], lw, lb)
+            loss = -(out[torch.arange(B), r_i]).mean()
+            torch.autograd.grad(loss, [w for w, _ in heads] + [out_p[0], lw[0], lb[0]])
+            ts.append(time.perf_counter() - t0)
+    finally:
+        O._t = orig_t
+    t = min(ts[1:])
+    return {"value": col.size * 2 / t, "unit": "edges/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"the 2015 graph only (1 of the 4 yearly graphs), full step fwd + nll + bwd without Adam, best of {reps} "
+                      "after warm-up; oracle port (torch CPU fp32)", "ms_per_step_est": t * 1e3}
+
+
+def run_yearly(args):
+    import msha_gnn_b200 as mg
+    from msha_gnn_b200 import ops
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    M, H, B = 32, 8, 4096                                                      # LLP.py:32 batch size
+    years = []
+    for y, (N, n_rec) in YEARLY.items():
+        src, dst, _, _ = flow_graph(seed=int(y), N=N, M=M, n_records=n_rec)
+        graph = mg.Graph.from_coo(torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), N, M)
+        graph.attention_csr()
+        years.append(dict(year=y, N=N, src=src, dst=dst, graph=graph))
+    torch.manual_seed(42)
+    for yr in years:
+        gdp = {str(i): 0.05 for i in range(yr["N"])}
+        yr["model"] = mg.GAT(n_features=M, n_classes=M, n_heads=H, dropout=0.5, gdp=gdp, N=yr["N"]).to(dev)   # train.py:199
+    predictor = mg.LinkPredictor('mlp', M, M, 1, 2, 0.5).to(dev)                # LLP.py:292
+    params = [p for yr in years for p in yr["model"].parameters()] + list(predictor.parameters())
+    opt = torch.optim.Adam(params, lr=5e-3, fused=True)                         # LLP.py:15,297
+    rng = np.random.default_rng(0)
+    n_batches = args.warmup + 2 * args.steps + 4
+    for yr in years:
+        idx = rng.integers(0, yr["src"].size, (n_batches, B))
+        yr["host"] = torch.from_numpy(np.stack([yr["src"][idx], yr["dst"][idx]], axis=1)).pin_memory()   # (batches, 2, B)
+        yr["dev"] = yr["host"].to(dev)
+        yr["model"].train()
+    predictor.train()
+    lib = mg._lib.lib()
+    E_tot = sum(yr["graph"].nnz for yr in years)
+    N_tot = sum(yr["N"] for yr in years)
+
+    def step(i, from_host=False):
+        opt.zero_grad(set_to_none=True)
+        total = None
+        for yr in years:
+            b = yr["host"][i].to(dev, non_blocking=True) if from_host else yr["dev"][i]
+            s_i, r_i = b[0], b[1]
+            h = yr["model"](yr["graph"])                                        # (N, M) log-probs, GAT.py:53-58
+            loss = predictor.nll_loss_pairs(h, h, s_i, r_i, r_i)                # LLP.py:233-235
+            total = loss if total is None else total + loss
+        total.backward()
+        opt.step()
+        return total
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = lib.msha_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.msha_launch_count() - l0
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        loss_host = float(step(args.warmup + args.steps + i, from_host=True).item())
+    e3.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_e2e = e2.elapsed_time(e3) / args.steps
+    with KernelTimer(ops) as kt:
+        step(0)
+        step(1)
+    agg = kt.summary()
+    tot = sum(v[1] for v in agg.values())
+    kernels = [{"call": f, "launches_per_step": c // 2, "avg_ms": round(ms / c, 4), "share": round(ms / tot, 4)}
+               for f, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])][:10]
+    # a-1 is node-dominated (SURVEY 8d): per head-layer fwd+bwd N*(12F + 8M) + 8E bytes; H heads of F = M plus out_att (F = H*M)
+    alg_bytes = sum(yr["N"] * (12 * M + 8 * M) * H + yr["N"] * (12 * H * M + 8 * M) + 8 * yr["graph"].nnz * (H + 1) for yr in years)
+    hbm_peak, _, peak_src = load_peaks()
+    out = {"metric": "gat_fwd_bwd_layer_edges_per_sec", "value": E_tot * 2 / (ms_dev / 1e3), "unit": "edges/s", "n_gpus": 1,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"yearly: 4 yearly graphs N={[yr['N'] for yr in years]}, M={M}, nnz={[yr['graph'].nnz for yr in years]} "
+                                  f"(2015-shaped synthetic flows), GAT(n_features=32,n_classes=32,n_heads=8,p=0.5) per year + shared "
+                                  f"LinkPredictor(mlp,32,32,1,2,0.5), batch {B} pairs per year, nll_loss, Adam (BASELINE.json configs[1])",
+                      "l2_policy": "per-step working set (4 x N x 256 x 4 B x several tensors, ~0.5 GB) exceeds the 126 MB L2; no explicit flush"},
+           "nodes_per_sec": N_tot / (ms_dev / 1e3), "pairs_per_sec": 4 * B / (ms_dev / 1e3),
+           "e2e": {"value": E_tot * 2 / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": 4 * 2 * B * 8, "d2h_bytes_per_step": 4},
+           "gpu_launches": int(launches), "clocks": clocks,
+           "roofline": {"bound": "hbm", "kernel": "whole step (node-dominated a-1 path; launch-bound)", "achieved": alg_bytes / (ms_dev / 1e3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (ms_dev / 1e3) / 1e9 / hbm_peak, "traffic": None,
+                        "note": "algorithmic bytes of the step (SURVEY 8d a-1 model) / device step time; peak " + peak_src},
+           "kernels": kernels, "loss": loss_host}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = yearly_cpu_baseline(years[0]["src"], years[0]["dst"], years[0]["N"], M, H, B)
+    print(json.dumps(out))
+
+
 def flow_cpu_baseline(src, dst, N, M, B, reps=2):
     """The reference's ablation3 training step (Ablation.py:279-301 via the oracle port, fp32, all host threads)."""
     from oracle import msha_oracle as O
@@ -701,7 +841,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="ddi", choices=list(WORKLOADS) + ["flow", "flow-ours"])
+    ap.add_argument("--workload", default="ddi", choices=list(WORKLOADS) + ["flow", "flow-ours", "yearly"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused-loss", action="store_true",
@@ -709,7 +849,19 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
-    if args.workload.startswith("flow"):
+    if args.workload == "yearly":
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                src, dst, _, _ = flow_graph(seed=2015)
+                cb = yearly_cpu_baseline(src, dst, 39179, 32, 8, 4096, reps=max(1, min(args.steps, 3)))
+                print(json.dumps({"impl": "reference", "metric": "gat_fwd_bwd_layer_edges_per_sec", "value": cb["value"],
+                                  "unit": "edges/s", "n_gpus": 1, "steps": args.steps, "warmup": 1, "higher_is_better": True,
+                                  "ms_per_step": cb["ms_per_step_est"], "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                                  "data": "synthetic", "config": {"workload": args.workload}, "cpu_baseline": cb,
+                                  "e2e": {"value": cb["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        else:
+            run_yearly(args)
+    elif args.workload.startswith("flow"):
         if args.impl == "reference":
             if int(os.environ.get("RANK", "0")) == 0:
                 src, dst, _, _ = flow_graph()
