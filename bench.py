@@ -473,18 +473,37 @@ def run_ours(args):
 # records, 1-30 distinct recipients per source, 291 cities / 25 provinces.  Step = train.py:221-232.
 # ------------------------------------------------------------------------------------------------
 def flow_graph(seed=2015, N=39179, M=32, n_records=233887):
+    """2015-shaped flow records (SURVEY.md section 8d cfg 1/2): every source has k distinct recipients, k ~ geometric with
+    mean 2.33 capped at 30 (nnz ~ 2.33 N: 91 283 in the real 2015 files), recipients drawn without replacement in
+    proportion to a skewed in-degree (Gumbel top-k), the remaining records repeat existing (source, recipient) pairs."""
     rng = np.random.default_rng(seed)
-    k = np.minimum(1 + rng.geometric(1 / 1.33, N) - 1, 30)                    # distinct recipients per source, mean ~2.3
+    k = np.minimum(rng.geometric(1 / 2.33, N), min(30, M))
     pop = rng.pareto(1.0, M) + 0.05
     pop /= pop.sum()                                                          # skewed recipient in-degree
+    order = np.argsort(-(np.log(pop)[None, :] + rng.gumbel(size=(N, M))), axis=1)
     src = np.repeat(np.arange(N), k)
-    dst = rng.choice(M, src.size, p=pop)
+    dst = order[np.arange(M)[None, :] < k[:, None]]                           # row-major: matches the repeat above
     extra = rng.integers(0, src.size, max(n_records - src.size, 0))           # repeated records (multiplicities)
     src = np.concatenate([src, src[extra]])
     dst = np.concatenate([dst, dst[extra]])
     city = rng.integers(0, 291, N)
     prov = city % 25
     return src.astype(np.int64), dst.astype(np.int64), city.astype(np.int64), prov.astype(np.int64)
+
+
+def capture_step(mg, lib, step, example, use_graph):
+    """Record `step` (forward, loss, backward, Adam) into one CUDA graph (msha_gnn_b200.graphs.CapturedStep).
+    -> (callable, {"cuda_graph": bool, ...}, library kernels per step).  A failed capture is reported, not hidden."""
+    if not use_graph:
+        return step, {"cuda_graph": False}, 0
+    try:
+        l0 = lib.msha_launch_count()
+        captured = mg.CapturedStep(step, [example], warmup=2)
+        per_step = (lib.msha_launch_count() - l0) // 3              # 2 eager warm-ups + the recorded step
+        return captured, {"cuda_graph": True, "launches_in_graph": int(per_step)}, per_step
+    except Exception as e:      # noqa: BLE001
+        torch.cuda.synchronize()
+        return step, {"cuda_graph": False, "cuda_graph_error": repr(e)[:300]}, 0
 
 
 def run_flow(args):
@@ -505,7 +524,8 @@ def run_flow(args):
     torch.manual_seed(42)
     cls = mg.Ours if full else mg.ablation3
     model = cls(in_features=128, out_features=64, n_classes=M, n_heads=2, dropout=0.5, gdp=gdp, Scount=N, Rcount=M).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4, fused=True)      # train.py:207
+    use_graph = not args.no_cuda_graph
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4, fused=True, capturable=use_graph)   # train.py:207
     city_d, prov_d = torch.from_numpy(city).to(dev), torch.from_numpy(prov).to(dev)
     rng = np.random.default_rng(0)
     rec_idx = rng.integers(0, src.size, (args.warmup + 2 * args.steps + 4, B))
@@ -526,22 +546,24 @@ def run_flow(args):
     for i in range(args.warmup):
         step(batches_dev[i])
     torch.cuda.synchronize()
+    run, graph_info, per_step_launches = capture_step(mg, lib, step, batches_dev[0], use_graph)
+    torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
     l0 = lib.msha_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        loss = step(batches_dev[args.warmup + i])
+        loss = run(batches_dev[args.warmup + i])
     e1.record()
     torch.cuda.synchronize()
-    launches = lib.msha_launch_count() - l0
+    launches = per_step_launches * args.steps if graph_info["cuda_graph"] else lib.msha_launch_count() - l0
     ms_dev = e0.elapsed_time(e1) / args.steps
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(args.steps):
-        b = batches_host[args.warmup + args.steps + i].to(dev, non_blocking=True)
-        loss_host = float(step(b).item())
+        hb = batches_host[args.warmup + args.steps + i]
+        loss_host = float(run(hb if graph_info["cuda_graph"] else hb.to(dev, non_blocking=True)).item())
     e3.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -563,7 +585,7 @@ def run_flow(args):
                       "l2_policy": "graph and parameters (~50 MB) are L2-resident by nature of the workload; launch/latency bound"},
            "e2e": {"value": E * layers / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": 2 * B * 8, "d2h_bytes_per_step": 4},
-           "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "kernels": kernels, "loss": loss_host}
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "kernels": kernels, "loss": loss_host, **graph_info}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = flow_cpu_baseline(src, dst, N, M, B, reps=2)
     print(json.dumps(out))
@@ -631,25 +653,27 @@ def run_yearly(args):
         yr["model"] = mg.GAT(n_features=M, n_classes=M, n_heads=H, dropout=0.5, gdp=gdp, N=yr["N"]).to(dev)   # train.py:199
     predictor = mg.LinkPredictor('mlp', M, M, 1, 2, 0.5).to(dev)                # LLP.py:292
     params = [p for yr in years for p in yr["model"].parameters()] + list(predictor.parameters())
-    opt = torch.optim.Adam(params, lr=5e-3, fused=True)                         # LLP.py:15,297
+    use_graph = not args.no_cuda_graph
+    opt = torch.optim.Adam(params, lr=5e-3, fused=True, capturable=use_graph)   # LLP.py:15,297
     rng = np.random.default_rng(0)
     n_batches = args.warmup + 2 * args.steps + 4
+    per_year = []
     for yr in years:
         idx = rng.integers(0, yr["src"].size, (n_batches, B))
-        yr["host"] = torch.from_numpy(np.stack([yr["src"][idx], yr["dst"][idx]], axis=1)).pin_memory()   # (batches, 2, B)
-        yr["dev"] = yr["host"].to(dev)
+        per_year.append(np.stack([yr["src"][idx], yr["dst"][idx]], axis=1))      # (batches, 2, B)
         yr["model"].train()
+    batches_host = torch.from_numpy(np.stack(per_year, axis=1)).pin_memory()     # (batches, years, 2, B)
+    batches_dev = batches_host.to(dev)
     predictor.train()
     lib = mg._lib.lib()
     E_tot = sum(yr["graph"].nnz for yr in years)
     N_tot = sum(yr["N"] for yr in years)
 
-    def step(i, from_host=False):
+    def step(batch):
         opt.zero_grad(set_to_none=True)
         total = None
-        for yr in years:
-            b = yr["host"][i].to(dev, non_blocking=True) if from_host else yr["dev"][i]
-            s_i, r_i = b[0], b[1]
+        for k, yr in enumerate(years):
+            s_i, r_i = batch[k, 0], batch[k, 1]
             h = yr["model"](yr["graph"])                                        # (N, M) log-probs, GAT.py:53-58
             loss = predictor.nll_loss_pairs(h, h, s_i, r_i, r_i)                # LLP.py:233-235
             total = loss if total is None else total + loss
@@ -658,7 +682,9 @@ def run_yearly(args):
         return total
 
     for i in range(args.warmup):
-        step(i)
+        step(batches_dev[i])
+    torch.cuda.synchronize()
+    run, graph_info, per_step_launches = capture_step(mg, lib, step, batches_dev[0], use_graph)
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
@@ -666,22 +692,23 @@ def run_yearly(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        step(args.warmup + i)
+        run(batches_dev[args.warmup + i])
     e1.record()
     torch.cuda.synchronize()
-    launches = lib.msha_launch_count() - l0
+    launches = per_step_launches * args.steps if graph_info["cuda_graph"] else lib.msha_launch_count() - l0
     ms_dev = e0.elapsed_time(e1) / args.steps
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(args.steps):
-        loss_host = float(step(args.warmup + args.steps + i, from_host=True).item())
+        hb = batches_host[args.warmup + args.steps + i]
+        loss_host = float(run(hb if graph_info["cuda_graph"] else hb.to(dev, non_blocking=True)).item())
     e3.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms_e2e = e2.elapsed_time(e3) / args.steps
     with KernelTimer(ops) as kt:
-        step(0)
-        step(1)
+        step(batches_dev[0])
+        step(batches_dev[1])
     agg = kt.summary()
     tot = sum(v[1] for v in agg.values())
     kernels = [{"call": f, "launches_per_step": c // 2, "avg_ms": round(ms / c, 4), "share": round(ms / tot, 4)}
@@ -703,7 +730,7 @@ def run_yearly(args):
            "roofline": {"bound": "hbm", "kernel": "whole step (node-dominated a-1 path; launch-bound)", "achieved": alg_bytes / (ms_dev / 1e3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (ms_dev / 1e3) / 1e9 / hbm_peak, "traffic": None,
                         "note": "algorithmic bytes of the step (SURVEY 8d a-1 model) / device step time; peak " + peak_src},
-           "kernels": kernels, "loss": loss_host}
+           "kernels": kernels, "loss": loss_host, **graph_info}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = yearly_cpu_baseline(years[0]["src"], years[0]["dst"], years[0]["N"], M, H, B)
     print(json.dumps(out))
@@ -844,6 +871,8 @@ def main():
     ap.add_argument("--workload", default="ddi", choices=list(WORKLOADS) + ["flow", "flow-ours", "yearly"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true",
+                    help="flow / flow-ours / yearly: launch every kernel from the host instead of replaying one captured CUDA graph")
     ap.add_argument("--unfused-loss", action="store_true",
                     help="separate nll_loss op: the dense d scores tensor is written and re-read (default: fused into the scorer backward)")
     args = ap.parse_args()

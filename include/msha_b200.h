@@ -202,6 +202,12 @@ int msha_score_mlp_nll_bwd(const int64_t* target, const float* gout, const float
 int msha_negative_sample(uint64_t seed, int64_t P, int64_t n_src, int64_t n_dst, int64_t* src, int64_t* dst,
                          void* stream);
 int msha_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* keep, void* stream);
+/* Dropout epoch for CUDA-graph replay: every dropout draw keys Philox with seed + epoch * 0x9E3779B97F4A7C15 (mod 2^64).
+ * A captured launch bakes its by-value seed; put msha_dropout_epoch_advance(1, capture_stream) first in the captured step
+ * and each replay draws fresh keep-masks (forward and backward of one replay still agree).  Stream-ordered device-side
+ * state (the one piece of global state besides the descriptor caches); epoch 0 is the default and changes nothing. */
+int msha_dropout_epoch_set(uint64_t epoch, void* stream);
+int msha_dropout_epoch_advance(uint64_t by, void* stream);
 
 /* ==== callers either side of the path ==== */
 

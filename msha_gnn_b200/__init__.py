@@ -14,11 +14,12 @@ from .layers import (GAT, GATConv, GATLinkModel, GraphAttentionLayer, GraphConvo
                      export_attention)
 from .data import HigherDataset, read_flow_files, normalize_adjacency_matrix   # noqa: F401
 from . import functional                             # noqa: F401
+from .graphs import CapturedStep                     # noqa: F401
 
 __all__ = ["Graph", "as_graph", "GroupLists", "GAT", "GATConv", "GATLinkModel", "GraphAttentionLayer",
            "GraphConvolution", "HGANELayer", "LinkPredictor", "Teacher_LinkPredictor", "Ours", "OursLayer", "OursLayer2",
            "OursLayer3", "ablation1", "ablation2", "ablation3", "functional", "MLP", "KD_cosine", "llp_distill_loss", "GCN",
-           "GraphSAGE", "export_attention", "HigherDataset", "read_flow_files", "normalize_adjacency_matrix"]
+           "GraphSAGE", "export_attention", "CapturedStep", "HigherDataset", "read_flow_files", "normalize_adjacency_matrix"]
 
 
 def build(force: bool = False):

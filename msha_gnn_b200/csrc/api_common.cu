@@ -33,3 +33,25 @@ MSHA_API int msha_check_device(void) {
     }
     return 0;
 }
+
+// Dropout epoch: see common.cuh.  Stream-ordered and capturable; one hook per translation unit that draws dropout.
+int msha_drop_epoch_hook_gat(unsigned long long v, int set, cudaStream_t st);
+int msha_drop_epoch_hook_dense(unsigned long long v, int set, cudaStream_t st);
+int msha_drop_epoch_hook_intra(unsigned long long v, int set, cudaStream_t st);
+
+static int drop_epoch_all(unsigned long long v, int set, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int (*hooks[3])(unsigned long long, int, cudaStream_t) = {msha_drop_epoch_hook_gat, msha_drop_epoch_hook_dense,
+                                                               msha_drop_epoch_hook_intra};
+    for (int i = 0; i < 3; ++i) {
+        int e = hooks[i](v, set, st);
+        if (e != 0) {
+            msha_set_error("dropout epoch kernel launch -> %s", cudaGetErrorString((cudaError_t)e));
+            return e;
+        }
+        __atomic_fetch_add(&g_msha_launches, 1ull, __ATOMIC_RELAXED);
+    }
+    return 0;
+}
+MSHA_API int msha_dropout_epoch_set(uint64_t epoch, void* stream) { return drop_epoch_all(epoch, 1, stream); }
+MSHA_API int msha_dropout_epoch_advance(uint64_t by, void* stream) { return drop_epoch_all(by, 0, stream); }

@@ -98,9 +98,31 @@ __device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint32_t stream, 
     return l == 0 ? r.x : (l == 1 ? r.y : (l == 2 ? r.z : r.w));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dropout epoch (CUDA-graph replay).  A captured launch bakes its by-value seed, so a replayed graph would repeat its
+// keep-masks.  Every dropout draw therefore keys Philox with seed + epoch * 2^64/phi, where `epoch` is a device word
+// that msha_dropout_epoch_advance() bumps with a (capturable) one-thread kernel -- put it first in the captured step.
+// The word is per translation unit (no relocatable device code): MSHA_DEFINE_DROP_EPOCH_HOOK(tu) defines the hook
+// api_common.cu calls for each unit that draws dropout.  epoch == 0 (the default) leaves the stream unchanged.
+// ---------------------------------------------------------------------------------------------
+static __device__ unsigned long long g_drop_epoch __attribute__((unused)) = 0ull;
+
+__device__ __forceinline__ uint64_t drop_seed_eff(uint64_t seed) {
+    return seed + (uint64_t)g_drop_epoch * 0x9E3779B97F4A7C15ull;
+}
+
 // dropout multiplier of element i: 0 if dropped, 1/(1-p) if kept (keep iff word >= thr)
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t stream, uint64_t i, uint32_t thr,
                                                float inv_keep) {
-    return philox_word(seed, stream, i) >= thr ? inv_keep : 0.f;
+    return philox_word(drop_seed_eff(seed), stream, i) >= thr ? inv_keep : 0.f;
 }
+
+#define MSHA_DEFINE_DROP_EPOCH_HOOK(tu)                                                             \
+    __global__ void drop_epoch_kernel_##tu(unsigned long long v, int set) {                         \
+        g_drop_epoch = set ? v : g_drop_epoch + v;                                                  \
+    }                                                                                               \
+    int msha_drop_epoch_hook_##tu(unsigned long long v, int set, cudaStream_t st) {                 \
+        drop_epoch_kernel_##tu<<<1, 1, 0, st>>>(v, set);                                            \
+        return (int)cudaGetLastError();                                                             \
+    }
 #endif

@@ -8,6 +8,8 @@
 //   * pair gather * Hadamard / scatter-add for the link scorer                        (LLP.py:105)
 #include "common.cuh"
 
+MSHA_DEFINE_DROP_EPOCH_HOOK(dense)
+
 enum { ACT_NONE = 0, ACT_ELU = 1, ACT_RELU = 2, ACT_SIGMOID_RELU = 3, ACT_LRELU = 4, ACT_SIGMOID = 5 };
 
 __device__ __forceinline__ float apply_act(float x, int act, float slope) {
@@ -205,6 +207,25 @@ __global__ void dropout_apply_kernel(const float* __restrict__ x, float* __restr
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) y[i] = x[i] * dropout_scale(drop.seed, drop.stream, (uint64_t)i, drop.thr, drop.inv_keep);
 }
+// same masks, one Philox block (4 words) per thread and 128-bit accesses: element 4b + k <- word k of block b
+__global__ void dropout_apply_kernel4(const float* x, float* y, int64_t n, DropArgsD drop) {
+    const uint64_t seed = drop_seed_eff(drop.seed);
+    const int64_t nb = n >> 2, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += stride) {
+        const Philox4 r = philox4x32_10((uint32_t)b, (uint32_t)((uint64_t)b >> 32), drop.stream, 0u, (uint32_t)seed,
+                                        (uint32_t)(seed >> 32));
+        float4 v = reinterpret_cast<const float4*>(x)[b];
+        v.x *= r.x >= drop.thr ? drop.inv_keep : 0.f;
+        v.y *= r.y >= drop.thr ? drop.inv_keep : 0.f;
+        v.z *= r.z >= drop.thr ? drop.inv_keep : 0.f;
+        v.w *= r.w >= drop.thr ? drop.inv_keep : 0.f;
+        reinterpret_cast<float4*>(y)[b] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
+        const int64_t i = (nb << 2) + threadIdx.x;
+        y[i] = x[i] * dropout_scale(drop.seed, drop.stream, (uint64_t)i, drop.thr, drop.inv_keep);
+    }
+}
 MSHA_API int msha_dropout_apply(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t stream_id,
                                 void* stream) {
     MSHA_REQUIRE(p >= 0.f && p < 1.f, "dropout: p must be in [0,1)");
@@ -213,9 +234,13 @@ MSHA_API int msha_dropout_apply(const float* x, float* y, int64_t n, float p, ui
         if (x != y) MSHA_CUDA(cudaMemcpyAsync(y, x, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         return 0;
     }
-    int64_t g = msha_cdiv(n, 256);
+    const bool vec = ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 && n >= 4;
+    int64_t g = msha_cdiv(vec ? (n >> 2) : n, 256);
     if (g > (int64_t)MSHA_NUM_SMS * 16) g = (int64_t)MSHA_NUM_SMS * 16;
-    dropout_apply_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, y, n, make_drop_d(p, seed, stream_id));
+    if (vec)
+        dropout_apply_kernel4<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, y, n, make_drop_d(p, seed, stream_id));
+    else
+        dropout_apply_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, y, n, make_drop_d(p, seed, stream_id));
     MSHA_LAUNCH_OK();
     return 0;
 }
@@ -587,7 +612,7 @@ MSHA_API int msha_negative_sample(uint64_t seed, int64_t P, int64_t n_src, int64
 __global__ void dropout_mask_kernel(uint64_t seed, uint32_t stream_id, int64_t n, uint32_t thr, uint8_t* __restrict__ keep) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    keep[i] = philox_word(seed, stream_id, (uint64_t)i) >= thr ? 1 : 0;
+    keep[i] = philox_word(drop_seed_eff(seed), stream_id, (uint64_t)i) >= thr ? 1 : 0;
 }
 MSHA_API int msha_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* keep, void* stream) {
     if (n <= 0) return 0;

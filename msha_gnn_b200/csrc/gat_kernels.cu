@@ -13,6 +13,8 @@
 // loads), VPL vectors per lane.  Per-edge weights of the current 32-edge chunk are staged in shared memory.
 // Masked edges (col < 0, j = ~col) are the reference's isolated-row semantics: logit = -9e15, no gradient.
 #include "common.cuh"
+
+MSHA_DEFINE_DROP_EPOCH_HOOK(gat)
 #include "msha_b200.h"
 
 #define NEG_MASK_F (-9e15f)

@@ -11,6 +11,8 @@
 // adjacency, or group-member lists when the adjacency is a group-equality block structure).
 #include "common.cuh"
 
+MSHA_DEFINE_DROP_EPOCH_HOOK(intra)
+
 struct DropI { uint32_t thr; float inv_keep; uint64_t seed; uint32_t stream; };
 static DropI make_drop_i(float p, uint64_t seed, uint32_t stream) {
     DropI d; d.thr = 0; d.inv_keep = 1.f; d.seed = seed; d.stream = stream;

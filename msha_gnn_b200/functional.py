@@ -629,10 +629,13 @@ class _ScoreMLPNll(torch.autograd.Function):
         ctx.act, ctx.has_bias = act, b0 is not None
         ctx.save_for_backward(hi, hj, src, dst, W0, out, target)
         ctx.mark_non_differentiable(out)
+        ctx.set_materialize_grads(False)      # otherwise autograd zero-fills a (P, Hd) gradient for `out` on every backward
         return loss, out
 
     @staticmethod
     def backward(ctx, gloss, _gout_unused):
+        if gloss is None:
+            return (None,) * 8
         hi, hj, src, dst, W0, out, target = ctx.saved_tensors
         P, Hd = out.shape
         C = W0.shape[1]

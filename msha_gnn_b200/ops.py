@@ -125,3 +125,14 @@ def dropout_apply(x, p, seed, stream_id=4):
     y = torch.empty_like(x)
     call("msha_dropout_apply", ptr(x), ptr(y), x.numel(), float(p), seed, stream_id, _stream())
     return y
+
+
+# ------------------------------------------------------------------------------------------ dropout epoch
+def dropout_epoch_set(epoch: int):
+    """Set the device-side dropout epoch (stream-ordered; 0 = the plain seed stream).  See ``msha_dropout_epoch_set``."""
+    call("msha_dropout_epoch_set", int(epoch) & 0xFFFFFFFFFFFFFFFF, _stream())
+
+
+def dropout_epoch_advance(by: int = 1):
+    """Bump the dropout epoch on the current stream -- capturable: first node of a captured training step."""
+    call("msha_dropout_epoch_advance", int(by) & 0xFFFFFFFFFFFFFFFF, _stream())

@@ -576,7 +576,12 @@ def negative_sample(seed: int, n_pairs: int, n_src: int, n_dst: int):
     return s.astype(np.int64), d.astype(np.int64)
 
 
-def dropout_keep_mask(seed: int, n: int, p: float, stream: int = 2) -> np.ndarray:
-    """Element i is kept iff word i of ``stream`` >= floor(p * 2^32)."""
+DROP_EPOCH_STRIDE = 0x9E3779B97F4A7C15   # 2^64 / golden ratio: the per-replay key stride (csrc/common.cuh drop_seed_eff)
+
+
+def dropout_keep_mask(seed: int, n: int, p: float, stream: int = 2, epoch: int = 0) -> np.ndarray:
+    """Element i is kept iff word i of ``stream`` >= floor(p * 2^32); the Philox key is
+    ``seed + epoch * DROP_EPOCH_STRIDE (mod 2^64)`` -- ``epoch`` is the CUDA-graph replay counter, 0 outside graphs."""
     thr = np.uint64(min(int(p * 4294967296.0), 0xFFFFFFFF))
-    return _philox_words(seed, stream, n).astype(np.uint64) >= thr
+    key = (int(seed) + int(epoch) * DROP_EPOCH_STRIDE) & 0xFFFFFFFFFFFFFFFF
+    return _philox_words(key, stream, n).astype(np.uint64) >= thr
