@@ -337,7 +337,19 @@ MSHA_API int msha_gemm_tf32x3(const float* A, const float* B, float* C, int64_t 
     if (splits > total_kb) splits = total_kb;
     const bool a_mn = transA != 0;      // A stored [K, M]  -> MN-major
     const bool b_mn = transB == 0;      // B stored [K, N]  -> MN-major
-    const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    // N tile: the widest that N allows, narrowed while that shortens the schedule -- a persistent CTA per SM runs
+    // ceil(work / 148) rounds of tiles whose cost grows with BLOCK_N (+ a fixed part: pipeline fill, epilogue drain).
+    // 4 267 x 256 (DDI layer): 34 tiles of 256 leave 114 SMs idle, 136 tiles of 64 do not.
+    int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    {
+        const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+        int64_t best = -1;
+        for (int bn = BN; bn >= 64; bn >>= 1) {
+            const int64_t work = m_tiles * ((N + bn - 1) / bn) * splits;
+            const int64_t cost = ((work + MSHA_NUM_SMS - 1) / MSHA_NUM_SMS) * (bn + 32);
+            if (best < 0 || cost < best) { best = cost; BN = bn; }
+        }
+    }
     CUtensorMap ta, tb;
     int rc;
     if (a_mn) rc = tc_make_map(&ta, A, M, K, lda, 32, BLOCK_K, true); else rc = tc_make_map(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, false);
