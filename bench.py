@@ -98,9 +98,11 @@ def make_graph_host(wl, seed_shift=0):
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """Samples SM clock, power and throttle reasons DURING the timed region through NVML (in-process thread;
-    an `nvidia-smi -lms` child stalls the driver for tens of ms per query on these hosts)."""
+    an `nvidia-smi -lms` child stalls the driver for tens of ms per query on these hosts).  Every NVML query still
+    delays kernel-completion delivery a little: at a 20 ms period the host-synchronised e2e loop of the graph-replayed
+    `yearly` step measured 3.3-6.5 ms instead of 2.4 ms, hence the 50 ms default."""
 
-    def __init__(self, index=0, period_s=float(os.environ.get("MSHA_BENCH_NVML_PERIOD", "0.02"))):
+    def __init__(self, index=0, period_s=float(os.environ.get("MSHA_BENCH_NVML_PERIOD", "0.05"))):
         self.index, self.period, self.rows, self._stop, self.t, self.err = index, period_s, [], False, None, None
 
     def start(self):
@@ -491,15 +493,15 @@ def flow_graph(seed=2015, N=39179, M=32, n_records=233887):
     return src.astype(np.int64), dst.astype(np.int64), city.astype(np.int64), prov.astype(np.int64)
 
 
-def capture_step(mg, lib, step, example, use_graph):
+def capture_step(mg, lib, step, example, use_graph, warmup=2):
     """Record `step` (forward, loss, backward, Adam) into one CUDA graph (msha_gnn_b200.graphs.CapturedStep).
     -> (callable, {"cuda_graph": bool, ...}, library kernels per step).  A failed capture is reported, not hidden."""
     if not use_graph:
         return step, {"cuda_graph": False}, 0
     try:
         l0 = lib.msha_launch_count()
-        captured = mg.CapturedStep(step, [example], warmup=2)
-        per_step = (lib.msha_launch_count() - l0) // 3              # 2 eager warm-ups + the recorded step
+        captured = mg.CapturedStep(step, [example], warmup=warmup)
+        per_step = (lib.msha_launch_count() - l0) // (warmup + 1)   # eager warm-ups + the recorded step
         return captured, {"cuda_graph": True, "launches_in_graph": int(per_step)}, per_step
     except Exception as e:      # noqa: BLE001
         torch.cuda.synchronize()
@@ -543,10 +545,14 @@ def run_flow(args):
         opt.step()
         return loss
 
-    for i in range(args.warmup):
-        step(batches_dev[i])
+    if not use_graph:
+        for i in range(args.warmup):
+            step(batches_dev[i])
     torch.cuda.synchronize()
-    run, graph_info, per_step_launches = capture_step(mg, lib, step, batches_dev[0], use_graph)
+    run, graph_info, per_step_launches = capture_step(mg, lib, step, batches_dev[0], use_graph, warmup=args.warmup)
+    if use_graph and not graph_info["cuda_graph"]:
+        for i in range(args.warmup):
+            step(batches_dev[i])
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
@@ -561,13 +567,23 @@ def run_flow(args):
     ms_dev = e0.elapsed_time(e1) / args.steps
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    trace = [0.0, 0.0] if os.environ.get("MSHA_BENCH_TRACE") else None
     for i in range(args.steps):
         hb = batches_host[args.warmup + args.steps + i]
-        loss_host = float(run(hb if graph_info["cuda_graph"] else hb.to(dev, non_blocking=True)).item())
+        t0 = time.perf_counter()
+        loss_t = run(hb if graph_info["cuda_graph"] else hb.to(dev, non_blocking=True))
+        t1 = time.perf_counter()
+        loss_host = float(loss_t.item())
+        if trace is not None:
+            trace[0] += t1 - t0
+            trace[1] += time.perf_counter() - t1
     e3.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms_e2e = e2.elapsed_time(e3) / args.steps
+    if trace is not None:
+        print(f"e2e host trace: enqueue {trace[0] / args.steps * 1e3:.3f} ms, wait for loss {trace[1] / args.steps * 1e3:.3f} ms per step",
+              file=sys.stderr)
     with KernelTimer(ops) as kt:
         step(batches_dev[0])
         step(batches_dev[1])
@@ -681,10 +697,14 @@ def run_yearly(args):
         opt.step()
         return total
 
-    for i in range(args.warmup):
-        step(batches_dev[i])
+    if not use_graph:
+        for i in range(args.warmup):
+            step(batches_dev[i])
     torch.cuda.synchronize()
-    run, graph_info, per_step_launches = capture_step(mg, lib, step, batches_dev[0], use_graph)
+    run, graph_info, per_step_launches = capture_step(mg, lib, step, batches_dev[0], use_graph, warmup=args.warmup)
+    if use_graph and not graph_info["cuda_graph"]:
+        for i in range(args.warmup):
+            step(batches_dev[i])
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
@@ -699,13 +719,23 @@ def run_yearly(args):
     ms_dev = e0.elapsed_time(e1) / args.steps
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    trace = [0.0, 0.0] if os.environ.get("MSHA_BENCH_TRACE") else None
     for i in range(args.steps):
         hb = batches_host[args.warmup + args.steps + i]
-        loss_host = float(run(hb if graph_info["cuda_graph"] else hb.to(dev, non_blocking=True)).item())
+        t0 = time.perf_counter()
+        loss_t = run(hb if graph_info["cuda_graph"] else hb.to(dev, non_blocking=True))
+        t1 = time.perf_counter()
+        loss_host = float(loss_t.item())
+        if trace is not None:
+            trace[0] += t1 - t0
+            trace[1] += time.perf_counter() - t1
     e3.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms_e2e = e2.elapsed_time(e3) / args.steps
+    if trace is not None:
+        print(f"e2e host trace: enqueue {trace[0] / args.steps * 1e3:.3f} ms, wait for loss {trace[1] / args.steps * 1e3:.3f} ms per step",
+              file=sys.stderr)
     with KernelTimer(ops) as kt:
         step(batches_dev[0])
         step(batches_dev[1])

@@ -33,17 +33,19 @@ class CapturedStep:
             raise RuntimeError("msha_b200 is CUDA-only: CapturedStep needs a CUDA device")
         self.fn = fn
         self.static_inputs = [x.clone() for x in example_inputs]
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        # warm-up and capture share one side stream: autograd pins each parameter's gradient accumulation to the stream
+        # it first ran on, and a capture on a different stream would have to cross-synchronise with it
+        self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
             for _ in range(max(warmup, 1)):
                 if advance_dropout:
                     ops.dropout_epoch_advance(1)
                 fn(*self.static_inputs)
-        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream().wait_stream(self.stream)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=self.stream):
             if advance_dropout:
                 ops.dropout_epoch_advance(1)
             self.static_output = fn(*self.static_inputs)
