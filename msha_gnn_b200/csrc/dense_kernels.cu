@@ -160,23 +160,25 @@ __global__ void gal_rows_kernel(const float* __restrict__ h, const float* __rest
     __syncwarp();
     const int beg = rowptr[row], end = rowptr[row + 1];
     if (end == beg) return;
-    const float w = 1.f / (float)(end - beg);
-    for (int e = beg + lane; e < end; e += 32) {
-        int c = col[e];
+    const int deg = end - beg;
+    const float w = 1.f / (float)deg;
+    // lanes tile the (head, edge) pairs of the row: a 2015-shaped row has ~2.3 edges, so an edge-per-lane loop would keep
+    // 2-3 lanes busy with H serial Philox draws and dependent loads each
+    for (int t = lane; t < deg * H; t += 32) {
+        const int hh = t / deg;
+        const int c = col[beg + (t - hh * deg)];
         const int j = c < 0 ? ~c : c;
-        for (int hh = 0; hh < H; ++hh) {
-            float a = w;
-            if (drop.thr)
-                a *= dropout_scale(drop.seed, drop.stream, ((uint64_t)hh * n_rows + row) * M + j, drop.thr, drop.inv_keep);
-            const int64_t idx = row * HM + hh * M + j;
-            const float x = h[idx];
-            if (mode == 0) {
-                const float v = a * x;
-                o[hh * M + j] = v > 0.f ? v : expm1f(v);
-            } else {
-                const float yy = y[idx];
-                o[hh * M + j] = x * (yy > 0.f ? 1.f : yy + 1.f) * a;
-            }
+        float a = w;
+        if (drop.thr)
+            a *= dropout_scale(drop.seed, drop.stream, ((uint64_t)hh * n_rows + row) * M + j, drop.thr, drop.inv_keep);
+        const int64_t idx = row * HM + hh * M + j;
+        const float x = h[idx];
+        if (mode == 0) {
+            const float v = a * x;
+            o[hh * M + j] = v > 0.f ? v : expm1f(v);
+        } else {
+            const float yy = y[idx];
+            o[hh * M + j] = x * (yy > 0.f ? 1.f : yy + 1.f) * a;
         }
     }
 }
