@@ -159,6 +159,9 @@ def algorithmic_bytes(wl, E, P):
         "msha_gat_fwd": E * (4 + 8 * H + 4 * C) + N * 4 * C,
         "msha_gat_bwd_rows": E * (4 + 8 * H + 4 * C + 4 * H) + N * 12 * C,
         "msha_spmm_csc": E * (8 + 8 * H + 4 * C) + N * 4 * C,
+        # contraction-free scorer backward under the nll read-out: order + label + indices + one score sector, two row
+        # gathers and two read-modify-write row scatters per pair (SURVEY 8d scoring model minus the dense dOut / out / G)
+        "msha_score_mlp_nll_bwd_sparse": P * (4 + 8 + 16 + 32 + 8 * C + 16 * C),
         "msha_pair_gather_mul": P * (16 + 8 * C + 4 * C),
         "msha_pair_scatter_mul_add": P * (16 + 4 * C + 8 * C + 16 * C),
     }
@@ -224,6 +227,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     hbm_peak, _, peak_src = load_peaks()
+    if args.dense_nll_bwd:
+        mg.functional.SPARSE_NLL_BWD = False
 
     # ---- data.  N = 1: the workload graph.  N > 1 (weak scaling): the graph grows with N -- N*n nodes, N*E edges,
     # same degree distribution -- and is partitioned by destination-node range; rank r generates the edges of its
@@ -449,7 +454,11 @@ def run_ours(args):
                                f"{'strong' if strong else 'weak'} scaling: graph of {n_glob} nodes / {E_global} edges partitioned by destination-node range, "
                                "per layer one NCCL all-gather (fwd) + reduce-scatter (bwd) of [Wh|s_nbr]; pairs data-parallel; "
                                "parameter gradients all-reduced"),
-                   "l2_policy": "per-step working set (>= 4*P*pred_hidden bytes of scores) exceeds the 126 MB L2; no explicit flush"},
+                   "l2_policy": "per-step working set (>= 4*P*pred_hidden bytes of scores) exceeds the 126 MB L2; no explicit flush",
+                   "scorer_backward": ("separate nll_loss op + tensor-core backward" if args.unfused_loss else
+                                       "tensor-core backward with the nll gradient generated in-kernel" if not mg.functional.SPARSE_NLL_BWD else
+                                       "contraction-free: d scores of the nll read-out is one-hot per pair, so dZ = g_p * W0[label] and "
+                                       "dW0 is a per-label sum (same gradients as the dense GEMMs, --dense-nll-bwd runs those)")},
         "pairs_per_sec": P_global / (ms_dev / 1e3),
         "e2e": {"value": total_edges / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(pos_host.numel() * 8), "d2h_bytes_per_step": 4,
@@ -903,6 +912,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true",
                     help="flow / flow-ours / yearly: launch every kernel from the host instead of replaying one captured CUDA graph")
+    ap.add_argument("--dense-nll-bwd", action="store_true",
+                    help="scorer backward on the tensor cores even under the nll read-out (default: the contraction-free "
+                         "kernel that exploits the one-hot d scores)")
     ap.add_argument("--unfused-loss", action="store_true",
                     help="separate nll_loss op: the dense d scores tensor is written and re-read (default: fused into the scorer backward)")
     args = ap.parse_args()

@@ -198,6 +198,19 @@ int msha_score_mlp_nll_bwd(const int64_t* target, const float* gout, const float
                            const float* hj_tab, const int64_t* src, const int64_t* dst, int64_t P, int64_t C,
                            const float* W0, int64_t Hd, int act, float slope, float* G, float* dhi, float* dhj,
                            float* dW0, float* db0, void* ws, size_t ws_bytes, void* stream);
+/* The same backward without any contraction: under the nll read-out G = dOut * act'(out) has one non-zero per row
+ * (g_p at column target[p]), so dZ[p] = g_p * W0[target[p]], dW0[c] = sum_{p: target[p] == c} g_p * Z[p], db0[c] = sum g_p --
+ * O(P C) gathers and vector atomics instead of 4 P C Hd flops; pairs whose activation is flat at the target are skipped.
+ * order: uint32[P] pair indices stably sorted by label (msha_score_nll_label_order; NULL = identity, for labels that
+ * already come in runs): label runs keep the dW0 / db0 partial sums in registers.  dhi / dhj accumulated into,
+ * dW0 / db0 overwritten.  Needs C % 4 == 0, C <= 1024 and 16-byte aligned tables / gradients; any Hd. */
+int msha_score_mlp_nll_bwd_sparse(const uint32_t* order, const int64_t* target, const float* gout, const float* out,
+                                  int64_t ldo, const float* hi_tab, const float* hj_tab, const int64_t* src,
+                                  const int64_t* dst, int64_t P, int64_t C, const float* W0, int64_t Hd, int act,
+                                  float slope, float* dhi, float* dhj, float* dW0, float* db0, void* stream);
+/* keys, keys_tmp: uint64[P]; order, order_tmp: uint32[P]; ws: msha_radix_sort_workspace_bytes(P) */
+int msha_score_nll_label_order(const int64_t* target, int64_t P, int64_t Hd, uint64_t* keys, uint64_t* keys_tmp,
+                               uint32_t* order, uint32_t* order_tmp, void* ws, size_t ws_bytes, void* stream);
 /* builder-defined sampler (the reference's --ns_rate flags are dead code, LLP.py:26-29) */
 int msha_negative_sample(uint64_t seed, int64_t P, int64_t n_src, int64_t n_dst, int64_t* src, int64_t* dst,
                          void* stream);

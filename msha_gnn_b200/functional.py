@@ -6,6 +6,8 @@ library as raw pointers on the current stream.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -640,16 +642,39 @@ class _ScoreMLPNll(torch.autograd.Function):
         P, Hd = out.shape
         C = W0.shape[1]
         lib = ops._lib.lib()
-        g = torch.empty_like(out)
         dhi, dhj = torch.zeros_like(hi), torch.zeros_like(hj)
         dW = torch.empty_like(W0)
         db = torch.empty(Hd, dtype=torch.float32, device=out.device)
-        ws = workspace(lib.msha_score_mlp_workspace_bytes(C, Hd), out.device)
         gl = _c(gloss.reshape(1).float())
+        if SPARSE_NLL_BWD and C % 4 == 0 and C <= 1024 and P < (1 << 31):
+            # d out is one-hot per row: no GEMM left, only gathers and vector atomics (csrc/score_nll_sparse.cu)
+            order = nll_label_order(target, Hd)
+            call("msha_score_mlp_nll_bwd_sparse", ptr(order, I32), ptr(target, torch.int64), ptr(gl), ptr(out), Hd, ptr(hi),
+                 ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C, ptr(W0), Hd, ctx.act, LRELU_SLOPE, ptr(dhi),
+                 ptr(dhj), ptr(dW), ptr(db), _stream())
+            return dhi, dhj, None, None, dW, (db if ctx.has_bias else None), None, None
+        g = torch.empty_like(out)
+        ws = workspace(lib.msha_score_mlp_workspace_bytes(C, Hd), out.device)
         call("msha_score_mlp_nll_bwd", ptr(target, torch.int64), ptr(gl), ptr(out), ptr(hi), ptr(hj), ptr(src, torch.int64),
              ptr(dst, torch.int64), P, C, ptr(W0), Hd, ctx.act, LRELU_SLOPE, ptr(g), ptr(dhi), ptr(dhj), ptr(dW), ptr(db),
              ws.data_ptr(), ws.numel(), _stream())
         return dhi, dhj, None, None, dW, (db if ctx.has_bias else None), None, None
+
+
+SPARSE_NLL_BWD = os.environ.get("MSHA_NLL_BWD", "sparse") != "dense"   # "dense": the tensor-core backward (validation / comparison)
+
+
+def nll_label_order(target, n_classes):
+    """Pair indices stably sorted by label (uint32 bits in an int32 tensor) -- the traversal order of the sparse backward."""
+    P = target.numel()
+    dev = target.device
+    keys = torch.empty((2, P), dtype=torch.int64, device=dev)
+    order = torch.empty((2, P), dtype=I32, device=dev)
+    lib = ops._lib.lib()
+    ws = workspace(lib.msha_radix_sort_workspace_bytes(P), dev)
+    call("msha_score_nll_label_order", ptr(target, torch.int64), P, n_classes, keys[0].data_ptr(), keys[1].data_ptr(),
+         order[0].data_ptr(), order[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    return order[0]
 
 
 def score_mlp_nll_supported(hi, hj, W0):

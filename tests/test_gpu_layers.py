@@ -399,3 +399,78 @@ def test_fused_scorer_nll_matches_separate_ops(P, C, Hd, Nn):
     got = [h2.grad, lp.lins[0].weight.grad, lp.lins[0].bias.grad]
     for a, b in zip(got, ref):
         assert rel_err(_np(a), _np(b)) < 1e-5
+
+
+@pytest.mark.parametrize("P,C,Hd,Nn,labels", [(5000, 256, 256, 300, "random"), (4097, 64, 128, 50, "random"),
+                                              (70001, 256, 256, 4267, "runs"), (1000, 128, 32, 77, "bad"),
+                                              (257, 256, 256, 9, "one")])
+def test_sparse_nll_backward_matches_dense_and_oracle(P, C, Hd, Nn, labels, monkeypatch):
+    """The contraction-free backward (d scores is one-hot per row) == the tensor-core backward == the fp64 oracle, for labels
+    spread over all Hd classes, in runs, partly out of range, and all equal."""
+    g = torch.Generator().manual_seed(P + 7)
+    lp = mg.LinkPredictor("mlp", C, Hd, 1, 2, 0.0).to(DEV)
+    h = (torch.randn(Nn, C, generator=g) * 0.5)
+    src = torch.randint(0, Nn, (P,), generator=g)
+    dst = torch.randint(0, Nn, (P,), generator=g)
+    if labels == "random":
+        tgt = torch.randint(0, Hd, (P,), generator=g)
+    elif labels == "runs":
+        tgt = torch.cat([torch.ones(P // 2, dtype=torch.int64), torch.zeros(P - P // 2, dtype=torch.int64)])
+    elif labels == "one":
+        tgt = torch.full((P,), Hd - 1, dtype=torch.int64)
+    else:
+        tgt = torch.randint(0, Hd, (P,), generator=g)
+        tgt[::7] = Hd + 3                                  # out of range: contributes nothing to any gradient
+        tgt[3::11] = -1
+    grads = {}
+    for mode in ("sparse", "dense"):
+        monkeypatch.setattr(Fn, "SPARSE_NLL_BWD", mode == "sparse")
+        lp.zero_grad(set_to_none=True)
+        hd = h.clone().to(DEV).requires_grad_(True)
+        loss = 2.0 * lp.nll_loss_pairs(hd, hd, src.to(DEV), dst.to(DEV), tgt.to(DEV))
+        loss.backward()
+        grads[mode] = [_np(hd.grad), _np(lp.lins[0].weight.grad), _np(lp.lins[0].bias.grad)]
+    for a, b in zip(grads["sparse"], grads["dense"]):
+        assert rel_err(a, b) < 2e-5
+    # oracle (fp64): autograd through the restated scorer + read-out; bad labels masked out of the mean's numerator
+    ho = torch.tensor(h.numpy(), dtype=torch.float64, requires_grad=True)
+    W = [torch.tensor(_np(l.weight), dtype=torch.float64, requires_grad=True) for l in lp.lins]
+    b = [torch.tensor(_np(l.bias), dtype=torch.float64, requires_grad=True) for l in lp.lins]
+    out = O.link_predictor(ho[src], ho[dst], W, b)
+    ok = (tgt >= 0) & (tgt < Hd)
+    picked = out[torch.arange(P)[ok], tgt[ok]]
+    (2.0 * -(picked.sum() / P)).backward()
+    assert rel_err(grads["sparse"][0], ho.grad.numpy()) < TOL
+    assert rel_err(grads["sparse"][1], W[0].grad.numpy()) < TOL
+    assert rel_err(grads["sparse"][2], b[0].grad.numpy()) < TOL
+
+
+def test_sparse_nll_backward_identity_order():
+    """order == NULL walks the pairs as they come (labels already in runs)."""
+    from msha_gnn_b200.ops import call, ptr, _stream
+    g = torch.Generator().manual_seed(3)
+    P, C, Hd, Nn = 3000, 256, 64, 40
+    h = (torch.randn(Nn, C, generator=g) * 0.5).to(DEV)
+    W0 = (torch.randn(Hd, C, generator=g) * 0.1).to(DEV)
+    out = torch.rand(P, Hd, generator=g).to(DEV)                     # any saved activations in (0, 1)
+    src = torch.randint(0, Nn, (P,), generator=g).to(DEV)
+    dst = torch.randint(0, Nn, (P,), generator=g).to(DEV)
+    tgt = torch.sort(torch.randint(0, Hd, (P,), generator=g)).values.to(DEV)
+    gl = torch.ones(1, device=DEV)
+    res = []
+    for order in (None, Fn.nll_label_order(tgt, Hd)):
+        dhi, dhj = torch.zeros_like(h), torch.zeros_like(h)
+        dW, db = torch.empty_like(W0), torch.empty(Hd, device=DEV)
+        call("msha_score_mlp_nll_bwd_sparse", ptr(order, torch.int32), ptr(tgt, torch.int64), ptr(gl), ptr(out), Hd, ptr(h),
+             ptr(h), ptr(src, torch.int64), ptr(dst, torch.int64), P, C, ptr(W0), Hd, 3, 0.2, ptr(dhi), ptr(dhj), ptr(dW),
+             ptr(db), _stream())
+        res.append([_np(dhi), _np(dhj), _np(dW), _np(db)])
+    assert np.array_equal(_np(Fn.nll_label_order(tgt, Hd)), np.arange(P))      # stable sort of sorted labels
+    for a, b in zip(*res):
+        assert rel_err(a, b) < 1e-5
+    # closed form of db0: sum of g_p per label
+    y = _np(out)[np.arange(P), _np(tgt)]
+    gp = -(1.0 / P) * np.where(y > 0.5, y * (1 - y), 0.0)
+    want = np.zeros(Hd)
+    np.add.at(want, _np(tgt), gp)
+    assert rel_err(res[0][3], want) < 1e-5

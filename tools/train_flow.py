@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--weight_decay", type=float, default=5e-4)     # train.py:31
     ap.add_argument("--batch_size", type=int, default=64)           # train.py:33
     ap.add_argument("--max_steps", type=int, default=0, help="stop an epoch early (0 = full epoch)")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="replay the training step as one CUDA graph (msha_gnn_b200.CapturedStep); full batches only")
     args = ap.parse_args()
     torch.manual_seed(args.seed)
     np.random.seed(args.seed)
@@ -60,20 +62,31 @@ def main():
     print("load data: {:.3f}s  (N={}, M={}, records={}, nnz={})".format(time.time() - t1, Scount, Rcount, len(Dataset), inter_adj.nnz))
     model = getattr(mg, args.model)(in_features=128, out_features=64, n_classes=Rcount, n_heads=2, dropout=0.5, gdp=GDP,
                                     Scount=Scount, Rcount=Rcount).to(device)                # train.py:206
-    optimizer = optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)  # train.py:207
+    optimizer = optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay,
+                           capturable=args.cuda_graph)                                       # train.py:207
 
+    def train_step(source_index, recipient_index):                                          # train.py:221-232
+        optimizer.zero_grad(set_to_none=True)
+        output = model(inter_adj, city_adj, province_adj, source_index)
+        loss_train = F.nll_loss(output[source_index], recipient_index)                      # train.py:229
+        loss_train.backward()
+        optimizer.step()
+        return loss_train
+
+    captured = None
     for epoch in range(args.epochs):
         t = time.time()
         model.train()
         Loss_train, n = 0.0, 0
         for i, (source_index, recipient_index) in enumerate(train_loader):
             source_index, recipient_index = source_index.to(device), recipient_index.to(device)
-            optimizer.zero_grad()
-            output = model(inter_adj, city_adj, province_adj, source_index)
-            loss_train = F.nll_loss(output[source_index], recipient_index)                  # train.py:229
+            if args.cuda_graph and source_index.numel() == args.batch_size:
+                if captured is None:
+                    captured = mg.CapturedStep(train_step, [source_index, recipient_index])
+                loss_train = captured(source_index, recipient_index)
+            else:
+                loss_train = train_step(source_index, recipient_index)
             Loss_train += loss_train.item()
-            loss_train.backward()
-            optimizer.step()
             n += 1
             if args.max_steps and n >= args.max_steps:
                 break
