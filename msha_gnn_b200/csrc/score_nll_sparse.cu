@@ -45,6 +45,16 @@ __device__ __forceinline__ void flush_label(float4 (&acc)[NV], float& gsum, int 
 }
 
 template <int NV>
+__device__ __forceinline__ void flush_rows(float4 (&acc)[NV], float* __restrict__ row, int lane, int C4) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int c4 = lane + 32 * v;
+        if (c4 < C4) atomicAdd(reinterpret_cast<float4*>(row + 4 * c4), acc[v]);
+        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int NV>
 __global__ void __launch_bounds__(256)
 score_nll_sparse_bwd_kernel(const uint32_t* __restrict__ order, const int64_t* __restrict__ target,
                             const float* __restrict__ gout, const float* __restrict__ out, int64_t ldo,
@@ -64,6 +74,12 @@ score_nll_sparse_bwd_kernel(const uint32_t* __restrict__ order, const int64_t* _
     for (int v = 0; v < NV; ++v) acc[v] = w0[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur = -1;
     float gsum = 0.f;
+    // positives arrive in CSR order (runs of equal src, and the label sort is stable): their dh_i contributions are summed
+    // in registers and scattered once per run
+    float4 run_hi[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) run_hi[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t run_a = -1;
     for (int64_t qb = q0; qb < q1; qb += 32) {
         // batch phase: lane l fetches everything scalar about pair qb + l
         const int64_t q = qb + lane;
@@ -96,6 +112,10 @@ score_nll_sparse_bwd_kernel(const uint32_t* __restrict__ order, const int64_t* _
                 }
             }
             gsum += gj;
+            if (aj != run_a) {
+                if (run_a >= 0) flush_rows<NV>(run_hi, dhi + run_a * C, lane, C4);
+                run_a = aj;
+            }
             const float* xi_row = hi + aj * C;
             const float* xj_row = hj + bj * C;
             float4 xi[NV], xj[NV];
@@ -112,8 +132,10 @@ score_nll_sparse_bwd_kernel(const uint32_t* __restrict__ order, const int64_t* _
                 const int c4 = lane + 32 * v;
                 if (c4 < C4) {
                     const float4 dz = make_float4(gj * w0[v].x, gj * w0[v].y, gj * w0[v].z, gj * w0[v].w);
-                    atomicAdd(reinterpret_cast<float4*>(dhi + aj * C + 4 * c4),
-                              make_float4(dz.x * xj[v].x, dz.y * xj[v].y, dz.z * xj[v].z, dz.w * xj[v].w));
+                    run_hi[v].x = fmaf(dz.x, xj[v].x, run_hi[v].x);
+                    run_hi[v].y = fmaf(dz.y, xj[v].y, run_hi[v].y);
+                    run_hi[v].z = fmaf(dz.z, xj[v].z, run_hi[v].z);
+                    run_hi[v].w = fmaf(dz.w, xj[v].w, run_hi[v].w);
                     atomicAdd(reinterpret_cast<float4*>(dhj + bj * C + 4 * c4),
                               make_float4(dz.x * xi[v].x, dz.y * xi[v].y, dz.z * xi[v].z, dz.w * xi[v].w));
                     acc[v].x = fmaf(gj, xi[v].x * xj[v].x, acc[v].x);
@@ -125,6 +147,7 @@ score_nll_sparse_bwd_kernel(const uint32_t* __restrict__ order, const int64_t* _
         }
     }
     if (cur >= 0) flush_label<NV>(acc, gsum, cur, lane, C, C4, dW0, db0);
+    if (run_a >= 0) flush_rows<NV>(run_hi, dhi + run_a * C, lane, C4);
 }
 
 // keys for the label sort: key = label (clamped into [0, Hd] so that bad labels sort last), value = pair index

@@ -7,6 +7,7 @@ library as raw pointers on the current stream.
 from __future__ import annotations
 
 import os
+import weakref
 
 import torch
 
@@ -629,6 +630,9 @@ class _ScoreMLPNll(torch.autograd.Function):
         call("msha_nll_loss_fwd", ptr(out), ptr(target, torch.int64), P, Hd, loss.data_ptr(), ptr(status, I32),
              ws2.data_ptr(), ws2.numel(), _stream())
         ctx.act, ctx.has_bias = act, b0 is not None
+        ctx.order = None
+        if SPARSE_NLL_BWD and C % 4 == 0 and C <= 1024 and P < (1 << 31) and any(ctx.needs_input_grad):
+            ctx.order = nll_label_order(target, Hd)       # here `target` is still the caller's tensor: the cache can hit
         ctx.save_for_backward(hi, hj, src, dst, W0, out, target)
         ctx.mark_non_differentiable(out)
         ctx.set_materialize_grads(False)      # otherwise autograd zero-fills a (P, Hd) gradient for `out` on every backward
@@ -646,9 +650,9 @@ class _ScoreMLPNll(torch.autograd.Function):
         dW = torch.empty_like(W0)
         db = torch.empty(Hd, dtype=torch.float32, device=out.device)
         gl = _c(gloss.reshape(1).float())
-        if SPARSE_NLL_BWD and C % 4 == 0 and C <= 1024 and P < (1 << 31):
+        if ctx.order is not None:
             # d out is one-hot per row: no GEMM left, only gathers and vector atomics (csrc/score_nll_sparse.cu)
-            order = nll_label_order(target, Hd)
+            order = ctx.order
             call("msha_score_mlp_nll_bwd_sparse", ptr(order, I32), ptr(target, torch.int64), ptr(gl), ptr(out), Hd, ptr(hi),
                  ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C, ptr(W0), Hd, ctx.act, LRELU_SLOPE, ptr(dhi),
                  ptr(dhj), ptr(dW), ptr(db), _stream())
@@ -664,8 +668,25 @@ class _ScoreMLPNll(torch.autograd.Function):
 SPARSE_NLL_BWD = os.environ.get("MSHA_NLL_BWD", "sparse") != "dense"   # "dense": the tensor-core backward (validation / comparison)
 
 
+_order_cache: dict = {}
+
+
 def nll_label_order(target, n_classes):
-    """Pair indices stably sorted by label (uint32 bits in an int32 tensor) -- the traversal order of the sparse backward."""
+    """Pair indices stably sorted by label (uint32 bits in an int32 tensor) -- the traversal order of the sparse backward.
+    Cached per label tensor (data pointer + version + weakref, like the adjacency cache): a training loop that scores a
+    fixed edge set passes the same labels every step."""
+    key = (target.data_ptr(), target._version, target.numel(), int(n_classes))
+    hit = _order_cache.get(key)
+    if hit is not None and hit[0]() is target:
+        return hit[1]
+    order = _nll_label_order(target, n_classes)
+    if len(_order_cache) > 8:
+        _order_cache.clear()
+    _order_cache[key] = (weakref.ref(target), order)
+    return order
+
+
+def _nll_label_order(target, n_classes):
     P = target.numel()
     dev = target.device
     keys = torch.empty((2, P), dtype=torch.int64, device=dev)
