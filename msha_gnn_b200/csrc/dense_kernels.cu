@@ -301,19 +301,43 @@ __global__ void bn_partial_kernel(const float* __restrict__ x, const float* __re
         partial[((int64_t)blockIdx.x * 2 + 1) * C + c] = s2;
     }
 }
+// Second stage of the two column sums: 32 columns per CTA of 8 warps, warp w adds every 8th partial in a fixed order and
+// warp 0 combines the 8 (one thread per column walking all ~300 partials was a 30 us chain of dependent fp64 adds).
+// Returns true in the threads of warp 0 that own a column; s1 / s2 are valid there.
+__device__ __forceinline__ bool bn_column_sums(const double* __restrict__ partial, int nblocks, int C, int& c, double& s1,
+                                               double& s2) {
+    __shared__ double sm[2][8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    c = blockIdx.x * 32 + lane;
+    double a1 = 0.0, a2 = 0.0;
+    if (c < C)
+        for (int b = w; b < nblocks; b += 8) {
+            a1 += partial[((int64_t)b * 2 + 0) * C + c];
+            a2 += partial[((int64_t)b * 2 + 1) * C + c];
+        }
+    sm[0][w][lane] = a1;
+    sm[1][w][lane] = a2;
+    __syncthreads();
+    s1 = s2 = 0.0;
+    if (w != 0 || c >= C) return false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        s1 += sm[0][k][lane];
+        s2 += sm[1][k][lane];
+    }
+    return true;
+}
+
 // training: mean/invstd from batch stats; updates running stats (unbiased var) -- eval: from running stats
+// launch: cdiv(C, 32) CTAs of 256 threads
 __global__ void bn_finalize_kernel(const double* __restrict__ partial, int nblocks, int64_t n, int C, int training,
                                    float momentum, float eps, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ save_mean,
                                    float* __restrict__ save_invstd) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    int c;
+    double s1, s2;
+    if (!bn_column_sums(partial, training ? nblocks : 0, C, c, s1, s2)) return;
     if (training) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int b = 0; b < nblocks; ++b) {
-            s1 += partial[((int64_t)b * 2 + 0) * C + c];
-            s2 += partial[((int64_t)b * 2 + 1) * C + c];
-        }
         const double mean = s1 / (double)n;
         double var = s2 / (double)n - mean * mean;
         if (var < 0.0) var = 0.0;
@@ -357,7 +381,7 @@ MSHA_API int msha_bn_lrelu_fwd(const float* x, int64_t n, int C, const float* ga
         bn_partial_kernel<<<nb, 256, 0, st>>>(x, nullptr, n, C, (double*)ws);
         MSHA_LAUNCH_OK();
     }
-    bn_finalize_kernel<<<(unsigned)msha_cdiv(C, 128), 128, 0, st>>>((const double*)ws, nb, n, C, training, momentum, eps,
+    bn_finalize_kernel<<<(unsigned)msha_cdiv(C, 32), 256, 0, st>>>((const double*)ws, nb, n, C, training, momentum, eps,
                                                                   running_mean, running_var, save_mean, save_invstd);
     MSHA_LAUNCH_OK();
     bn_apply_kernel<<<ew_grid(n * C), 256, 0, st>>>(x, n, C, save_mean, save_invstd, gamma, beta, slope, y);
@@ -379,13 +403,9 @@ __global__ void bn_bwd_prep_kernel(const float* __restrict__ dy, const float* __
 }
 __global__ void bn_bwd_reduce_kernel(const double* __restrict__ partial, int nblocks, int C, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-        s1 += partial[((int64_t)b * 2 + 0) * C + c];
-        s2 += partial[((int64_t)b * 2 + 1) * C + c];
-    }
+    int c;
+    double s1, s2;
+    if (!bn_column_sums(partial, nblocks, C, c, s1, s2)) return;
     dbeta[c] = (float)s1;
     dgamma[c] = (float)s2;
 }
@@ -415,7 +435,7 @@ MSHA_API int msha_bn_lrelu_bwd(const float* dy, const float* y, const float* x, 
     MSHA_LAUNCH_OK();
     bn_partial_kernel<<<nb, 256, 0, st>>>(dx, xhat, n, C, (double*)ws);
     MSHA_LAUNCH_OK();
-    bn_bwd_reduce_kernel<<<(unsigned)msha_cdiv(C, 128), 128, 0, st>>>((const double*)ws, nb, C, dgamma, dbeta);
+    bn_bwd_reduce_kernel<<<(unsigned)msha_cdiv(C, 32), 256, 0, st>>>((const double*)ws, nb, C, dgamma, dbeta);
     MSHA_LAUNCH_OK();
     bn_bwd_apply_kernel<<<ew_grid(n * C), 256, 0, st>>>(dx, xhat, n, C, gamma, save_invstd, dgamma, dbeta, training);
     MSHA_LAUNCH_OK();
@@ -733,11 +753,21 @@ __global__ void act_bwd_colsum_stage1(const float* __restrict__ dy, const float*
     }
 }
 __global__ void colsum_stage2(const double* __restrict__ partial, int nblocks, int C, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    // 32 columns per CTA, 8 warps each summing every 8th partial, fixed order (see colreduce_stage2 in gat_kernels.cu)
+    __shared__ double sm[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
     double acc = 0.0;
-    for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * C + c];
-    out[c] = (float)acc;
+    if (c < C)
+        for (int b = w; b < nblocks; b += 8) acc += partial[(int64_t)b * C + c];
+    sm[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && c < C) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][lane];
+        out[c] = (float)t;
+    }
 }
 MSHA_API size_t msha_act_bwd_colsum_workspace_bytes(int C) { return (size_t)ABC_BLOCKS * C * sizeof(double); }
 MSHA_API int msha_act_bwd_colsum(const float* dy, const float* y, float* g, int64_t n, int C, int act, float slope,
@@ -748,7 +778,7 @@ MSHA_API int msha_act_bwd_colsum(const float* dy, const float* y, float* g, int6
     const int nb = (int)(n < ABC_BLOCKS ? n : ABC_BLOCKS);
     act_bwd_colsum_stage1<<<nb, C >= 256 ? 256 : (C >= 128 ? 128 : 64), 0, st>>>(dy, y, g, n, C, act, slope, (double*)ws);
     MSHA_LAUNCH_OK();
-    colsum_stage2<<<(unsigned)msha_cdiv(C, 128), 128, 0, st>>>((const double*)ws, nb, C, colsum);
+    colsum_stage2<<<(unsigned)msha_cdiv(C, 32), 256, 0, st>>>((const double*)ws, nb, C, colsum);
     MSHA_LAUNCH_OK();
     return 0;
 }

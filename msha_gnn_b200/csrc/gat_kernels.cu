@@ -1035,12 +1035,23 @@ __global__ void colreduce_stage1(const float* __restrict__ x, const float* __res
 }
 __global__ void colreduce_stage2(const double* __restrict__ partial, int nblocks, int C, float* __restrict__ out,
                                  double* __restrict__ out_d) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    // 32 columns per CTA, 8 warps each summing every 8th partial (a single thread per column made this a chain of
+    // ~300 dependent fp64 adds: 32 us for a 600 KB reduction); fixed order -> still deterministic
+    __shared__ double sm[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
     double acc = 0.0;
-    for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * C + c];
-    if (out) out[c] = (float)acc;
-    if (out_d) out_d[c] = acc;
+    if (c < C)
+        for (int b = w; b < nblocks; b += 8) acc += partial[(int64_t)b * C + c];
+    sm[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && c < C) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][lane];
+        if (out) out[c] = (float)t;
+        if (out_d) out_d[c] = t;
+    }
 }
 
 MSHA_API size_t msha_colreduce_workspace_bytes(int C) { return (size_t)COLRED_BLOCKS * C * sizeof(double); }
@@ -1053,7 +1064,7 @@ MSHA_API int msha_colreduce(const float* x, const float* y, const float* s, int6
     int nb = (int)(n < COLRED_BLOCKS ? (n > 0 ? n : 1) : COLRED_BLOCKS);
     colreduce_stage1<<<nb, 256, 0, st>>>(x, y, s, n, C, D, (double*)ws);
     MSHA_LAUNCH_OK();
-    colreduce_stage2<<<(unsigned)msha_cdiv(C, 128), 128, 0, st>>>((const double*)ws, nb, C, out, nullptr);
+    colreduce_stage2<<<(unsigned)msha_cdiv(C, 32), 256, 0, st>>>((const double*)ws, nb, C, out, nullptr);
     MSHA_LAUNCH_OK();
     return 0;
 }
