@@ -53,15 +53,16 @@ class GroupLists:
 
 
 def _as_lists(adj, n_nodes):
-    """dense (N,N) float adjacency / Graph / GroupLists / 1-D group-id vector -> (rowptr, col, row_map, counts_fn)."""
+    """dense (N,N) float adjacency / Graph / GroupLists / 1-D group-id vector -> (rowptr, col, row_map, counts_fn, nonempty);
+    ``nonempty``: every node is known to have at least one list member (a group always contains the node itself)."""
     if isinstance(adj, GroupLists):
-        return adj.rowptr, adj.col, adj.row_map, adj.counts
+        return adj.rowptr, adj.col, adj.row_map, adj.counts, True
     if isinstance(adj, torch.Tensor) and adj.dim() == 1:
         gl = _group_cache(adj)
-        return gl.rowptr, gl.col, gl.row_map, gl.counts
+        return gl.rowptr, gl.col, gl.row_map, gl.counts, True
     g = as_graph(adj, n_rows=n_nodes, n_cols=n_nodes)
     deg = g.degrees.to(torch.float32)
-    return g.rowptr, g.col, None, (lambda src: deg[src])
+    return g.rowptr, g.col, None, (lambda src: deg[src]), False
 
 
 _gl_cache: dict = {}
@@ -149,8 +150,8 @@ def intra_scales(layers, graph: Graph, h2, alpha, city_adj, province_adj, source
     t3, t4 = Fn.node_scores(h2b, a3, a4, H, d)
     t3 = torch.nn.functional.leaky_relu(t3, 0.2)
     t4 = torch.nn.functional.leaky_relu(t4, 0.2)
-    rp3, col3, map3, cnt3 = _as_lists(city_adj, N)
-    rp4, col4, map4, cnt4 = _as_lists(province_adj, N)
+    rp3, col3, map3, cnt3, full3 = _as_lists(city_adj, N)
+    rp4, col4, map4, cnt4, full4 = _as_lists(province_adj, N)
     n3 = cnt3(src).view(B, 1)
     n4 = cnt4(src).view(B, 1)
     if joint:
@@ -161,7 +162,9 @@ def intra_scales(layers, graph: Graph, h2, alpha, city_adj, province_adj, source
         c3 = torch.exp(t3) / total                                                          # Ours.py:87
         c4 = torch.exp(t4) / total                                                          # Ours.py:89
     else:
-        if bool((n3 == 0).any()) or bool((n4 == 0).any()):
+        # dense / Graph adjacencies may hold empty rows: one host read to refuse them (group-id vectors cannot, and skip
+        # the read -- which also keeps the step capturable into a CUDA graph)
+        if not (full3 and full4) and (bool((n3 == 0).any()) or bool((n4 == 0).any())):
             raise RuntimeError("OursLayer2: a batch row without city/province neighbours is not supported")
         # softmax of a row-constant logit: uniform over the list, zero gradient w.r.t. a3/a4 (Ablation.py:194-197)
         c3 = (1.0 / n3).expand(B, H).contiguous()

@@ -1,6 +1,6 @@
 """Loader adapter: the host-side parse of the reference's on-disk files, pinned against the dense
 matrices the reference's own ``HigherDataset.intra_adjacent`` / ``inter_adjacent`` produced (tests/golden/dataset.npz,
-oracle/make_golden.py:case_dataset).  CPU only; the device graph build on top of it is in test_gpu_data.py."""
+oracle/make_golden.py:case_dataset).  CPU only; the device graph build on top of it is in test_gpu_widen.py."""
 import json
 import os
 
@@ -91,3 +91,24 @@ def test_real_2015_files():
     city_nnz = int((np.bincount(ff.city).astype(np.int64) ** 2).sum())
     prov_nnz = int((np.bincount(ff.province).astype(np.int64) ** 2).sum())
     assert abs(city_nnz - 8.93e6) < 0.01e6 and abs(prov_nnz - 83.3e6) < 0.1e6
+
+
+def test_synthetic_flow_generator_is_2015_shaped():
+    """bench.flow_graph (the generator behind the flow / yearly workloads and tools/train_flow.py --synthetic): every source has
+    k distinct recipients (no duplicate edge before the repeated records are appended), nnz ~ 2.33 N like the real 2015 files
+    (91 283 for N = 39 179), the requested record count, every recipient used."""
+    import bench
+    src, dst, city, prov = bench.flow_graph()
+    assert src.size == 233887 and src.dtype == np.int64
+    key = src * 32 + dst
+    nnz = np.unique(key).size
+    assert abs(nnz - 91283) < 0.02 * 91283
+    k = np.bincount(np.unique(key) // 32, minlength=39179)
+    assert k.min() >= 1 and k.max() <= 30 and abs(k.mean() - 2.33) < 0.05
+    assert np.bincount(dst, minlength=32).min() > 0
+    assert city.size == prov.size == 39179 and np.array_equal(prov, city % 25)
+    s2, d2, _, _ = bench.flow_graph()
+    assert np.array_equal(src, s2) and np.array_equal(dst, d2)          # deterministic
+    # the files written from it parse back to the same records
+    rowptr, col, val = O.csr_from_coo(src, dst, 39179, 32)
+    assert col.size == nnz and float(val.sum()) == 233887.0
