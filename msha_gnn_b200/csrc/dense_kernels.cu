@@ -654,10 +654,22 @@ __global__ void nll_fwd_stage1(const float* __restrict__ logp, const int64_t* __
                                double* __restrict__ partial, int32_t* __restrict__ status) {
     __shared__ double sm[8];
     double acc = 0.0;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t t = target[p];
-        if (t < 0 || t >= C) { atomicOr(status, 1); continue; }
-        acc += (double)logp[p * C + t];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // four pairs per iteration: the picked scores are one scattered 32 B sector each, so the labels and then the scores of
+    // four pairs are requested together instead of one dependent load pair at a time
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += 4 * stride) {
+        int64_t t[4];
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = p + k * stride < P ? target[p + k * stride] : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t pk = p + k * stride;
+            const bool in_range = t[k] >= 0 && t[k] < C;
+            v[k] = (pk < P && in_range) ? logp[pk * C + t[k]] : 0.f;
+            if (pk < P && !in_range) atomicOr(status, 1);
+        }
+        acc += ((double)v[0] + (double)v[1]) + ((double)v[2] + (double)v[3]);
     }
     acc = warp_sum_d(acc);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;

@@ -77,7 +77,7 @@ def test_captured_dropout_draws_fresh_masks_per_replay():
         step(torch.rand(n + 1, device=DEV))
 
 
-@pytest.mark.parametrize("name,cls", [("ablation3", "ablation3"), ("ours", "Ours")])
+@pytest.mark.parametrize("name,cls", [("ablation3", "ablation3"), ("ablation2", "ablation2"), ("ours", "Ours")])
 def test_captured_training_step_matches_eager(name, cls):
     """train.py:217-232 as one graph launch: same losses and parameters as the eager loop (dropout 0)."""
     g = load_golden(name)
