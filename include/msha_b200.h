@@ -208,9 +208,11 @@ int msha_score_mlp_nll_bwd_sparse(const uint32_t* order, const int64_t* target, 
                                   int64_t ldo, const float* hi_tab, const float* hj_tab, const int64_t* src,
                                   const int64_t* dst, int64_t P, int64_t C, const float* W0, int64_t Hd, int act,
                                   float slope, float* dhi, float* dhj, float* dW0, float* db0, void* stream);
-/* keys, keys_tmp: uint64[P]; order, order_tmp: uint32[P]; ws: msha_radix_sort_workspace_bytes(P) */
-int msha_score_nll_label_order(const int64_t* target, int64_t P, int64_t Hd, uint64_t* keys, uint64_t* keys_tmp,
-                               uint32_t* order, uint32_t* order_tmp, void* ws, size_t ws_bytes, void* stream);
+/* Stable pair order by label, and by source row inside a label when src != NULL (rows of hi_tab, n_src of them).
+ * keys, keys_tmp: uint64[P]; order, order_tmp: uint32[P]; ws: msha_radix_sort_workspace_bytes(P) */
+int msha_score_nll_label_order(const int64_t* target, const int64_t* src, int64_t P, int64_t Hd, int64_t n_src,
+                               uint64_t* keys, uint64_t* keys_tmp, uint32_t* order, uint32_t* order_tmp, void* ws,
+                               size_t ws_bytes, void* stream);
 /* builder-defined sampler (the reference's --ns_rate flags are dead code, LLP.py:26-29) */
 int msha_negative_sample(uint64_t seed, int64_t P, int64_t n_src, int64_t n_dst, int64_t* src, int64_t* dst,
                          void* stream);

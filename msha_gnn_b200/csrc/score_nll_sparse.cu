@@ -150,13 +150,20 @@ score_nll_sparse_bwd_kernel(const uint32_t* __restrict__ order, const int64_t* _
     if (run_a >= 0) flush_rows<NV>(run_hi, dhi + run_a * C, lane, C4);
 }
 
-// keys for the label sort: key = label (clamped into [0, Hd] so that bad labels sort last), value = pair index
-__global__ void label_keys_kernel(const int64_t* __restrict__ target, int64_t P, int Hd, uint64_t* __restrict__ keys,
-                                  uint32_t* __restrict__ vals) {
+// keys for the pair sort: key = label (clamped into [0, Hd] so that bad labels sort last), optionally refined by the
+// source row (key = label << sbits | src) so that equal sources become neighbours inside a label; value = pair index
+__global__ void label_keys_kernel(const int64_t* __restrict__ target, const int64_t* __restrict__ src, int64_t P, int Hd,
+                                  int64_t n_src, int sbits, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     const int64_t t = target[p];
-    keys[p] = (t >= 0 && t < Hd) ? (uint64_t)t : (uint64_t)Hd;
+    uint64_t k = (t >= 0 && t < Hd) ? (uint64_t)t : (uint64_t)Hd;
+    if (src) {
+        int64_t a = src[p];
+        a = a < 0 ? 0 : (a >= n_src ? n_src - 1 : a);
+        k = (k << sbits) | (uint64_t)a;
+    }
+    keys[p] = k;
     vals[p] = (uint32_t)p;
 }
 
@@ -200,19 +207,26 @@ MSHA_API int msha_score_mlp_nll_bwd_sparse(const uint32_t* order, const int64_t*
     return 0;
 }
 
-// Stable order of the pairs by label for the kernel above: fills keys / vals and sorts them with the library's LSD radix
-// sort (one 8-bit pass per 8 bits of Hd).  keys, keys_tmp: uint64[P]; order, order_tmp: uint32[P]; ws from
-// msha_radix_sort_workspace_bytes(P).  The sorted pair indices end up in `order`.
+// Stable order of the pairs for the kernel above: by label, and inside a label by source row when `src` is given (then the
+// dh_i contributions of a source are summed in registers and scattered once per run, and its h_i row stays in L1).  Fills
+// keys / order and sorts them with the library's LSD radix sort (one 8-bit pass per 8 key bits).  keys, keys_tmp:
+// uint64[P]; order, order_tmp: uint32[P]; ws from msha_radix_sort_workspace_bytes(P).  The result ends up in `order`.
 MSHA_API int msha_radix_sort_u64(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, int64_t n,
                                  int begin_bit, int end_bit, void* ws, size_t ws_bytes, void* stream);   // graph_build.cu
-MSHA_API int msha_score_nll_label_order(const int64_t* target, int64_t P, int64_t Hd, uint64_t* keys, uint64_t* keys_tmp,
-                                        uint32_t* order, uint32_t* order_tmp, void* ws, size_t ws_bytes, void* stream) {
+MSHA_API int msha_score_nll_label_order(const int64_t* target, const int64_t* src, int64_t P, int64_t Hd, int64_t n_src,
+                                        uint64_t* keys, uint64_t* keys_tmp, uint32_t* order, uint32_t* order_tmp, void* ws,
+                                        size_t ws_bytes, void* stream) {
     MSHA_REQUIRE(P >= 0 && P < ((int64_t)1 << 32) && Hd >= 1 && Hd < ((int64_t)1 << 31), "score_nll_label_order: bad shape");
+    MSHA_REQUIRE(src == nullptr || (n_src >= 1 && n_src < ((int64_t)1 << 31)), "score_nll_label_order: bad n_src");
     if (P == 0) return 0;
-    label_keys_kernel<<<(unsigned)msha_cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(target, P, (int)Hd, keys, order);
+    int lbits = 1;
+    while (((int64_t)1 << lbits) <= Hd) ++lbits;          // labels lie in [0, Hd]
+    int sbits = 0;
+    if (src)
+        while (((int64_t)1 << sbits) < n_src) ++sbits;
+    label_keys_kernel<<<(unsigned)msha_cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(target, src, P, (int)Hd, n_src, sbits, keys,
+                                                                                  order);
     MSHA_LAUNCH_OK();
-    int bits = 1;
-    while (((int64_t)1 << bits) <= Hd) ++bits;            // labels lie in [0, Hd]
-    const int end_bit = ((bits + 7) / 8) * 8;
+    const int end_bit = ((lbits + sbits + 7) / 8) * 8;
     return msha_radix_sort_u64(keys, keys_tmp, order, order_tmp, P, 0, end_bit, ws, ws_bytes, stream);
 }

@@ -632,7 +632,10 @@ class _ScoreMLPNll(torch.autograd.Function):
         ctx.act, ctx.has_bias = act, b0 is not None
         ctx.order = None
         if SPARSE_NLL_BWD and C % 4 == 0 and C <= 1024 and P < (1 << 31) and any(ctx.needs_input_grad):
-            ctx.order = nll_label_order(target, Hd)       # here `target` is still the caller's tensor: the cache can hit
+            if NLL_ORDER_BY_SRC and src is not None:
+                ctx.order = nll_label_order(target, Hd, src, hi.shape[0])   # per call: the sources change with the batch
+            else:
+                ctx.order = nll_label_order(target, Hd)   # here `target` is still the caller's tensor: the cache can hit
         ctx.save_for_backward(hi, hj, src, dst, W0, out, target)
         ctx.mark_non_differentiable(out)
         ctx.set_materialize_grads(False)      # otherwise autograd zero-fills a (P, Hd) gradient for `out` on every backward
@@ -665,16 +668,20 @@ class _ScoreMLPNll(torch.autograd.Function):
         return dhi, dhj, None, None, dW, (db if ctx.has_bias else None), None, None
 
 
+NLL_ORDER_BY_SRC = os.environ.get("MSHA_NLL_ORDER", "label") == "src"   # sort the pairs of a label by source row as well
 SPARSE_NLL_BWD = os.environ.get("MSHA_NLL_BWD", "sparse") != "dense"   # "dense": the tensor-core backward (validation / comparison)
 
 
 _order_cache: dict = {}
 
 
-def nll_label_order(target, n_classes):
+def nll_label_order(target, n_classes, src=None, n_src=0):
     """Pair indices stably sorted by label (uint32 bits in an int32 tensor) -- the traversal order of the sparse backward.
-    Cached per label tensor (data pointer + version + weakref, like the adjacency cache): a training loop that scores a
-    fixed edge set passes the same labels every step."""
+    With ``src`` the pairs of a label are further ordered by source row.  The label-only order is cached per label tensor
+    (data pointer + version + weakref, like the adjacency cache): a training loop that scores a fixed edge set passes the
+    same labels every step."""
+    if src is not None:
+        return _nll_label_order(target, n_classes, src, n_src)
     key = (target.data_ptr(), target._version, target.numel(), int(n_classes))
     hit = _order_cache.get(key)
     if hit is not None and hit[0]() is target:
@@ -686,15 +693,15 @@ def nll_label_order(target, n_classes):
     return order
 
 
-def _nll_label_order(target, n_classes):
+def _nll_label_order(target, n_classes, src=None, n_src=0):
     P = target.numel()
     dev = target.device
     keys = torch.empty((2, P), dtype=torch.int64, device=dev)
     order = torch.empty((2, P), dtype=I32, device=dev)
     lib = ops._lib.lib()
     ws = workspace(lib.msha_radix_sort_workspace_bytes(P), dev)
-    call("msha_score_nll_label_order", ptr(target, torch.int64), P, n_classes, keys[0].data_ptr(), keys[1].data_ptr(),
-         order[0].data_ptr(), order[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    call("msha_score_nll_label_order", ptr(target, torch.int64), ptr(src, torch.int64), P, n_classes, n_src,
+         keys[0].data_ptr(), keys[1].data_ptr(), order[0].data_ptr(), order[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     return order[0]
 
 

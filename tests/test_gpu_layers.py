@@ -423,15 +423,16 @@ def test_sparse_nll_backward_matches_dense_and_oracle(P, C, Hd, Nn, labels, monk
         tgt[::7] = Hd + 3                                  # out of range: contributes nothing to any gradient
         tgt[3::11] = -1
     grads = {}
-    for mode in ("sparse", "dense"):
-        monkeypatch.setattr(Fn, "SPARSE_NLL_BWD", mode == "sparse")
+    for mode in ("sparse", "sparse_by_src", "dense"):
+        monkeypatch.setattr(Fn, "SPARSE_NLL_BWD", mode != "dense")
+        monkeypatch.setattr(Fn, "NLL_ORDER_BY_SRC", mode == "sparse_by_src")
         lp.zero_grad(set_to_none=True)
         hd = h.clone().to(DEV).requires_grad_(True)
         loss = 2.0 * lp.nll_loss_pairs(hd, hd, src.to(DEV), dst.to(DEV), tgt.to(DEV))
         loss.backward()
         grads[mode] = [_np(hd.grad), _np(lp.lins[0].weight.grad), _np(lp.lins[0].bias.grad)]
-    for a, b in zip(grads["sparse"], grads["dense"]):
-        assert rel_err(a, b) < 2e-5
+    for a, b, c in zip(grads["sparse"], grads["dense"], grads["sparse_by_src"]):
+        assert rel_err(a, b) < 2e-5 and rel_err(c, b) < 2e-5
     # oracle (fp64): autograd through the restated scorer + read-out; bad labels masked out of the mean's numerator
     ho = torch.tensor(h.numpy(), dtype=torch.float64, requires_grad=True)
     W = [torch.tensor(_np(l.weight), dtype=torch.float64, requires_grad=True) for l in lp.lins]
@@ -466,6 +467,9 @@ def test_sparse_nll_backward_identity_order():
              ptr(db), _stream())
         res.append([_np(dhi), _np(dhj), _np(dW), _np(db)])
     assert np.array_equal(_np(Fn.nll_label_order(tgt, Hd)), np.arange(P))      # stable sort of sorted labels
+    by_src = _np(Fn.nll_label_order(tgt, Hd, src, Nn)).astype(np.int64)          # (label, src, original position) order
+    want_order = np.lexsort((np.arange(P), _np(src), _np(tgt)))
+    assert np.array_equal(by_src, want_order)
     for a, b in zip(*res):
         assert rel_err(a, b) < 1e-5
     # closed form of db0: sum of g_p per label
