@@ -320,12 +320,24 @@ def run_ours(args):
     l0 = lib.msha_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    trace = [] if os.environ.get("MSHA_BENCH_TRACE") else None
     for it in range(args.steps):
+        t0 = time.perf_counter()
         loss = step(args.warmup + it, pos_dev)
+        if trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            trace.append((time.perf_counter() - t0, e))
     ev1.record()
     barrier()
     launches = lib.msha_launch_count() - l0
     ms_dev = ev0.elapsed_time(ev1) / args.steps
+    if trace is not None and rank == 0:
+        prev, gpu = ev0, []
+        for _, e in trace:
+            gpu.append(round(prev.elapsed_time(e), 2))
+            prev = e
+        print("dev loop trace: host enqueue ms/step", [round(t * 1e3, 2) for t, _ in trace], "gpu ms/step", gpu, file=sys.stderr)
     # ---- end-to-end timing: pinned host batch -> device every step, loss back to the host
     # The pinned batch of step i+1 is copied on a second stream while step i computes (two device buffers, an event per
     # buffer) -- every step's host->device copy and its loss read-back stay inside the timed region.
