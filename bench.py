@@ -894,6 +894,19 @@ def cpu_baseline(args, wl, rows, cols):
             "ms_per_step_est": t_step * 1e3}
 
 
+def reference_workload_name(name, wl, rows, cols):
+    """The GPU arm's config.workload string (run_ours) rebuilt from the host-side graph: same workload, same wording."""
+    n = wl["n_nodes"]
+    if rows.size <= 20_000_000:
+        E = int(np.unique(rows.astype(np.int64) * n + cols.astype(np.int64)).size)      # Graph.from_coo coalesces duplicates
+    else:
+        E = int(rows.size)                                                             # not coalesced here (a 100 M-key sort)
+    n_pos = wl["pos_pairs"] or E
+    return (f"{name}: {n} nodes, {E} directed edges ({wl['graph']}), F={wl['feat']}, {wl['layers']}-layer {wl['heads']}-head "
+            f"GAT C={wl['hidden']} + LinkPredictor(mlp,{wl['hidden']},{wl['pred_hidden']}) over P={2 * n_pos} pairs "
+            "(positives + as many Philox negatives), nll loss, Adam")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -911,7 +924,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "gat_fwd_bwd_layer_edges_per_sec", "value": best["value"], "unit": "edges/s",
            "n_gpus": world, "steps": n, "warmup": min(args.warmup, 1), "ms_per_step": best["ms_per_step_est"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.workload} (same graph/model shapes as the GPU arm)"},
+           "config": {"workload": reference_workload_name(args.workload, wl, rows, cols),
+                      "per_gpu": "CPU arm: oracle port on the host cores (rank 0 only), bounded sample -- see cpu_baseline.sample"},
            "cpu_baseline": best,
            "e2e": {"value": best["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
