@@ -843,7 +843,8 @@ def _index(idx):
 
 def kd_cosine(s, t, idx_s=None, idx_t=None, eps=1e-8):
     """``KD_cosine`` (LLP.py:34-35): ``1 - cosine_similarity(s[idx_s], t[idx_t].detach(), dim=-1).mean()``; the teacher
-    operand is detached like the reference's."""
+    operand is detached like the reference's.  Indices must lie inside the tables: torch's indexing would trip a device
+    assert, this kernel (which never synchronises) lets such a pair contribute cos = 0 and sets its status word."""
     return _KDCosine.apply(s, t.detach(), _index(idx_s), _index(idx_t), float(eps))
 
 
