@@ -327,17 +327,20 @@ def run_ours(args):
         if trace is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
-            trace.append((time.perf_counter() - t0, e))
+            import gc
+            trace.append((time.perf_counter() - t0, e, torch.cuda.memory_reserved() >> 20,
+                          sum(g["collections"] for g in gc.get_stats())))
     ev1.record()
     barrier()
     launches = lib.msha_launch_count() - l0
     ms_dev = ev0.elapsed_time(ev1) / args.steps
     if trace is not None and rank == 0:
         prev, gpu = ev0, []
-        for _, e in trace:
-            gpu.append(round(prev.elapsed_time(e), 2))
-            prev = e
-        print("dev loop trace: host enqueue ms/step", [round(t * 1e3, 2) for t, _ in trace], "gpu ms/step", gpu, file=sys.stderr)
+        for rec in trace:
+            gpu.append(round(prev.elapsed_time(rec[1]), 2))
+            prev = rec[1]
+        print("dev loop trace: host enqueue ms/step", [round(r[0] * 1e3, 2) for r in trace], "gpu ms/step", gpu,
+              "reserved MiB", [r[2] for r in trace], "gc collections so far", [r[3] for r in trace], file=sys.stderr)
     # ---- end-to-end timing: pinned host batch -> device every step, loss back to the host
     # The pinned batch of step i+1 is copied on a second stream while step i computes (two device buffers, an event per
     # buffer) -- every step's host->device copy and its loss read-back stay inside the timed region.

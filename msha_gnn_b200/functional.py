@@ -656,6 +656,7 @@ class _ScoreMLPNll(torch.autograd.Function):
         if ctx.order is not None:
             # d out is one-hot per row: no GEMM left, only gathers and vector atomics (csrc/score_nll_sparse.cu)
             order = ctx.order
+            ctx.order = None          # the node outlives its backward while the caller holds the loss: release the buffer now
             call("msha_score_mlp_nll_bwd_sparse", ptr(order, I32), ptr(target, torch.int64), ptr(gl), ptr(out), Hd, ptr(hi),
                  ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C, ptr(W0), Hd, ctx.act, LRELU_SLOPE, ptr(dhi),
                  ptr(dhj), ptr(dW), ptr(db), _stream())
