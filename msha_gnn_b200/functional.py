@@ -630,10 +630,11 @@ class _ScoreMLPNll(torch.autograd.Function):
         call("msha_nll_loss_fwd", ptr(out), ptr(target, torch.int64), P, Hd, loss.data_ptr(), ptr(status, I32),
              ws2.data_ptr(), ws2.numel(), _stream())
         ctx.act, ctx.has_bias = act, b0 is not None
-        ctx.order = None
+        ctx.order, ctx.order_owned = None, False
         if SPARSE_NLL_BWD and C % 4 == 0 and C <= 1024 and P < (1 << 31) and any(ctx.needs_input_grad):
             if NLL_ORDER_BY_SRC and src is not None:
                 ctx.order = nll_label_order(target, Hd, src, hi.shape[0])   # per call: the sources change with the batch
+                ctx.order_owned = True
             else:
                 ctx.order = nll_label_order(target, Hd)   # here `target` is still the caller's tensor: the cache can hit
         ctx.save_for_backward(hi, hj, src, dst, W0, out, target)
@@ -656,7 +657,9 @@ class _ScoreMLPNll(torch.autograd.Function):
         if ctx.order is not None:
             # d out is one-hot per row: no GEMM left, only gathers and vector atomics (csrc/score_nll_sparse.cu)
             order = ctx.order
-            ctx.order = None          # the node outlives its backward while the caller holds the loss: release the buffer now
+            if ctx.order_owned:
+                ctx.order = None      # per-call buffer: the node outlives its backward while the caller holds the loss
+                                      # (a second backward through a retained graph takes the tensor-core path below)
             call("msha_score_mlp_nll_bwd_sparse", ptr(order, I32), ptr(target, torch.int64), ptr(gl), ptr(out), Hd, ptr(hi),
                  ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C, ptr(W0), Hd, ctx.act, LRELU_SLOPE, ptr(dhi),
                  ptr(dhj), ptr(dW), ptr(db), _stream())
