@@ -102,3 +102,28 @@ def test_gat_and_linkpredictor_state_dict():
     gc = mg.GraphConvolution(10, 5)
     for k, v in gc.state_dict().items():
         np.testing.assert_allclose(v.numpy(), params_of(g)[k], rtol=0, atol=1e-7, err_msg=k)
+
+
+def test_integration_doc_binding_matches_header():
+    """The ctypes stub shown in INTEGRATION.md binds msha_gat_fwd with as many arguments as the header declares."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "INTEGRATION.md")) as f:
+        doc = f.read()
+    m = re.search(r"lib\.msha_gat_fwd\.argtypes = \[(.*?)\]\s*#", doc, flags=re.S)
+    assert m, "INTEGRATION.md no longer shows the msha_gat_fwd binding"
+    shown = re.findall(r"ctypes\.c_\w+", m.group(1))
+    args = {n: a for n, _, a in _lib.parse_header()}["msha_gat_fwd"]
+    assert len(shown) == len(args), (len(shown), len(args))
+    want = {"int": "c_int", "float": "c_float", "int64_t": "c_int64", "uint64_t": "c_uint64"}
+    for doc_t, (c_t, name) in zip(shown, args):
+        c_t = c_t.replace("const", "").strip()
+        expect = "c_void_p" if c_t.endswith("*") else want[c_t]
+        assert doc_t == "ctypes." + expect, (name, doc_t, c_t)
+    call = re.search(r"rc = lib\.msha_gat_fwd\((.*?)\)\nif rc", doc, flags=re.S).group(1)
+    depth, n_args = 0, 1
+    for ch in call:
+        depth += ch in "([" 
+        depth -= ch in ")]"
+        n_args += ch == "," and depth == 0
+    assert n_args == len(args)

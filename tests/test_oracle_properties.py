@@ -1,0 +1,69 @@
+"""Property tests (hypothesis) of the integer part of the oracle -- the CSR / CSC build that the device graph build has to
+match bit for bit -- against scipy's coalescing COO -> CSR conversion and torch's sparse tensors.  CPU only."""
+import numpy as np
+import scipy.sparse as sp
+import torch
+from hypothesis import given, settings, strategies as st
+
+from oracle import msha_oracle as O
+
+
+@st.composite
+def coo(draw):
+    n_rows = draw(st.integers(1, 40))
+    n_cols = draw(st.integers(1, 12))
+    n = draw(st.integers(0, 300))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, n_rows, n), rng.integers(0, n_cols, n), n_rows, n_cols
+
+
+@settings(max_examples=60, deadline=None)
+@given(coo())
+def test_csr_from_coo_equals_scipy_coalesce(c):
+    src, dst, n_rows, n_cols = c
+    rowptr, col, val = O.csr_from_coo(src, dst, n_rows, n_cols)
+    m = sp.coo_matrix((np.ones(src.size, dtype=np.float32), (src, dst)), shape=(n_rows, n_cols)).tocsr()
+    m.sum_duplicates()
+    m.sort_indices()
+    assert np.array_equal(rowptr, m.indptr) and np.array_equal(col, m.indices) and np.array_equal(val, m.data)
+    assert rowptr.dtype == np.int32 and col.dtype == np.int32 and val.dtype == np.float32
+    assert float(val.sum()) == float(src.size)                       # multiplicities, dataset.py:286-288
+
+
+@settings(max_examples=60, deadline=None)
+@given(coo())
+def test_csc_is_the_transpose_and_perm_maps_slots(c):
+    src, dst, n_rows, n_cols = c
+    rowptr, col, val = O.csr_from_coo(src, dst, n_rows, n_cols)
+    colptr, rowidx, perm = O.csc_from_csr(rowptr, col, n_cols)
+    t = sp.csr_matrix((val, col, rowptr), shape=(n_rows, n_cols)).tocsc()
+    t.sort_indices()
+    assert np.array_equal(colptr, t.indptr) and np.array_equal(rowidx, t.indices)
+    assert np.array_equal(val[perm], t.data)                         # perm: CSC slot -> CSR slot
+    assert np.array_equal(np.sort(perm), np.arange(col.size))        # a permutation
+    rows_of = np.repeat(np.arange(n_rows), np.diff(rowptr))
+    assert np.array_equal(rows_of[perm], rowidx)
+    for j in range(n_cols):                                          # rows ascend inside a column
+        seg = rowidx[colptr[j]:colptr[j + 1]]
+        assert np.all(np.diff(seg) > 0)
+
+
+@settings(max_examples=40, deadline=None)
+@given(coo())
+def test_csr_from_dense_equals_torch_nonzero_and_attention_edges(c):
+    src, dst, n_rows, n_cols = c
+    dense = np.zeros((n_rows, n_cols), dtype=np.float32)
+    np.add.at(dense, (src, dst), 1.0)
+    rowptr, col, val = O.csr_from_dense(dense)
+    nz = torch.nonzero(torch.from_numpy(dense) > 0)                  # the reference's mask `adj > 0` (GAT.py:30)
+    assert np.array_equal(col, nz[:, 1].numpy()) and np.array_equal(np.repeat(np.arange(n_rows), np.diff(rowptr)), nz[:, 0].numpy())
+    r, cc, masked = O.attention_edges(rowptr, col, n_cols)
+    deg = np.diff(rowptr)
+    n_iso = int((deg == 0).sum())
+    assert r.numel() == col.size + n_iso * n_cols                    # rows without neighbours attend to all M columns
+    assert int(masked.sum()) == n_iso * n_cols
+    vals = O.normalize_csr_values(val, col, n_cols)
+    colsum = dense.sum(axis=0)
+    want = (dense / np.where(colsum > 0, colsum, 1.0))[dense > 0]
+    np.testing.assert_allclose(vals, want, rtol=2e-6)
