@@ -1,5 +1,7 @@
 """Pins oracle/msha_oracle.py (the CPU restatement) to the golden vectors produced by the
 unmodified reference classes (oracle/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -382,3 +384,19 @@ def test_explainer_argmax():
     dense = np.array([[0.2, 0.5, 0.5, 0.0], [0.0, 0.0, 0.0, 0.0], [0.1, 0.0, 0.0, 0.9]], dtype=np.float32)
     assert O.explainer_argmax(dense) == [[1, 2], [0, 1, 2, 3], [3]]
     assert O.explainer_argmax(dense.T) == [[0], [0], [0], [2]]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_committed_goldens_regenerate_bit_for_bit(tmp_path, monkeypatch):
+    """tests/golden/*.npz are exactly what oracle/make_golden.py produces from the unmodified reference classes today."""
+    from oracle import make_golden as mgold
+    committed = mgold.OUT
+    monkeypatch.setattr(mgold, "OUT", str(tmp_path))
+    mgold.main()
+    names = sorted(f for f in os.listdir(committed) if f.endswith(".npz"))
+    assert names == sorted(os.listdir(tmp_path)) and len(names) == 26
+    for f in names:
+        with np.load(os.path.join(committed, f)) as a, np.load(os.path.join(tmp_path, f)) as b:
+            assert set(a.files) == set(b.files), f
+            for k in a.files:
+                assert np.array_equal(a[k], b[k], equal_nan=True), (f, k)
