@@ -127,3 +127,15 @@ def test_integration_doc_binding_matches_header():
         depth -= ch in ")]"
         n_args += ch == "," and depth == 0
     assert n_args == len(args)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU / eager fallback: with the shared library absent every op entry point raises with build instructions."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libmsha_b200.so"))
+    with pytest.raises(RuntimeError, match="not built"):
+        _lib.lib()
+    from msha_gnn_b200 import ops
+    monkeypatch.setattr(ops, "_fn_cache", {})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.call("msha_abi_version")
