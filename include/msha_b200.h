@@ -87,6 +87,18 @@ int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_rows, cons
                  const float* feat, int H, int D, float slope, const float* alpha_in, float* alpha_out, float* out,
                  int act, float* lse_out, float drop_p, uint64_t drop_seed, const msha_hub_t* hub, float* hub_scratch,
                  void* stream);
+/* Partitioned forward (no reference counterpart, train.py:18 is single-device): the same arithmetic as
+ * msha_gat_fwd split into (1) the row log-sum-exp of the logits, which needs only the H scores per node, and (2) one
+ * aggregation pass per owner block of columns -- edges [rowbeg[i], rowend[i]) of row i -- so that a block is consumed as
+ * soon as its feature rows have arrived from the owning GPU.  alpha = exp(logit - lse) is final in every block.
+ * H a power of two <= 32, D % 4 == 0.  hub_scratch of the stats call: float[2 * H * hub->n_segs]. */
+int msha_gat_softmax_stats(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
+                           const float* s_self, int H, float slope, float* lse, const msha_hub_t* hub,
+                           float* hub_scratch, void* stream);
+int msha_gat_fwd_block(const int32_t* rowbeg, const int32_t* rowend, const int32_t* col, int64_t n_rows,
+                       const float* s_nbr, const float* s_self, const float* lse, const float* feat, int H, int D,
+                       float slope, float* alpha_out, float* out, int accumulate, float drop_p, uint64_t drop_seed,
+                       const msha_hub_t* hub, void* stream);
 /* backward row pass (autograd of the lines above): d alpha, softmax and LeakyReLU backward, d s_self */
 int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
                       const float* s_self, float slope, const float* alpha, const float* feat, const float* dout,
@@ -223,6 +235,26 @@ int msha_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uin
  * state (the one piece of global state besides the descriptor caches); epoch 0 is the default and changes nothing. */
 int msha_dropout_epoch_set(uint64_t epoch, void* stream);
 int msha_dropout_epoch_advance(uint64_t by, void* stream);
+
+/* ==== multi-GPU exchange over peer-mapped memory (the halo all-gather of boundary features and the
+ * reduce-scatter of their gradients; the reference is single-device, train.py:18).  Buffers are allocated by the caller in
+ * memory every rank of the node has mapped (NVLink peer access); *_tab arguments are DEVICE arrays uint64[world] holding,
+ * per rank, the address of that rank's buffer as mapped in the calling process. ==== */
+/* flags: uint32[n_channels][world] per rank.  signal: flags_of_peer_q[channel][rank] = value (+ *epoch) for every q in
+ * peer_mask, released at system scope after all earlier work of the stream.  wait: until flags[channel][q] >= value
+ * (+ *epoch) for every q in peer_mask; traps after timeout_ns (0 = never) with 0x100|q in *status. */
+int msha_peer_signal(const uint64_t* flag_tab, int world, int rank, int channel, uint32_t peer_mask,
+                     const uint32_t* epoch, uint32_t value, void* stream);
+int msha_peer_wait(const uint32_t* flags, int world, int channel, uint32_t peer_mask, const uint32_t* epoch,
+                   uint32_t value, uint64_t timeout_ns, int32_t* status, void* stream);
+/* gathered layout [world][block_bytes]: copy the first nbytes of every remote rank's block out of that rank's buffer */
+int msha_peer_pull_blocks(void* dst, const uint64_t* src_tab, int world, int rank, int64_t block_bytes, int64_t nbytes,
+                          int max_ctas, void* stream);
+/* halo lists: rows row_ids[row_ptr[q] .. row_ptr[q+1]) (indices into the gathered [world * n_max, C] buffer) from rank q */
+int msha_peer_pull_rows(float* dst, const uint64_t* src_tab, int world, int rank, const int32_t* row_ids,
+                        const int64_t* row_ptr, int64_t max_rows_per_peer, int64_t C, int max_ctas, void* stream);
+/* out[i] = sum_k src_ptrs[k][i] in table order; src_ptrs is a HOST array of n_src (<= 32) device addresses */
+int msha_peer_sum(float* out, const uint64_t* src_ptrs, int n_src, int64_t n, int max_ctas, void* stream);
 
 /* ==== callers either side of the path ==== */
 

@@ -63,21 +63,27 @@ struct DropArgs {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int VW, int VPL>
+// PIPE (column-block pass of the partitioned forward, dist.py): the row's edge range is [rowptr[row], rowend[row]) --
+// the slots whose neighbour lives in one owner block --, the softmax statistics come in as the row's log-sum-exp over
+// ALL its edges (gat_stats_kernel), alpha = exp(logit - lse) is final, and the aggregate is added to `out`
+// (accumulate != 0: read-modify-write; hub segments: atomics) so that the blocks can be processed as they arrive.
+template <int VW, int VPL, bool PIPE = false>
 __global__ void __launch_bounds__(GAT_THREADS)
-gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_rows,
+gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowend,
+               const int32_t* __restrict__ col, int n_rows,
                const float* __restrict__ s_nbr, const float* __restrict__ s_self,
                const float* __restrict__ feat, int H, int D, float slope,
                const float* __restrict__ alpha_in, float* __restrict__ alpha_out,
                float* __restrict__ out, int act, float* __restrict__ lse_out, DropArgs drop, HubArgs hub,
-               float* __restrict__ part) {
+               float* __restrict__ part, const float* __restrict__ lse_in = nullptr, int accumulate = 0) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * GAT_WARPS + warp;
     int row, beg, end, seg = -1;
     if (w < n_rows) {
-        row = w; beg = rowptr[row]; end = rowptr[row + 1];
+        row = w; beg = rowptr[row]; end = rowend[row];
         if (hub.seg_limit && end - beg > hub.seg_limit) return;         // handled segment-wise below
+        if (PIPE && accumulate && beg == end) return;                   // nothing to add from this block
     } else {
         seg = w - n_rows;
         if (seg >= hub.n_segs) return;
@@ -101,7 +107,9 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
     const bool hp2 = (H & (H - 1)) == 0;
     const int hh = lane & (H - 1), es = hp2 ? lane / H : 0, EPI = hp2 ? 32 / H : 1;
     float m_stat = 0.f, l_stat = 1.f;
-    if (alpha_in == nullptr && hp2) {
+    if (PIPE) {
+        m_stat = lse_in[(int64_t)row * H + hh];          // hp2 only (checked on the host): a = exp(lg - lse), final
+    } else if (alpha_in == nullptr && hp2) {
         const float ss = s_self[(int64_t)row * H + hh];
         float m = -INFINITY, l = 0.f;
         for (int e = beg + es; e < end; e += EPI) {
@@ -167,7 +175,7 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
                     } else {
                         const float lg = masked ? NEG_MASK_F
                                                 : lrelu(__ldg(s_nbr + (int64_t)jj * H + hh) + s_self[(int64_t)row * H + hh], slope);
-                        a = part_mode ? expf(lg - m_stat) : expf(lg - m_stat) / l_stat;
+                        a = (part_mode || PIPE) ? expf(lg - m_stat) : expf(lg - m_stat) / l_stat;
                         if (alpha_out) alpha_out[(int64_t)e * H + hh] = a;            // coalesced
                     }
                     if (drop.thr) a *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + hh, drop.thr, drop.inv_keep);
@@ -219,6 +227,28 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
             }
         }
         __syncwarp();
+    }
+    if (PIPE) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int v = lane + 32 * k;
+            if (v < nvec) {
+                float* o = out + (int64_t)row * C + v * VW;
+                if (part_mode) {                       // hub segment: rows zeroed (or carried over) by the host wrapper
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) atomicAdd(o + q, acc[k][q]);
+                } else {
+                    if (accumulate) {
+                        float x[VW];
+                        VecT<VW>::load(o, x);
+#pragma unroll
+                        for (int q = 0; q < VW; ++q) acc[k][q] += x[q];
+                    }
+                    VecT<VW>::store(o, acc[k]);
+                }
+            }
+        }
+        return;
     }
     if (part_mode) {
         float* P = part + (int64_t)seg * (2 * H + C);
@@ -825,7 +855,7 @@ MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_r
     const size_t smem = (size_t)GAT_WARPS * (32 * H + 32) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(A, B)                                                                                             \
-    gat_fwd_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, feat, H, D, \
+    gat_fwd_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, rowptr + 1, col, (int)n_rows, s_nbr, s_self, feat, H, D, \
                                                           slope, alpha_in, alpha_out, out, act, lse_out, drop, hub, hub_scratch)
     DISPATCH_LAYOUT(vw, vpl, CALL)
 #undef CALL
@@ -840,6 +870,127 @@ MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_r
             MSHA_LAUNCH_OK();
         }
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// partitioned forward (dist.py): softmax statistics first, then one aggregation pass per owner block of columns
+// ---------------------------------------------------------------------------------------------
+// lse[row, h] = log sum_j exp(e_ij) over the whole row (needs only the H scores per node, which are exchanged before the
+// features).  H a power of two <= 32: lanes are (edge slot, head) pairs.  Hub rows: one warp per segment writes a partial
+// (m, l) pair, gat_stats_merge_kernel folds them.
+__global__ void __launch_bounds__(GAT_THREADS)
+gat_stats_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_rows,
+                 const float* __restrict__ s_nbr, const float* __restrict__ s_self, int H, float slope,
+                 float* __restrict__ lse_out, HubArgs hub, float* __restrict__ part) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * GAT_WARPS + warp;
+    int row, beg, end, seg = -1;
+    if (w < n_rows) {
+        row = w; beg = rowptr[row]; end = rowptr[row + 1];
+        if (hub.seg_limit && end - beg > hub.seg_limit) return;
+    } else {
+        seg = w - n_rows;
+        if (seg >= hub.n_segs) return;
+        row = hub.seg_item[seg]; beg = hub.seg_beg[seg]; end = hub.seg_end[seg];
+    }
+    const int hh = lane & (H - 1), es = lane / H, EPI = 32 / H;
+    const float ss = s_self[(int64_t)row * H + hh];
+    float m = -INFINITY, l = 0.f;
+    for (int e0 = beg + es; e0 < end; e0 += 4 * EPI) {          // 4 independent score gathers per lane in flight
+        float lg[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * EPI;
+            lg[u] = -INFINITY;
+            if (e < end) {
+                const int c = col[e];
+                lg[u] = c < 0 ? NEG_MASK_F : lrelu(__ldg(s_nbr + (int64_t)c * H + hh) + ss, slope);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (lg[u] == -INFINITY) continue;
+            if (lg[u] > m) { l = l * expf(m - lg[u]) + 1.f; m = lg[u]; } else { l += expf(lg[u] - m); }
+        }
+    }
+    for (int o = H; o < 32; o <<= 1) {
+        const float m2 = __shfl_xor_sync(FULL_MASK, m, o), l2 = __shfl_xor_sync(FULL_MASK, l, o);
+        const float M = fmaxf(m, m2);
+        l = (m == -INFINITY ? 0.f : l * expf(m - M)) + (m2 == -INFINITY ? 0.f : l2 * expf(m2 - M));
+        m = M;
+    }
+    if (lane < H) {
+        if (seg >= 0) { part[(int64_t)seg * 2 * H + lane] = m; part[(int64_t)seg * 2 * H + H + lane] = l; }
+        else lse_out[(int64_t)row * H + lane] = (end > beg) ? m + logf(l) : -INFINITY;
+    }
+}
+
+__global__ void gat_stats_merge_kernel(HubArgs hub, const float* __restrict__ part, int H, float* __restrict__ lse_out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= hub.n_hub * H) return;
+    const int i = idx / H, h = idx - i * H;
+    const int s0 = hub.hub_seg_ptr[i], s1 = hub.hub_seg_ptr[i + 1];
+    float M = -INFINITY, L = 0.f;
+    for (int s = s0; s < s1; ++s) M = fmaxf(M, part[(int64_t)s * 2 * H + h]);
+    for (int s = s0; s < s1; ++s) {
+        const float m = part[(int64_t)s * 2 * H + h];
+        if (m != -INFINITY) L += part[(int64_t)s * 2 * H + H + h] * expf(m - M);
+    }
+    lse_out[(int64_t)hub.hub_ids[i] * H + h] = M + logf(L);
+}
+
+// hub_scratch: float[2 * H * hub->n_segs] when the graph has hub rows.  H must be a power of two <= 32.
+MSHA_API int msha_gat_softmax_stats(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
+                                    const float* s_self, int H, float slope, float* lse, const msha_hub_t* hub_p,
+                                    float* hub_scratch, void* stream) {
+    MSHA_REQUIRE(H >= 1 && H <= 32 && (H & (H - 1)) == 0, "gat_softmax_stats: H must be a power of two <= 32");
+    MSHA_REQUIRE(s_nbr != nullptr && s_self != nullptr && lse != nullptr, "gat_softmax_stats: null argument");
+    MSHA_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), "gat_softmax_stats: bad n_rows");
+    if (n_rows == 0) return 0;
+    HubArgs hub = make_hub(hub_p);
+    MSHA_REQUIRE(hub.n_segs == 0 || hub_scratch != nullptr, "gat_softmax_stats: hub rows need scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    gat_stats_kernel<<<(unsigned)msha_cdiv(n_rows + hub.n_segs, GAT_WARPS), GAT_THREADS, 0, st>>>(
+        rowptr, col, (int)n_rows, s_nbr, s_self, H, slope, lse, hub, hub_scratch);
+    MSHA_LAUNCH_OK();
+    if (hub.n_hub > 0) {
+        gat_stats_merge_kernel<<<(unsigned)msha_cdiv((int64_t)hub.n_hub * H, 128), 128, 0, st>>>(hub, hub_scratch, H, lse);
+        MSHA_LAUNCH_OK();
+    }
+    return 0;
+}
+
+// One owner block of the partitioned forward: edges [rowbeg[i], rowend[i]) of every row i, alpha = exp(logit - lse)
+// written to alpha_out, out[i] (+)= sum alpha_ij feat[j].  accumulate == 0: out is overwritten (first block).
+// hub: segment description of THIS block's ranges (rows whose range exceeds seg_limit); their sums arrive by atomics.
+MSHA_API int msha_gat_fwd_block(const int32_t* rowbeg, const int32_t* rowend, const int32_t* col, int64_t n_rows,
+                                const float* s_nbr, const float* s_self, const float* lse, const float* feat, int H,
+                                int D, float slope, float* alpha_out, float* out, int accumulate, float drop_p,
+                                uint64_t drop_seed, const msha_hub_t* hub_p, void* stream) {
+    MSHA_REQUIRE(H >= 1 && H <= 32 && (H & (H - 1)) == 0 && D >= 4 && D % 4 == 0,
+                 "gat_fwd_block: H must be a power of two <= 32 and D a multiple of 4");
+    MSHA_REQUIRE(rowbeg && rowend && col && s_nbr && s_self && lse && feat && out, "gat_fwd_block: null argument");
+    MSHA_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), "gat_fwd_block: bad n_rows");
+    int vw, vpl;
+    MSHA_REQUIRE(pick_layout(H, D, &vw, &vpl) == 0 && vw == 4, "gat_fwd_block: unsupported channel count H*D=%d", H * D);
+    if (n_rows == 0) return 0;
+    HubArgs hub = make_hub(hub_p);
+    DropArgs drop = make_drop(drop_p, drop_seed, 2u);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (hub.n_hub > 0 && !accumulate) {
+        zero_rows_kernel<<<hub.n_hub, 128, 0, st>>>(out, hub.hub_ids, hub.n_hub, H * D);
+        MSHA_LAUNCH_OK();
+    }
+    const unsigned grid = (unsigned)msha_cdiv(n_rows + hub.n_segs, GAT_WARPS);
+    const size_t smem = (size_t)GAT_WARPS * (32 * H + 32) * sizeof(float);
+#define CALLP(B)                                                                                                        \
+    gat_fwd_kernel<4, B, true><<<grid, GAT_THREADS, smem, st>>>(rowbeg, rowend, col, (int)n_rows, s_nbr, s_self, feat, \
+                                                                H, D, slope, nullptr, alpha_out, out, 0, nullptr, drop, \
+                                                                hub, nullptr, lse, accumulate)
+    if (vpl == 1) { CALLP(1); } else if (vpl == 2) { CALLP(2); } else { CALLP(4); }
+#undef CALLP
+    MSHA_LAUNCH_OK();
     return 0;
 }
 
