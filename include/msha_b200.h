@@ -242,7 +242,7 @@ int msha_dropout_epoch_advance(uint64_t by, void* stream);
  * per rank, the address of that rank's buffer as mapped in the calling process. ==== */
 /* flags: uint32[n_channels][world] per rank.  signal: flags_of_peer_q[channel][rank] = value (+ *epoch) for every q in
  * peer_mask, released at system scope after all earlier work of the stream.  wait: until flags[channel][q] >= value
- * (+ *epoch) for every q in peer_mask; traps after timeout_ns (0 = never) with 0x100|q in *status. */
+ * (+ *epoch) for every q in peer_mask; gives up after timeout_ns (0 = never) leaving 0x100|q in *status. */
 int msha_peer_signal(const uint64_t* flag_tab, int world, int rank, int channel, uint32_t peer_mask,
                      const uint32_t* epoch, uint32_t value, void* stream);
 int msha_peer_wait(const uint32_t* flags, int world, int channel, uint32_t peer_mask, const uint32_t* epoch,

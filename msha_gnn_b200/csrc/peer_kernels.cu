@@ -8,7 +8,7 @@
 //   signal    release at system scope: everything this rank's earlier work on the stream wrote (kernel boundary) is
 //             visible to a peer that has observed the flag.
 //   wait      one thread per awaited peer spins with ld.acquire.sys; a bounded spin (timeout in ns of %globaltimer)
-//             traps instead of hanging the GPU when a peer died.
+//             sets a status word and returns instead of hanging the GPU when a peer died (PeerGroup.check raises).
 //   pull      gathers row blocks (or listed halo rows) out of the peers' buffers with 128-bit P2P loads.
 //   sum       out = sum over a table of pointers (local staging slots or peer buffers) in table order: the
 //             reduce-scatter of d Wh / d s_nbr; fixed order -> run-to-run deterministic.
@@ -54,9 +54,8 @@ __global__ void peer_wait_kernel(const uint32_t* __restrict__ flags, int world, 
     while ((int32_t)(ld_acquire_sys(f) - want) < 0) {
         __nanosleep(64);
         if (timeout_ns && globaltimer_ns() - t0 > timeout_ns) {
-            if (status) atomicExch(status, 0x100 | q);
-            __threadfence_system();
-            __trap();                      // a peer never arrived: fail the process instead of hanging the GPU
+            if (status) atomicExch(status, 0x100 | q);      // a peer never arrived: give up instead of hanging the GPU;
+            return;                                          // the host raises when it reads the status word
         }
     }
 }

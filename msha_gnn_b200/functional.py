@@ -41,10 +41,14 @@ def _c(t):
 # ------------------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W):
+    def forward(ctx, x, W, out=None):
         x, W = _c(x), _c(W)
         ctx.save_for_backward(x, W)
-        return ops.gemm(x, W)
+        if out is None:
+            return ops.gemm(x, W)
+        ops.gemm(x, W, out=out)              # caller-owned destination (a rank's own block of a peer-mapped buffer)
+        ctx.mark_dirty(out)
+        return out
 
     @staticmethod
     def backward(ctx, dy):
@@ -52,11 +56,11 @@ class _Linear(torch.autograd.Function):
         dy = _c(dy)
         dx = ops.gemm(dy, W, transB=True) if ctx.needs_input_grad[0] else None
         dW = ops.gemm(x, dy, transA=True) if ctx.needs_input_grad[1] else None
-        return dx, dW
+        return dx, dW, None
 
 
-def linear(x, W):
-    return _Linear.apply(x, W)
+def linear(x, W, out=None):
+    return _Linear.apply(x, W, out)
 
 
 class _LinearBiasAct(torch.autograd.Function):
@@ -260,9 +264,15 @@ class _AttentionBlock(torch.autograd.Function):
         r_buf = torch.empty((N, H), dtype=torch.float32, device=dev) if hub.n_segs else None
         extra = _c(d_alpha) if d_alpha is not None else None
         dlse = _c(d_lse) if d_lse is not None else None
-        dfeat_nbr = torch.empty((M, C), dtype=torch.float32, device=dev)
-        ds_nbr = torch.empty((M, H), dtype=torch.float32, device=dev)
-        sink = ctx.grad_sink if d_cols is None else None
+        # a sink may own the destinations of the two column-side gradients (peer-mapped buffers, dist.py)
+        dfeat_nbr = getattr(ctx.grad_sink, "feat_grad", None)
+        ds_nbr = getattr(ctx.grad_sink, "score_grad", None)
+        if dfeat_nbr is None:
+            dfeat_nbr = torch.empty((M, C), dtype=torch.float32, device=dev)
+        if ds_nbr is None:
+            ds_nbr = torch.empty((M, H), dtype=torch.float32, device=dev)
+        assert dfeat_nbr.shape == (M, C) and ds_nbr.shape == (M, H)
+        sink = ctx.grad_sink if (d_cols is None and hasattr(ctx.grad_sink, "start")) else None
         if sink is not None:
             # Partitioned graphs (dist.gat_encode): d feat_nbr is the big message of the backward.  Produce it first
             # -- it needs only alpha and dZ -- and hand it to the sink, which starts its reduce-scatter; the row pass
@@ -550,6 +560,20 @@ def pair_mul(hi, hj, src=None, dst=None):
     return _PairMul.apply(hi, hj, src, dst)
 
 
+
+def _pair_grad_tables(ctx, hi, hj):
+    """Destinations of d h_i / d h_j for the pair scatters.  One table scored against itself (``hi is hj``: link scoring
+    over a single embedding matrix) gets ONE buffer -- both scatters are atomic adds -- instead of two tables that
+    autograd would then have to add (three passes over the table); its gradient is returned for the first input only.
+    ``ctx.grad_buffer`` (set in the forward from the table's ``_msha_grad_buffer`` attribute) lets the caller own that
+    buffer: dist.py hands out the peer-mapped one its reduce-scatter reads."""
+    same = hi.data_ptr() == hj.data_ptr() and hi.shape == hj.shape
+    if same:
+        buf = ctx.grad_buffer() if ctx.grad_buffer is not None else None
+        dhi = buf.zero_() if buf is not None else torch.zeros_like(hi)
+        return dhi, dhi, True
+    return torch.zeros_like(hi), torch.zeros_like(hj), False
+
 class _ScoreMLP(torch.autograd.Function):
     """Fused LinkPredictor with one hidden Linear: act((h_i[src] * h_j[dst]) @ W0.T + b0)  (LLP.py:105-115).
     Forward: one tensor-core kernel (gather, Hadamard, 3xTF32 split in the producer warps; no Z tensor in HBM)."""
@@ -566,6 +590,7 @@ class _ScoreMLP(torch.autograd.Function):
              ptr(b0) if b0 is not None else None, Hd, act, LRELU_SLOPE, ptr(out), Hd, ws.data_ptr(), ws.numel(), _stream())
         ctx.act = act
         ctx.has_bias = b0 is not None
+        ctx.grad_buffer = getattr(hi, "_msha_grad_buffer", None)
         ctx.save_for_backward(hi, hj, src, dst, W0, out)
         return out
 
@@ -579,15 +604,14 @@ class _ScoreMLP(torch.autograd.Function):
         lib = ops._lib.lib()
         if FUSED_SCORE_BWD and Hd % 4 == 0 and C <= 256:
             # two tensor-core kernels: (G, db, dZ, scatter) and (dW0 with Z regenerated from the gathers)
-            dhi = torch.zeros_like(hi)
-            dhj = torch.zeros_like(hj)
+            dhi, dhj, same = _pair_grad_tables(ctx, hi, hj)
             dW = torch.empty_like(W0)
             db = torch.empty(Hd, dtype=torch.float32, device=out.device)
             ws = workspace(lib.msha_score_mlp_workspace_bytes(C, Hd), out.device)
             call("msha_score_mlp_bwd", ptr(dout), ptr(out), ptr(hi), ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P,
                  C, ptr(W0), Hd, ctx.act, LRELU_SLOPE, ptr(g), ptr(dhi), ptr(dhj), ptr(dW), ptr(db), ws.data_ptr(), ws.numel(),
                  _stream())
-            return dhi, dhj, None, None, dW, (db if ctx.has_bias else None), None
+            return dhi, (None if same else dhj), None, None, dW, (db if ctx.has_bias else None), None
         db = torch.empty(Hd, dtype=torch.float32, device=out.device)
         ws = workspace(lib.msha_act_bwd_colsum_workspace_bytes(Hd), out.device)
         call("msha_act_bwd_colsum", ptr(dout), ptr(out), ptr(g), P, Hd, ctx.act, LRELU_SLOPE, ptr(db), ws.data_ptr(),
@@ -630,6 +654,7 @@ class _ScoreMLPNll(torch.autograd.Function):
         call("msha_nll_loss_fwd", ptr(out), ptr(target, torch.int64), P, Hd, loss.data_ptr(), ptr(status, I32),
              ws2.data_ptr(), ws2.numel(), _stream())
         ctx.act, ctx.has_bias = act, b0 is not None
+        ctx.grad_buffer = getattr(hi, "_msha_grad_buffer", None)
         ctx.order, ctx.order_owned = None, False
         if SPARSE_NLL_BWD and C % 4 == 0 and C <= 1024 and P < (1 << 31) and any(ctx.needs_input_grad):
             if NLL_ORDER_BY_SRC and src is not None:
@@ -650,7 +675,7 @@ class _ScoreMLPNll(torch.autograd.Function):
         P, Hd = out.shape
         C = W0.shape[1]
         lib = ops._lib.lib()
-        dhi, dhj = torch.zeros_like(hi), torch.zeros_like(hj)
+        dhi, dhj, same = _pair_grad_tables(ctx, hi, hj)
         dW = torch.empty_like(W0)
         db = torch.empty(Hd, dtype=torch.float32, device=out.device)
         gl = _c(gloss.reshape(1).float())
@@ -663,16 +688,16 @@ class _ScoreMLPNll(torch.autograd.Function):
             call("msha_score_mlp_nll_bwd_sparse", ptr(order, I32), ptr(target, torch.int64), ptr(gl), ptr(out), Hd, ptr(hi),
                  ptr(hj), ptr(src, torch.int64), ptr(dst, torch.int64), P, C, ptr(W0), Hd, ctx.act, LRELU_SLOPE, ptr(dhi),
                  ptr(dhj), ptr(dW), ptr(db), _stream())
-            return dhi, dhj, None, None, dW, (db if ctx.has_bias else None), None, None
+            return dhi, (None if same else dhj), None, None, dW, (db if ctx.has_bias else None), None, None
         g = torch.empty_like(out)
         ws = workspace(lib.msha_score_mlp_workspace_bytes(C, Hd), out.device)
         call("msha_score_mlp_nll_bwd", ptr(target, torch.int64), ptr(gl), ptr(out), ptr(hi), ptr(hj), ptr(src, torch.int64),
              ptr(dst, torch.int64), P, C, ptr(W0), Hd, ctx.act, LRELU_SLOPE, ptr(g), ptr(dhi), ptr(dhj), ptr(dW), ptr(db),
              ws.data_ptr(), ws.numel(), _stream())
-        return dhi, dhj, None, None, dW, (db if ctx.has_bias else None), None, None
+        return dhi, (None if same else dhj), None, None, dW, (db if ctx.has_bias else None), None, None
 
 
-NLL_ORDER_BY_SRC = os.environ.get("MSHA_NLL_ORDER", "label") == "src"   # sort the pairs of a label by source row as well
+NLL_ORDER_BY_SRC = os.environ.get("MSHA_NLL_ORDER", "src") == "src"   # sort the pairs of a label by source row as well
 SPARSE_NLL_BWD = os.environ.get("MSHA_NLL_BWD", "sparse") != "dense"   # "dense": the tensor-core backward (validation / comparison)
 
 

@@ -46,10 +46,20 @@ class _HubStruct(ctypes.Structure):
 class Hub:
     """Segment decomposition of the rows (columns) with more than ``seg_limit`` entries; ``ptr`` is 0 when none."""
 
-    def __init__(self, ptr_arr: torch.Tensor, seg_limit: int = None):
-        seg_limit = default_seg_limit(int(ptr_arr[-1])) if seg_limit is None else seg_limit
-        deg = (ptr_arr[1:] - ptr_arr[:-1]).long()
+    def __init__(self, ptr_arr: torch.Tensor = None, seg_limit: int = None, beg: torch.Tensor = None,
+                 end: torch.Tensor = None):
+        """``ptr_arr``: a CSR / CSC pointer array (item i owns slots [ptr[i], ptr[i+1])); or explicit per-item slot
+        ranges ``beg`` / ``end`` (the owner-block sub-ranges of the partitioned forward, dist.py)."""
+        if ptr_arr is None:
+            ptr_arr_b, ptr_arr_e = beg, end
+            if seg_limit is None:
+                seg_limit = default_seg_limit(int((end.long() - beg.long()).sum().item()) if beg.numel() else 0)
+        else:
+            ptr_arr_b, ptr_arr_e = ptr_arr[:-1], ptr_arr[1:]
+            seg_limit = default_seg_limit(int(ptr_arr[-1])) if seg_limit is None else seg_limit
+        deg = (ptr_arr_e - ptr_arr_b).long()
         ids = torch.nonzero(deg > seg_limit).flatten()
+        ptr_arr = ptr_arr_b
         self.n_hub = int(ids.numel())
         self.n_segs = 0
         self.ptr = None
@@ -63,7 +73,7 @@ class Hub:
         local = torch.arange(self.n_segs, device=ptr_arr.device) - seg_ptr[:-1][which]
         item = ids[which]
         beg = ptr_arr.long()[item] + local * seg_limit
-        end = torch.minimum(beg + seg_limit, ptr_arr.long()[item + 1])
+        end = torch.minimum(beg + seg_limit, ptr_arr_e.long()[item])
         self.tensors = [t.to(torch.int32).contiguous() for t in (item, beg, end, ids, seg_ptr)]
         self.struct = _HubStruct(seg_limit, self.n_segs, self.tensors[0].data_ptr(), self.tensors[1].data_ptr(),
                                  self.tensors[2].data_ptr(), self.n_hub, 0, self.tensors[3].data_ptr(),

@@ -28,6 +28,16 @@ TIMEOUT_NS = int(float(os.environ.get("MSHA_PEER_TIMEOUT_S", "30")) * 1e9)
 CE_MIN_BYTES = int(os.environ.get("MSHA_PEER_CE_MIN_BYTES", str(4 << 20)))
 
 
+def require_eager_module_loading():
+    """Kernels of this path spin on flags that OTHER kernels set.  With CUDA's default lazy module loading the first
+    launch of a kernel function loads it, which can need the context to drain -- behind a spinning wait kernel that is a
+    deadlock (CUDA programming guide, "lazy loading": programs relying on concurrent kernels must preload).  The loading
+    mode is read when the CUDA context is created, so it has to be in the environment before the first CUDA call."""
+    if os.environ.get("CUDA_MODULE_LOADING", "").upper() != "EAGER" and os.environ.get("MSHA_PEER_ALLOW_LAZY") != "1":
+        raise RuntimeError("msha_b200 peer path: set CUDA_MODULE_LOADING=EAGER in the environment before CUDA is "
+                           "initialised (kernels that wait on one another must not be loaded lazily)")
+
+
 class PeerTensor:
     """A buffer every rank holds with the same shape; ``views[q]`` is rank q's copy as addressable from this rank."""
 
@@ -82,6 +92,13 @@ class PeerGroup:
         call("msha_peer_wait", self.flags.local.data_ptr(), self.world, channel, mask, None, value & 0xFFFFFFFF,
              TIMEOUT_NS, self.status.data_ptr(), ops._stream())
 
+    def check(self):
+        """Raise if a flag wait of this rank ever timed out (reads one word: synchronises the host with the device)."""
+        st = int(self.status.item())
+        if st:
+            raise RuntimeError(f"msha_b200 peer path: rank {self.rank} gave up waiting for rank {st & 0xFF} "
+                               f"(no flag within {TIMEOUT_NS / 1e9:.0f} s)")
+
     def barrier(self):
         """Device-side barrier over the fabric (stream-ordered; the host does not block)."""
         self._barrier_seq += 1
@@ -113,18 +130,23 @@ class LocalFabric:
     """All ranks in one process on one device (tests, single-GPU emulation)."""
 
     def __init__(self, world: int, device):
+        require_eager_module_loading()
+        import threading
         self.world, self.device = int(world), device
         self._allocs = []
+        self._lock = threading.Lock()                      # the emulated ranks may run in one host thread each
         self.groups = [None] * world
         self.streams = [torch.cuda.Stream(device=device) for _ in range(world)]
         for r in range(world):
             self.groups[r] = PeerGroup(self, r, world, device)
 
     def alloc(self, group, index, shape, dtype, zero):
-        if index == len(self._allocs):
-            mk = torch.zeros if zero else torch.empty
-            self._allocs.append([mk(shape, dtype=dtype, device=self.device) for _ in range(self.world)])
-        views = self._allocs[index]
+        with self._lock:
+            if index == len(self._allocs):
+                mk = torch.zeros if zero else torch.empty
+                self._allocs.append([mk(shape, dtype=dtype, device=self.device) for _ in range(self.world)])
+                torch.cuda.current_stream().synchronize()      # zero-fill done before another rank's stream touches it
+            views = self._allocs[index]
         if tuple(views[0].shape) != shape or views[0].dtype != dtype:
             raise RuntimeError("LocalFabric: ranks must allocate the same buffers in the same order")
         return PeerTensor(views, group.rank)
@@ -137,6 +159,7 @@ class SymmFabric:
     """Real ranks over torch.distributed: symmetric-memory allocation, rendezvous over the process group."""
 
     def __init__(self, group=None, device=None):
+        require_eager_module_loading()
         import torch.distributed as dist
         self.dist = dist
         self.pg = group if group is not None else dist.group.WORLD

@@ -4,6 +4,12 @@ import sys
 import numpy as np
 import pytest
 
+# emulated ranks of tests/test_gpu_p2p.py spin on one another's flags from different streams of one process: give every
+# stream its own hardware queue (read when the CUDA context is created, i.e. before the first GPU test runs)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")    # ... and no kernel is loaded lazily behind a spinning one
+os.environ.setdefault("MSHA_PEER_TIMEOUT_S", "20")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

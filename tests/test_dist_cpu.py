@@ -32,6 +32,81 @@ def test_partition_bounds_and_padding():
     assert q.bounds[0] == 0 and q.bounds[-1] == 6 and 0 < q.bounds[1] < 6
     e0 = int(rowptr[q.bounds[1]])
     assert abs(e0 - 20) <= 10                                    # close to half of the edges
+    # block stride of the gathered layout: a multiple of 4 rows (128-bit peer pulls / sums)
+    assert Partition(10, 2, 0).n_max == 8 and Partition(10, 2, 0).n_padded == 16 and Partition(10, 2, 1).sizes == [5, 5]
+    assert Partition(10, 2, 1).to_padded(torch.arange(10)).tolist() == [0, 1, 2, 3, 4, 8, 9, 10, 11, 12]
+    # a hub row heavier than total / world must not produce empty ranks
+    hub = torch.tensor([0, 1000, 1001, 1002, 1003, 1004])
+    for w in (2, 3, 5):
+        b = Partition.edge_balanced(hub, w, 0).bounds
+        assert all(b[i + 1] > b[i] for i in range(w)), b
+    try:
+        Partition.edge_balanced(hub, 6, 0)
+        raise AssertionError("6 ranks over 5 rows must be rejected")
+    except ValueError:
+        pass
+
+
+class _StubPredictor:
+    """nll_loss_pairs with plain torch ops (the scaling logic under test is host-side)."""
+
+    def __init__(self, W):
+        self.W = W
+
+    def nll_loss_pairs(self, hi, hj, src, dst, target):
+        out = torch.sigmoid(torch.relu((hi[src] * hj[dst]) @ self.W.t()))
+        return torch.nn.functional.nll_loss(out, target)
+
+
+def _loss_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from msha_gnn_b200.dist import score_pairs
+        rng = np.random.default_rng(3)
+        N, C, Hd = 13, 6, 4
+        h = torch.tensor(rng.standard_normal((N, C)), dtype=torch.float64)
+        W0 = torch.tensor(rng.standard_normal((Hd, C)), dtype=torch.float64)
+        P = 37                                                   # uneven shards: 12 and 25 pairs
+        src, dst = torch.from_numpy(rng.integers(0, N, P)), torch.from_numpy(rng.integers(0, N, P))
+        lab = torch.from_numpy(rng.integers(0, Hd, P))
+        cut = [0, 12, P]
+        # single-process reference: mean over all pairs
+        hf, Wf = h.clone().requires_grad_(True), W0.clone().requires_grad_(True)
+        ref = _StubPredictor(Wf).nll_loss_pairs(hf, hf, src, dst, lab)
+        ref.backward()
+        part = Partition(N, world, rank)
+        hl = h[part.lo:part.hi].clone().requires_grad_(True)
+        Wl = W0.clone().requires_grad_(True)
+        sl = slice(cut[rank], cut[rank + 1])
+        for gp in (None, P):                                     # pair count all-reduced inside / given by the caller
+            hl.grad = Wl.grad = None
+            loss = score_pairs(_StubPredictor(Wl), hl, src[sl], dst[sl], part, target=lab[sl], global_pairs=gp)
+            loss.backward()
+            allreduce_gradients([Wl])
+            tot = loss.detach().clone()
+            dist.all_reduce(tot)
+            assert torch.allclose(tot, ref.detach(), atol=1e-12), (tot, ref)          # shares add up to the global mean
+            assert torch.allclose(Wl.grad, Wf.grad, atol=1e-12)
+            assert torch.allclose(hl.grad, hf.grad[part.lo:part.hi], atol=1e-12)
+        # a rank without a gradient for one parameter still takes part in the flat all-reduce
+        a, b = torch.ones(3, requires_grad=True), torch.ones(2, requires_grad=True)
+        (a.sum() * (rank + 1)).backward() if rank == 0 else (a.sum() + b.sum()).backward()
+        allreduce_gradients([a, b])
+        assert a.grad.tolist() == [2.0] * 3 and b.grad.tolist() == [1.0] * 2
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_mean_nll_over_ranks_equals_single_process_gloo():
+    """the per-rank mean losses used to add up to ~world x the single-GPU loss."""
+    world = 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_loss_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
 
 
 def _worker(rank, world, port, ret):

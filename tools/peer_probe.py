@@ -6,6 +6,8 @@ import os
 import sys
 import time
 
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
