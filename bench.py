@@ -24,6 +24,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # the peer-memory exchange runs kernels that wait on other kernels: nothing may be loaded lazily behind a spinning
+    # one, and the side streams get hardware queues of their own (both are read when the CUDA context is created)
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 import torch
@@ -153,18 +158,31 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # algorithmic bytes per C-ABI call (SURVEY.md section 8d gather model; fp32, int32 indices)
 # ------------------------------------------------------------------------------------------------
-def algorithmic_bytes(wl, E, P):
-    N, C, H, F, Hd = wl["n_nodes"], wl["hidden"], wl["heads"], wl["feat"], wl["pred_hidden"]
+def algorithmic_bytes(wl, E, P, N=None):
+    """Per C-ABI call family: SURVEY.md section 8d per-unit bytes x the units one step hands it.  GAT families are per LAYER
+    (one launch per layer on a single GPU; several block launches per layer on the pipelined multi-GPU path)."""
+    N = wl["n_nodes"] if N is None else N
+    C, H, Hd = wl["hidden"], wl["heads"], wl["pred_hidden"]
+    fwd = E * (4 + 8 * H + 4 * C) + N * 4 * C
     return {
-        "msha_gat_fwd": E * (4 + 8 * H + 4 * C) + N * 4 * C,
+        "msha_gat_fwd": fwd,
+        "msha_gat_fwd_block": fwd,
         "msha_gat_bwd_rows": E * (4 + 8 * H + 4 * C + 4 * H) + N * 12 * C,
         "msha_spmm_csc": E * (8 + 8 * H + 4 * C) + N * 4 * C,
-        # contraction-free scorer backward under the nll read-out: order + label + indices + one score sector, two row
-        # gathers and two read-modify-write row scatters per pair (SURVEY 8d scoring model minus the dense dOut / out / G)
+        # scoring MLP, per pair (8d): fwd  8 (idx) + 8C (two row gathers) + 4Hd (scores out);
+        # bwd  4Hd (d scores) + 4Hd (scores) + 8C (re-gather) + 16C (two read-modify-write row scatters)
+        "msha_score_mlp_fwd": P * (8 + 8 * C + 4 * Hd),
+        "msha_score_mlp_bwd": P * (8 + 8 * Hd + 8 * C + 16 * C),
+        # nll read-out folded in: d scores is generated in the kernel, not read
+        "msha_score_mlp_nll_bwd": P * (8 + 4 * Hd + 8 * C + 16 * C),
+        # contraction-free backward: order + label + indices + one score sector, two row gathers and two RMW row scatters
         "msha_score_mlp_nll_bwd_sparse": P * (4 + 8 + 16 + 32 + 8 * C + 16 * C),
         "msha_pair_gather_mul": P * (16 + 8 * C + 4 * C),
         "msha_pair_scatter_mul_add": P * (16 + 4 * C + 8 * C + 16 * C),
     }
+
+
+GAT_FAMILIES = ("msha_gat_fwd", "msha_gat_fwd_block", "msha_gat_softmax_stats", "msha_gat_bwd_rows", "msha_spmm_csc")
 
 
 class KernelTimer:
@@ -192,7 +210,8 @@ class KernelTimer:
 
     def _mods(self):
         import msha_gnn_b200.functional as f, msha_gnn_b200.graph as g, msha_gnn_b200.intra as i
-        return [f, g, i]
+        import msha_gnn_b200.dist as d, msha_gnn_b200.peer as p
+        return [f, g, i, d, p]
 
     def __exit__(self, *exc):
         self.ops.call = self.orig
@@ -213,38 +232,133 @@ class KernelTimer:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def rmat_graph_device(n, e, seed, dev, a=0.57, b=0.19, c=0.19):
+    """R-MAT edge list generated on the GPU (torch's Philox generator: the same seed gives the same list on every rank),
+    ids randomly permuted, one self loop per node (no isolated rows).  -> (rows, cols) int64 device tensors."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    scale = int(np.ceil(np.log2(n)))
+    rows = torch.zeros(e, dtype=torch.int64, device=dev)
+    cols = torch.zeros(e, dtype=torch.int64, device=dev)
+    for lvl in range(scale):
+        r = torch.rand(e, generator=g, device=dev)
+        rows |= (r >= a + b).long() << lvl
+        cols |= (((r >= a) & (r < a + b)) | (r >= a + b + c)).long() << lvl
+        del r
+    perm = torch.randperm(1 << scale, generator=g, device=dev)
+    rows, cols = perm[rows] % n, perm[cols] % n
+    loops = torch.arange(n, dtype=torch.int64, device=dev)
+    return torch.cat([rows, loops]), torch.cat([cols, loops])
+
+
+def measure_tf32_peak(dev):
+    """Dense TF32 tensor-pipe peak of THIS GPU, measured like MEASURED_PEAKS.json measures bf16 (library GEMM, 8192^3,
+    best of 5): the denominator of the tensor-pipe fractions (kind::tf32 is what the 3xTF32 kernels issue)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / best / 1e9
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def parity_block(mg, mdist, model, x, graph, part, world, dev, n_rows=256, n_pairs=4096, seed=0):
+    """Parity at benchmark scale ("check the GPU result on sampled rows"): every GAT layer's output
+    on `n_rows` sampled local rows, and the scores of `n_pairs` sampled pairs, against the fp64 oracle evaluated on
+    exactly those rows / pairs from the GPU's own layer inputs (oracle.gat_layer_rows / link_predictor).  rel. err =
+    max|gpu - oracle| / max|oracle|; the north-star tolerance is 1e-4."""
+    from oracle import msha_oracle as O               # checker only
+    import torch.distributed as dist
+    rng = np.random.default_rng(seed + part.rank)
+    res = {"rows_sampled": 0, "pairs_sampled": 0, "layers": [], "tolerance": 1e-4}
+    with torch.no_grad():
+        n_loc = graph.n_rows
+        S = np.sort(rng.choice(n_loc, size=min(n_rows, n_loc), replace=False))
+        S_d = torch.from_numpy(S).to(dev)
+        rp = graph.rowptr.long()
+        beg, end = rp[S_d], rp[S_d + 1]
+        cnt = (end - beg)
+        idx = torch.repeat_interleave(beg - torch.cumsum(cnt, 0) + cnt, cnt) + torch.arange(int(cnt.sum()), device=dev)
+        nbr = graph.col.long()[idx]                                     # padded column ids of the sampled rows' edges
+        self_ids = S_d + part.rank * part.n_max
+        nodes, inv = torch.unique(torch.cat([nbr, self_ids]), return_inverse=True)
+        nbr_ptr = np.concatenate([[0], np.cumsum(cnt.cpu().numpy())])
+        nbr_idx, self_idx = inv[:nbr.numel()].cpu().numpy(), inv[nbr.numel():].cpu().numpy()
+        h = x.detach()
+        worst = 0.0
+        for conv in model.convs:
+            h_g = mdist.all_gather_rows(h, part) if world > 1 else h     # layer input of every node (padded ids)
+            out = mdist.gat_encode([conv], h, graph, part, training=False) if world > 1 else conv(h, graph)
+            ref = O.gat_layer_rows(h_g[nodes].double().cpu(), conv.W.detach().double().cpu(), conv.a_nbr.detach().double().cpu(),
+                                   conv.a_self.detach().double().cpu(), self_idx, nbr_ptr, nbr_idx, conv.heads)
+            got = out[S_d].double().cpu()
+            err = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+            res["layers"].append(err)
+            worst = max(worst, err)
+            h = out
+        h_g = mdist.all_gather_rows(h, part) if world > 1 else h
+        n_all = h_g.shape[0]
+        ps = torch.from_numpy(rng.integers(0, n_loc, n_pairs)).to(dev) + part.rank * part.n_max
+        pd = part.to_padded(torch.from_numpy(rng.integers(0, part.n_nodes, n_pairs)).to(dev))
+        sc = model.predictor.forward_pairs(h_g, h_g, ps, pd)
+        lins = model.predictor.lins
+        ref = O.link_predictor(h_g[ps].double().cpu(), h_g[pd].double().cpu(), [l.weight.detach().double().cpu() for l in lins],
+                               [l.bias.detach().double().cpu() for l in lins])
+        err_s = float((sc.double().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        res.update(rows_sampled=int(S.size), pairs_sampled=int(n_pairs), scores=err_s)
+        worst = max(worst, err_s)
+    t = torch.tensor([worst], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["worst_over_ranks"] = float(t.item())
+    res["ok"] = bool(res["worst_over_ranks"] <= res["tolerance"])
+    return res
+
+
+_FABRIC = [None]
+
+
+def run_job(args, wl_name, steps, warmup, full=True):
+    """One workload on the ranks of this launch.  -> the JSON-line dict (rank 0) or None (other ranks)."""
     import torch.distributed as dist
     import msha_gnn_b200 as mg
     from msha_gnn_b200 import ops
+    from msha_gnn_b200 import dist as mdist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    wl = WORKLOADS[args.workload]
-    hbm_peak, _, peak_src = load_peaks()
-    if args.dense_nll_bwd:
-        mg.functional.SPARSE_NLL_BWD = False
+    wl = WORKLOADS[wl_name]
+    hbm_peak, bf16_peak, peak_src = load_peaks()
+    mg.functional.SPARSE_NLL_BWD = bool(args.contraction_free)
 
-    # ---- data.  N = 1: the workload graph.  N > 1 (weak scaling): the graph grows with N -- N*n nodes, N*E edges,
-    # same degree distribution -- and is partitioned by destination-node range; rank r generates the edges of its
-    # own rows (columns anywhere), so the per-GPU work is the N = 1 work plus the per-layer all-gather /
-    # reduce-scatter of the column-side tensors (msha_gnn_b200/dist.py).
-    from msha_gnn_b200 import dist as mdist
-    strong = wl["graph"].startswith("R-MAT")          # fixed graph partitioned over the ranks (BASELINE.json configs[3])
+    # ---- data.  "weak" (ER workloads, N > 1): the graph grows with N -- N*n nodes, N*E edges, same degree distribution --
+    # and rank r generates the edges of its own rows.  "strong" (R-MAT): one fixed graph, generated on every GPU from the
+    # same seed and partitioned by destination-node range with edge-balanced cut points.
+    strong = wl["graph"].startswith("R-MAT")
+    rows_h = cols_h = None
     if strong:
         n_glob = wl["n_nodes"]
-        rows, cols = make_graph_host(wl)               # identical on every rank (seeded)
+        rows_d, cols_d = rmat_graph_device(n_glob, wl["n_edges"], 4, dev)
         if world > 1:
-            rowptr_h = np.zeros(n_glob + 1, dtype=np.int64)
-            np.cumsum(np.bincount(rows, minlength=n_glob), out=rowptr_h[1:])
-            part = mdist.Partition.edge_balanced(torch.from_numpy(rowptr_h), world, rank)
-            keep = (rows >= part.lo) & (rows < part.hi)
-            rows, cols = rows[keep], cols[keep]
+            rowptr_h = torch.zeros(n_glob + 1, dtype=torch.int64)
+            rowptr_h[1:] = torch.cumsum(torch.bincount(rows_d, minlength=n_glob), 0).cpu()
+            part = mdist.Partition.edge_balanced(rowptr_h, world, rank)
+            keep = (rows_d >= part.lo) & (rows_d < part.hi)
+            rows_d, cols_d = rows_d[keep], cols_d[keep]
+            del keep
         else:
             part = mdist.Partition(n_glob, 1, 0)
         n_loc = part.n_local
@@ -252,14 +366,20 @@ def run_ours(args):
         n_loc, n_glob = wl["n_nodes"], wl["n_nodes"] * world
         part = mdist.Partition(n_glob, world, rank)
         if world == 1:
-            rows, cols = make_graph_host(wl)
+            rows_h, cols_h = make_graph_host(wl)
         else:
-            rows, cols = er_graph(n_loc, wl["n_edges"], 1 + rank, n_cols=n_glob)
-            rows = rows + part.lo
+            rows_h, cols_h = er_graph(n_loc, wl["n_edges"], 1 + rank, n_cols=n_glob)
+            rows_h = rows_h + part.lo
+        rows_d, cols_d = torch.from_numpy(rows_h).to(dev), torch.from_numpy(cols_h).to(dev)
     L = wl["layers"]
-    n_pos = rows.size if wl["pos_pairs"] is None else min(rows.size, wl["pos_pairs"] // (world if strong else 1))
-    pos_host = torch.from_numpy(np.stack([rows[:n_pos], cols[:n_pos]])).pin_memory()   # (2, n_pos) int64 positives (global ids)
-    rows_d, cols_d = torch.from_numpy(rows).to(dev), torch.from_numpy(cols).to(dev)
+    n_raw = int(rows_d.numel())
+    n_pos = n_raw if wl["pos_pairs"] is None else min(n_raw, wl["pos_pairs"] // (world if strong else 1))
+    pos_dev = torch.stack([rows_d[:n_pos], cols_d[:n_pos]]).contiguous()         # (2, n_pos) int64 positives (global ids)
+    pos_host = torch.empty(pos_dev.shape, dtype=torch.int64, pin_memory=True)
+    pos_host.copy_(pos_dev)
+    if strong and full and world == 1 and not args.no_cpu_baseline:              # 1 % node-induced subsample for the CPU leg
+        keep = (rows_d % 100 == 0) & (cols_d % 100 == 0)
+        rows_h, cols_h = (rows_d[keep] // 100).cpu().numpy(), (cols_d[keep] // 100).cpu().numpy()
     if world == 1:
         graph = mg.Graph.from_coo(rows_d, cols_d, n_loc, n_loc)
     else:
@@ -267,6 +387,13 @@ def run_ours(args):
     del rows_d, cols_d
     E = graph.nnz                                      # distinct directed edges owned by this rank
     graph.attention_csc()
+    use_p2p = world > 1 and args.comm == "p2p"
+    p2p = None
+    if use_p2p:
+        from msha_gnn_b200 import peer
+        if _FABRIC[0] is None:
+            _FABRIC[0] = peer.SymmFabric()
+        p2p = mdist.P2P(_FABRIC[0].group, part)
     torch.manual_seed(42)                                                        # identical parameters on every rank
     model = mg.GATLinkModel(wl["feat"], wl["hidden"], wl["heads"], L, wl["pred_hidden"], dropout=0.0).to(dev)
     torch.manual_seed(100 + rank)
@@ -275,7 +402,6 @@ def run_ours(args):
     opt = torch.optim.Adam(params + [x], lr=1e-3, weight_decay=5e-4, fused=True)   # train.py:207
     P = 2 * n_pos
     labels = torch.cat([torch.ones(n_pos, dtype=torch.int64, device=dev), torch.zeros(n_pos, dtype=torch.int64, device=dev)])
-    pos_dev = pos_host.to(dev)
     lib = mg._lib.lib()
     e_tot = torch.tensor([E, P], dtype=torch.int64, device=dev)
     if world > 1:
@@ -287,18 +413,17 @@ def run_ours(args):
         src = torch.cat([pos[0], nsrc + part.lo])
         dst = torch.cat([pos[1], ndst])
         opt.zero_grad(set_to_none=True)
-        if args.unfused_loss:
-            if world == 1:
-                out = model(x, graph, src, dst)                                  # (P, pred_hidden) sigmoid scores
+        if world == 1:
+            if args.unfused_loss:
+                loss = mg.functional.nll_loss(model(x, graph, src, dst), labels)     # separate read-out op (LLP.py:235)
+            else:
+                loss = model.loss(x, graph, src, dst, labels)                        # same read-out, fused into the scorer
+        else:
+            if use_p2p:
+                h = mdist.gat_encode_p2p(model.convs, x, graph, part, p2p)
             else:
                 h = mdist.gat_encode(model.convs, x, graph, part)
-                out = mdist.score_pairs(model.predictor, h, src, dst, part)
-            loss = mg.functional.nll_loss(out, labels)                           # LLP.py:235 read-out shape
-        elif world == 1:
-            loss = model.loss(x, graph, src, dst, labels)                        # same read-out, d scores generated in-kernel
-        else:
-            h = mdist.gat_encode(model.convs, x, graph, part)
-            loss = mdist.score_pairs(model.predictor, h, src, dst, part, target=labels)
+            loss = mdist.score_pairs(model.predictor, h, src, dst, part, target=labels, global_pairs=P_global, p2p=p2p)
         loss.backward()
         if world > 1:
             mdist.allreduce_gradients(params, world=world)
@@ -310,44 +435,34 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for it in range(args.warmup):
+    def timed(n, first_it, feed=None):
+        """n steps between two CUDA events on the launching stream, barrier + synchronize on both sides -> ms / step."""
+        barrier()
+        l0 = lib.msha_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for it in range(n):
+            last = feed(it) if feed is not None else step(first_it + it, pos_dev)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / n, lib.msha_launch_count() - l0, last
+
+    for it in range(warmup):
         step(it, pos_dev)
-    # ---- device-resident timing
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = lib.msha_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    trace = [] if os.environ.get("MSHA_BENCH_TRACE") else None
-    for it in range(args.steps):
-        t0 = time.perf_counter()
-        loss = step(args.warmup + it, pos_dev)
-        if trace is not None:
-            e = torch.cuda.Event(enable_timing=True)
-            e.record()
-            import gc
-            trace.append((time.perf_counter() - t0, e, torch.cuda.memory_reserved() >> 20,
-                          sum(g["collections"] for g in gc.get_stats())))
-    ev1.record()
-    barrier()
-    launches = lib.msha_launch_count() - l0
-    ms_dev = ev0.elapsed_time(ev1) / args.steps
-    if trace is not None and rank == 0:
-        prev, gpu = ev0, []
-        for rec in trace:
-            gpu.append(round(prev.elapsed_time(rec[1]), 2))
-            prev = rec[1]
-        print("dev loop trace: host enqueue ms/step", [round(r[0] * 1e3, 2) for r in trace], "gpu ms/step", gpu,
-              "reserved MiB", [r[2] for r in trace], "gc collections so far", [r[3] for r in trace], file=sys.stderr)
-    # ---- end-to-end timing: pinned host batch -> device every step, loss back to the host
-    # The pinned batch of step i+1 is copied on a second stream while step i computes (two device buffers, an event per
-    # buffer) -- every step's host->device copy and its loss read-back stay inside the timed region.
+    # ---- device-resident timing
+    ms_dev, launches, _ = timed(steps, warmup)
+    # ---- end-to-end timing: pinned host batch -> device every step, loss back to the host.  The pinned batch of step i+1 is
+    # copied on a second stream while step i computes (two device buffers, an event per buffer): every step's host->device
+    # copy and its loss read-back stay inside the timed region.
     copy_stream = torch.cuda.Stream()
     bufs = [torch.empty_like(pos_dev), torch.empty_like(pos_dev)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    total = [2]
 
     def prefetch(i):
         b = i & 1
@@ -356,127 +471,131 @@ def run_ours(args):
             bufs[b].copy_(pos_host, non_blocking=True)
             ready[b].record(copy_stream)
 
-    def host_fed_step(i, seed_it):
-        b = i & 1
-        torch.cuda.current_stream().wait_event(ready[b])
-        if i + 1 < host_fed_total[0]:
-            prefetch(i + 1)
-        loss_ = step(seed_it, bufs[b])
-        consumed[b].record()
-        return float(loss_.item())
+    def host_fed(seed0):
+        def run(i):
+            b = i & 1
+            torch.cuda.current_stream().wait_event(ready[b])
+            if i + 1 < total[0]:
+                prefetch(i + 1)
+            loss_ = step(seed0 + i, bufs[b])
+            consumed[b].record()
+            return float(loss_.item())
+        return run
 
-    host_fed_total = [2]
     for b in range(2):
         consumed[b].record()
     prefetch(0)
+    run = host_fed(20_000)
     for it in range(2):                # untimed: the first host-fed steps allocate the per-step staging tensors
-        host_fed_step(it, 20_000 + it)
+        run(it)
     barrier()
-    host_fed_total[0] = args.steps
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record()
+    total[0] = steps
     prefetch(0)
-    for it in range(args.steps):
-        loss_host = host_fed_step(it, args.warmup + args.steps + it)
-    ev3.record()
-    barrier()
+    ms_e2e, _, loss_host = timed(steps, 0, feed=host_fed(warmup + steps))
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = ev2.elapsed_time(ev3) / args.steps
-    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    # ---- the contraction-free scorer backward (exploits the one-hot d scores of the nll read-out) as a variant
+    variant = None
+    if full and not args.contraction_free and not args.unfused_loss:
+        mg.functional.SPARSE_NLL_BWD = True
+        for it in range(3):
+            step(30_000 + it, pos_dev)
+        ms_var, _, _ = timed(steps, 30_003)
+        mg.functional.SPARSE_NLL_BWD = False
+        variant = ms_var
+    t = torch.tensor([ms_dev, ms_e2e, variant if variant is not None else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = t.tolist()
+    ms_dev, ms_e2e, ms_var = t.tolist()
 
-    # ---- per-kernel profile pass (outside the timed region)
-    roofline, kernels, gat_roofline = None, [], None
-    if rank != 0:                      # the profile steps contain collectives: every rank must run them
+    # ---- per-kernel profile pass (outside the timed region; every rank runs it: the steps contain exchanges)
+    roofline, kernels, gat_roofline, tf32_peak = None, [], None, None
+    with KernelTimer(ops) as kt:
         step(10_000, pos_dev)
         step(10_001, pos_dev)
+    if p2p is not None:
+        p2p.pg.check()
     if rank == 0:
-        with KernelTimer(ops) as kt:
-            step(10_000, pos_dev)
-            step(10_001, pos_dev)
+        tf32_peak = measure_tf32_peak(dev)
         agg = kt.summary()
-        ab = algorithmic_bytes(wl, E, P)
+        ab = algorithmic_bytes(wl, E, P, n_loc)
         tot = sum(v[1] for v in agg.values())
         for fname, (cnt, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             per = ms / cnt
             row = {"call": fname, "launches_per_step": cnt // 2, "avg_ms": round(per, 4), "share": round(ms / tot, 4)}
             if fname in ab:
+                units = L if fname in GAT_FAMILIES else 1          # GAT families: bytes per layer, time per layer
+                per_unit_ms = ms / 2 / units
                 row["algorithmic_GB"] = round(ab[fname] / 1e9, 4)
-                row["GBps"] = round(ab[fname] / 1e6 / per, 1)
-                row["frac_hbm"] = round(ab[fname] / 1e6 / per / hbm_peak, 4)
+                row["per"] = "layer" if units > 1 else "launch"
+                row["ms_per_unit"] = round(per_unit_ms, 4)
+                row["GBps"] = round(ab[fname] / 1e6 / per_unit_ms, 1)
+                row["frac_hbm"] = round(ab[fname] / 1e6 / per_unit_ms / hbm_peak, 4)
             kernels.append(row)
         # dense-contraction flops per call (fp32-equivalent 2*M*N*K; the 3xTF32 split issues 3x that on the tensor pipe)
         gemm_flops = sum(2.0 * sh[0] * sh[1] * sh[2] for f, a, b, sh in kt.records if f.startswith("msha_gemm") and len(sh) >= 3) / 2
         C_, Hd_ = wl["hidden"], wl["pred_hidden"]
         tensor_flops = {"msha_gemm_tf32x3": gemm_flops, "msha_score_mlp_fwd": 2.0 * P * C_ * Hd_,
                         "msha_score_mlp_bwd": 4.0 * P * C_ * Hd_, "msha_score_mlp_nll_bwd": 4.0 * P * C_ * Hd_}
-        _, bf16_peak, _ = load_peaks()
-        tf32_peak = bf16_peak / 2.0              # kind::tf32 runs at half the bf16 rate; bf16 peak = measured cuBLAS number
         for k in kernels:
             if k["call"] in tensor_flops:
                 tf = tensor_flops[k["call"]] / (k["avg_ms"] * k["launches_per_step"] * 1e-3) / 1e12
                 k["algorithmic_TFLOPs"] = round(tf, 1)
-                k["issued_tf32_TFLOPs"] = round(3 * tf, 1)
-                k["frac_tf32_peak"] = round(3 * tf / tf32_peak, 4)
+                k["tensor_frac_algorithmic"] = round(tf / tf32_peak, 4)
+                k["tensor_frac_issued_3xtf32"] = round(3 * tf / tf32_peak, 4)
         dom = kernels[0] if kernels else None
         traffic = None                     # DRAM bytes per launch of the dominant call, from the committed ncu capture
         try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
-                tr = json.load(f).get(args.workload, {})
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f).get(wl_name, {})
             if dom and world == 1 and tr.get("pairs") == P and dom["call"] in tr:
                 traffic = tr[dom["call"]]["bytes"]
         except (OSError, ValueError):
             pass
-        if dom and dom["call"] in tensor_flops:
-            roofline = {"bound": "tensor", "kernel": dom["call"], "achieved": dom["issued_tf32_TFLOPs"], "peak": tf32_peak,
-                        "unit": "TFLOP/s", "frac": dom["frac_tf32_peak"], "traffic": traffic,
-                        "algorithmic_fp32_equiv_TFLOPs": dom["algorithmic_TFLOPs"],
-                        "frac_algorithmic": round(dom["algorithmic_TFLOPs"] / tf32_peak, 4),
-                        "note": "achieved = tf32 flops issued per launch (3 per fp32-accurate product: 3xTF32 split) / CUDA-event "
-                                "time; peak = measured bf16 cuBLAS peak / 2 (kind::tf32 rate); frac_algorithmic counts the "
-                                "SURVEY 8d flops (2*P*C*Hd) once -- fp32-grade results (rel. err <= 1e-4) need the 3-way split, so its "
-                                "ceiling is 1/3; " + peak_src,
-                        "share_of_step": dom["share"]}
-        elif dom and "GBps" in dom:
+        if dom and "GBps" in dom:
             roofline = {"bound": "hbm", "kernel": dom["call"], "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                        "frac": dom["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
-                        "share_of_step": dom["share"]}
+                        "frac": dom["frac_hbm"], "traffic": traffic, "peak_source": peak_src, "share_of_step": dom["share"],
+                        "algorithmic_bytes": "SURVEY.md section 8d per-unit bytes x units per launch (DESIGN.md section 4)"}
+            if "algorithmic_TFLOPs" in dom:
+                roofline.update(tensor_TFLOPs_algorithmic=dom["algorithmic_TFLOPs"], tensor_peak_tf32_measured=round(tf32_peak, 1),
+                                tensor_frac_algorithmic=dom["tensor_frac_algorithmic"],
+                                tensor_frac_issued_3xtf32=dom["tensor_frac_issued_3xtf32"],
+                                note="SURVEY 8d classes the scorer as HBM-bound (35 flop/B): frac = algorithmic bytes / time / measured "
+                                     "copy peak.  The tensor-pipe view of the same launch: 2*P*C*Hd (fwd) or 4*P*C*Hd (bwd) flops counted "
+                                     "once against the TF32 peak measured in this run (torch.matmul, allow_tf32); fp32-grade results "
+                                     "(rel. err <= 1e-4) need the 3xTF32 split, which issues three times that")
         # the graph-attention kernels of one layer (fwd + both backward passes) against the HBM roofline
-        gat = [k for k in kernels if k["call"] in ("msha_gat_fwd", "msha_gat_bwd_rows", "msha_spmm_csc")]
+        gat = [k for k in kernels if k["call"] in GAT_FAMILIES]
         if gat:
-            gb = sum(k["algorithmic_GB"] for k in gat)
-            ms = sum(k["avg_ms"] for k in gat)
-            gat_roofline = {"bound": "hbm", "kernels": [k["call"] for k in gat], "algorithmic_GB_per_layer": round(gb, 3),
-                            "ms_per_layer": round(ms, 4), "achieved": round(gb / ms * 1e3, 1), "peak": hbm_peak,
-                            "unit": "GB/s", "frac": round(gb / ms * 1e3 / hbm_peak, 4),
-                            "note": "feature matrix (N*C*4 B) is L2-resident on this workload: fraction can exceed 1"}
-        else:
-            gat_roofline = None
+            gb = (ab["msha_gat_fwd"] + ab["msha_gat_bwd_rows"] + ab["msha_spmm_csc"]) / 1e9
+            ms = sum(k["avg_ms"] * k["launches_per_step"] for k in gat) / L
+            feat_mb = part.n_padded * wl["hidden"] * 4 / 1e6
+            gat_roofline = {"bound": "hbm" if feat_mb > 126 else "l2", "kernels": [k["call"] for k in gat],
+                            "algorithmic_GB_per_layer": round(gb, 3), "ms_per_layer": round(ms, 4),
+                            "achieved": round(gb / ms * 1e3, 1), "peak": hbm_peak, "unit": "GB/s",
+                            "frac": round(gb / ms * 1e3 / hbm_peak, 4),
+                            "note": (f"feature table {feat_mb:.0f} MB " + ("exceeds the 126 MB L2: an HBM figure" if feat_mb > 126 else
+                                     "is L2-resident: the gathers are served by L2, this is NOT an HBM fraction (it can exceed 1)"))}
+    parity = parity_block(mg, mdist, model, x, graph, part, world, dev)
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     total_edges = E_global * L
+    bwd_kind = ("separate nll_loss op + tensor-core backward (dense d scores written and re-read)" if args.unfused_loss else
+                "contraction-free: d scores of the nll read-out is one-hot per pair, dZ = g_p * W0[label], dW0 a per-label sum" if args.contraction_free else
+                "general tensor-core backward (dZ = G @ W0, dW0 = G^T @ Z on tcgen05), nll gradient generated in-kernel")
     out = {
         "metric": "gat_fwd_bwd_layer_edges_per_sec", "value": total_edges / (ms_dev / 1e3), "unit": "edges/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_dev, "higher_is_better": True,
         "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n_glob} nodes, {E_global} directed edges ({wl['graph']}), F={wl['feat']}, "
-                               f"{L}-layer {wl['heads']}-head GAT C={wl['hidden']} + LinkPredictor(mlp,{wl['hidden']},"
-                               f"{wl['pred_hidden']}) over P={P_global} pairs (positives + as many Philox negatives), nll loss, Adam",
-                   "per_gpu": ("whole graph on one GPU" if world == 1 else
-                               f"{'strong' if strong else 'weak'} scaling: graph of {n_glob} nodes / {E_global} edges partitioned by destination-node range, "
-                               "per layer one NCCL all-gather (fwd) + reduce-scatter (bwd) of [Wh|s_nbr]; pairs data-parallel; "
-                               "parameter gradients all-reduced"),
-                   "l2_policy": "per-step working set (>= 4*P*pred_hidden bytes of scores) exceeds the 126 MB L2; no explicit flush",
-                   "scorer_backward": ("separate nll_loss op + tensor-core backward" if args.unfused_loss else
-                                       "tensor-core backward with the nll gradient generated in-kernel" if not mg.functional.SPARSE_NLL_BWD else
-                                       "contraction-free: d scores of the nll read-out is one-hot per pair, so dZ = g_p * W0[label] and "
-                                       "dW0 is a per-label sum (same gradients as the dense GEMMs, --dense-nll-bwd runs those)")},
+        "config": workload_config(wl_name, wl, n_glob, E_global, P_global),
+        "per_gpu": ("whole graph on one GPU" if world == 1 else
+                    f"{'strong' if strong else 'weak'} scaling: graph of {n_glob} nodes / {E_global} edges partitioned by destination-node "
+                    f"range; per layer the gather of [Wh | s_nbr] (fwd) and the reduce-scatter of their gradients (bwd) "
+                    + ("over NVLink peer memory: own flag kernels + copy-engine / SM pulls, pipelined under the attention kernels for "
+                       "large blocks (msha_gnn_b200/peer.py, dist.py)" if use_p2p else "as NCCL all_gather / reduce_scatter")
+                    + "; pairs data-parallel; parameter gradients all-reduced (NCCL)"),
+        "scorer_backward": bwd_kind,
         "pairs_per_sec": P_global / (ms_dev / 1e3),
         "e2e": {"value": total_edges / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(pos_host.numel() * 8), "d2h_bytes_per_step": 4,
@@ -486,13 +605,56 @@ def run_ours(args):
         "roofline": roofline,
         "gat_layer_roofline": gat_roofline,
         "kernels": kernels,
+        "parity": parity,
         "loss": loss_host,
     }
-    if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_baseline(args, wl, rows, cols)
+    if variant is not None:
+        out["contraction_free_scorer_backward"] = {
+            "ms_per_step": ms_var, "value": total_edges / (ms_var / 1e3), "unit": "edges/s",
+            "note": "same step with msha_score_mlp_nll_bwd_sparse (MSHA_NLL_BWD=sparse, the library default): exploits the one-hot "
+                    "d scores of F.nll_loss; not the general backward, hence reported beside the headline"}
+    if full and not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(args, wl, rows_h, cols_h, subsampled=strong)
+    return out
 
-    print(json.dumps(out))
+
+def workload_config(name, wl, n_glob, E_global, P_global):
+    """config of the JSON line -- identical for the GPU and the reference arm (same workload, same wording)."""
+    return {"workload": f"{name}: {n_glob} nodes, {E_global} directed edges ({wl['graph']}), F={wl['feat']}, "
+                        f"{wl['layers']}-layer {wl['heads']}-head GAT C={wl['hidden']} + LinkPredictor(mlp,{wl['hidden']},"
+                        f"{wl['pred_hidden']}) over P={P_global} pairs (positives + as many Philox negatives), nll loss, Adam",
+            "dropout": 0.0,
+            "l2_policy": "per-step working set (>= 4*P*pred_hidden bytes of scores) exceeds the 126 MB L2; no explicit flush"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = run_job(args, args.workload, args.steps, args.warmup, full=True)
+    # BASELINE.json configs[3] next to the headline: the 100 M-edge R-MAT graph on the same N GPUs (north-star: >= 6x from
+    # 1 to 8 GPUs, strong scaling).  Fewer steps: a step is 50-300 ms.
+    if args.workload == "ddi" and not args.no_strong_scaling:
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            ss = run_job(args, "rmat", max(3, min(args.steps, 5)), 3, full=False)
+            if rank == 0:
+                keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "per_gpu",
+                        "pairs_per_sec", "e2e", "gpu_launches", "gat_layer_roofline", "kernels", "parity", "loss")
+                out["strong_scaling"] = {k: ss[k] for k in keep if k in ss}
+        except Exception as e:      # noqa: BLE001
+            if rank == 0:
+                out["strong_scaling"] = {"error": repr(e)[:400]}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -834,103 +996,122 @@ def flow_cpu_baseline(src, dst, N, M, B, reps=2):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (torch CPU, fp32, all host threads) on a bounded sample of the workload
 # ------------------------------------------------------------------------------------------------
-def cpu_step_time(wl, rows, cols, pair_sample, reps=1, dtype=torch.float32):
-    from oracle import msha_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    N, Fin, C, H, L, Hd = wl["n_nodes"], wl["feat"], wl["hidden"], wl["heads"], wl["layers"], wl["pred_hidden"]
-    rowptr, col, _ = O.csr_from_coo(rows, cols, N, N)
-    E = col.size
-    g = torch.Generator().manual_seed(0)
-    x = torch.rand(N, Fin, generator=g, dtype=dtype, requires_grad=True)
-    Ws = [torch.randn(Fin if l == 0 else C, C, generator=g, dtype=dtype).mul_(0.1).requires_grad_(True) for l in range(L)]
-    an = [torch.randn(H, C // H, generator=g, dtype=dtype).mul_(0.1).requires_grad_(True) for _ in range(L)]
-    as_ = [torch.randn(H, C // H, generator=g, dtype=dtype).mul_(0.1).requires_grad_(True) for _ in range(L)]
-    W0 = torch.randn(Hd, C, generator=g, dtype=dtype).mul_(0.1).requires_grad_(True)
-    b0 = torch.zeros(Hd, dtype=dtype, requires_grad=True)
-    W1 = torch.zeros(1, Hd, dtype=dtype)
-    Ps = min(pair_sample, 2 * E)
-    src = torch.randint(0, N, (Ps,), generator=g)
-    dst = torch.randint(0, N, (Ps,), generator=g)
-    lab = torch.randint(0, 2, (Ps,), generator=g)
-    orig_t = O._t
-    O._t = lambda a, dt=dtype: orig_t(a, dt)
-    try:
-        t_gat = t_score = 0.0
-        for _ in range(reps):
+class CpuStep:
+    """The oracle port (torch CPU fp32 sparse restatement, all host threads) of the same training step: L GAT layers,
+    LinkPredictor scoring of a pair sample, nll read-out, backward, Adam (train.py:221-232 / LLP.py:221-246 shape)."""
+
+    def __init__(self, wl, rows, cols, pair_sample, dtype=torch.float32):
+        from oracle import msha_oracle as O
+        self.O = O
+        torch.set_num_threads(os.cpu_count() or 1)
+        N, Fin, C, H, L, Hd = wl["n_nodes"], wl["feat"], wl["hidden"], wl["heads"], wl["layers"], wl["pred_hidden"]
+        self.H, self.L, self.dtype = H, L, dtype
+        self.rowptr, self.col, _ = O.csr_from_coo(rows, cols, N, N)
+        self.E = self.col.size
+        g = torch.Generator().manual_seed(0)
+        self.x = torch.rand(N, Fin, generator=g, dtype=dtype, requires_grad=True)
+        self.Ws = [torch.randn(Fin if l == 0 else C, C, generator=g, dtype=dtype).mul_(0.1).requires_grad_(True) for l in range(L)]
+        self.an = [torch.randn(H, C // H, generator=g, dtype=dtype).mul_(0.1).requires_grad_(True) for _ in range(L)]
+        self.as_ = [torch.randn(H, C // H, generator=g, dtype=dtype).mul_(0.1).requires_grad_(True) for _ in range(L)]
+        self.W0 = torch.randn(Hd, C, generator=g, dtype=dtype).mul_(0.1).requires_grad_(True)
+        self.b0 = torch.zeros(Hd, dtype=dtype, requires_grad=True)
+        self.W1 = torch.zeros(1, Hd, dtype=dtype)
+        self.Ps = min(pair_sample, 2 * self.E)
+        self.src = torch.randint(0, N, (self.Ps,), generator=g)
+        self.dst = torch.randint(0, N, (self.Ps,), generator=g)
+        self.lab = torch.randint(0, 2, (self.Ps,), generator=g)
+        self.leaves = [self.x] + self.Ws + self.an + self.as_ + [self.W0, self.b0]
+        self.opt = torch.optim.Adam(self.leaves, lr=1e-3, weight_decay=5e-4)          # train.py:207
+
+    def step(self):
+        """-> (seconds in the GAT layers fwd+bwd, seconds in scoring + loss fwd+bwd, seconds in Adam)"""
+        O, dtype = self.O, self.dtype
+        orig_t = O._t
+        O._t = lambda a, dt=dtype: orig_t(a, dt)
+        try:
             t0 = time.perf_counter()
-            h = x
-            for l in range(L):
-                h = O.gat_layer(h, Ws[l], an[l], as_[l], rowptr, col, H)
+            h = self.x
+            for l in range(self.L):
+                h = O.gat_layer(h, self.Ws[l], self.an[l], self.as_[l], self.rowptr, self.col, self.H)
             t1 = time.perf_counter()
-            out = O.link_predictor(h[src], h[dst], [W0, W1], [b0, torch.zeros(1, dtype=dtype)])
-            loss = torch.nn.functional.nll_loss(out, lab)
+            out = O.link_predictor(h[self.src], h[self.dst], [self.W0, self.W1], [self.b0, torch.zeros(1, dtype=dtype)])
+            loss = torch.nn.functional.nll_loss(out, self.lab)
             t2 = time.perf_counter()
-            gs = torch.autograd.grad(loss, [h, W0, b0])
+            gs = torch.autograd.grad(loss, [h, self.W0, self.b0])
             t3 = time.perf_counter()
-            torch.autograd.grad(h, [x] + Ws + an + as_, gs[0])
+            gl = torch.autograd.grad(h, [self.x] + self.Ws + self.an + self.as_, gs[0])
             t4 = time.perf_counter()
-            t_gat += (t1 - t0) + (t4 - t3)
-            t_score += (t2 - t1) + (t3 - t2)
-    finally:
-        O._t = orig_t
-    return t_gat / reps, t_score / reps, E, Ps
+            for p_, g_ in zip(self.leaves, list(gl) + [gs[1], gs[2]]):
+                p_.grad = g_
+            self.opt.step()
+            t5 = time.perf_counter()
+        finally:
+            O._t = orig_t
+        return (t1 - t0) + (t4 - t3), (t2 - t1) + (t3 - t2), t5 - t4
 
 
-def cpu_baseline(args, wl, rows, cols):
-    if wl["n_edges"] > 5_000_000:      # 1 % node-induced subsample for the big graphs
-        keep = (rows % 100 == 0) & (cols % 100 == 0)
+def cpu_steps(wl, rows, cols, steps, warmup, subsampled, pair_sample=131072):
+    """`warmup` untimed + `steps` timed CPU steps on a bounded sample of the workload -> cpu_baseline dict (value = the
+    whole-workload rate the sample extrapolates to, from the mean step)."""
+    if subsampled:
         sub_n = wl["n_nodes"] // 100 + 1
         wl = dict(wl, n_nodes=sub_n)
-        rows, cols = rows[keep] // 100, cols[keep] // 100
-        sample_note = "1% node-induced subsample of the graph; "
+        sample_note = "1% node-induced subsample of the graph (every 100th node id); "
     else:
         sample_note = "full graph for the GAT layers; "
-    # untimed warm-up on a sliver of the graph (first-call initialisation of the torch CPU thread pools)
-    m = (rows < 256) & (cols < 256)
-    cpu_step_time(dict(wl, n_nodes=256), rows[m], cols[m], pair_sample=1024)
-    t_gat, t_score, E, Ps = cpu_step_time(wl, rows, cols, pair_sample=131072)
+    m = (rows < 256) & (cols < 256)        # first-call initialisation of the torch CPU thread pools, off the clock
+    CpuStep(dict(wl, n_nodes=256), rows[m], cols[m], pair_sample=1024).step()
+    job = CpuStep(wl, rows, cols, pair_sample)
+    for _ in range(warmup):
+        job.step()
+    ts = [job.step() for _ in range(steps)]
+    t_gat, t_score, t_adam = (float(np.mean([t[k] for t in ts])) for k in range(3))
+    E, Ps = job.E, job.Ps
     P = 2 * E
-    t_step = t_gat + t_score * (P / Ps)
+    t_step = t_gat + t_score * (P / Ps) + t_adam
     return {"value": E * wl["layers"] / t_step, "unit": "edges/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": sample_note + f"scoring timed on {Ps} of {P} pairs and scaled; oracle port (sparse restatement, "
-                      f"torch CPU fp32); gat {t_gat:.2f}s + score {t_score:.2f}s measured",
+            "sample": sample_note + f"scoring timed on {Ps} of {P} pairs and scaled; oracle port (sparse restatement, torch CPU "
+                      f"fp32, {os.cpu_count()} threads); mean of {steps} steps after {warmup} warm-up: gat {t_gat:.2f}s + score "
+                      f"{t_score:.2f}s (sample) + Adam {t_adam:.3f}s",
             "ms_per_step_est": t_step * 1e3}
 
 
-def reference_workload_name(name, wl, rows, cols):
-    """The GPU arm's config.workload string (run_ours) rebuilt from the host-side graph: same workload, same wording."""
-    n = wl["n_nodes"]
-    if rows.size <= 20_000_000:
-        E = int(np.unique(rows.astype(np.int64) * n + cols.astype(np.int64)).size)      # Graph.from_coo coalesces duplicates
-    else:
-        E = int(rows.size)                                                             # not coalesced here (a 100 M-key sort)
-    n_pos = wl["pos_pairs"] or E
-    return (f"{name}: {n} nodes, {E} directed edges ({wl['graph']}), F={wl['feat']}, {wl['layers']}-layer {wl['heads']}-head "
-            f"GAT C={wl['hidden']} + LinkPredictor(mlp,{wl['hidden']},{wl['pred_hidden']}) over P={2 * n_pos} pairs "
-            "(positives + as many Philox negatives), nll loss, Adam")
+def cpu_baseline(args, wl, rows, cols, subsampled=False):
+    return cpu_steps(wl, rows, cols, steps=2, warmup=1, subsampled=subsampled)
 
 
 def run_reference(args):
+    """CPU arm on the GPU arm's config: the same workload at the same N (weak scaling: the N-times larger graph is N
+    copies of one rank's share, so one share is timed and the rate is the share's rate -- the CPU does not scale with N)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload]
-    rows, cols = make_graph_host(wl)
-    times = []
-    n = max(1, min(args.steps, 3))
-    for i in range(min(args.warmup, 1) + n):
-        cb = cpu_baseline(args, wl, rows, cols)
-        if i >= min(args.warmup, 1):
-            times.append(cb)
-    best = max(times, key=lambda c: c["value"])
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    out = {"impl": "reference", "metric": "gat_fwd_bwd_layer_edges_per_sec", "value": best["value"], "unit": "edges/s",
-           "n_gpus": world, "steps": n, "warmup": min(args.warmup, 1), "ms_per_step": best["ms_per_step_est"],
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": reference_workload_name(args.workload, wl, rows, cols),
-                      "per_gpu": "CPU arm: oracle port on the host cores (rank 0 only), bounded sample -- see cpu_baseline.sample"},
-           "cpu_baseline": best,
-           "e2e": {"value": best["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    wl = WORKLOADS[args.workload]
+    strong = wl["graph"].startswith("R-MAT")
+    if strong:
+        dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+        r, c = rmat_graph_device(wl["n_nodes"], wl["n_edges"], 4, dev)
+        E_glob = int(torch.unique(r * wl["n_nodes"] + c).numel())
+        keep = (r % 100 == 0) & (c % 100 == 0)
+        rows, cols = (r[keep] // 100).cpu().numpy(), (c[keep] // 100).cpu().numpy()
+        n_glob, n_pos = wl["n_nodes"], min(int(r.numel()), wl["pos_pairs"] // world) * world
+        del r, c, keep
+    else:
+        rows, cols = make_graph_host(wl)
+        E1 = int(np.unique(rows.astype(np.int64) * wl["n_nodes"] + cols.astype(np.int64)).size)   # Graph.from_coo coalesces
+        E_glob, n_glob, n_pos = E1 * world, wl["n_nodes"] * world, int(rows.size) * world
+    warm = max(0, min(args.warmup, 3))
+    cb = cpu_steps(wl, rows, cols, steps=max(1, args.steps), warmup=warm, subsampled=strong,
+                   pair_sample=(2 * rows.size if args.full_pairs else 131072))
+    if world > 1 and not strong:
+        cb["sample"] += f"; weak scaling at N={world}: one rank's share of the {world}x graph timed (the host does not scale with N)"
+    out = {"impl": "reference", "metric": "gat_fwd_bwd_layer_edges_per_sec", "value": cb["value"], "unit": "edges/s",
+           "n_gpus": world, "steps": max(1, args.steps), "warmup": warm, "ms_per_step": cb["ms_per_step_est"] * (1 if strong else world),
+           "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": workload_config(args.workload, wl, n_glob, E_glob, 2 * n_pos),
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
 
@@ -944,9 +1125,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true",
                     help="flow / flow-ours / yearly: launch every kernel from the host instead of replaying one captured CUDA graph")
-    ap.add_argument("--dense-nll-bwd", action="store_true",
-                    help="scorer backward on the tensor cores even under the nll read-out (default: the contraction-free "
-                         "kernel that exploits the one-hot d scores)")
+    ap.add_argument("--contraction-free", action="store_true",
+                    help="headline step with the contraction-free scorer backward (exploits the one-hot d scores of the nll "
+                         "read-out); default: the general tensor-core backward, the contraction-free step reported beside it")
+    ap.add_argument("--dense-nll-bwd", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: exchange over NVLink peer memory with this library's kernels (default) or NCCL collectives")
+    ap.add_argument("--no-strong-scaling", action="store_true",
+                    help="skip the R-MAT (BASELINE.json configs[3]) block the default workload appends to its line")
+    ap.add_argument("--full-pairs", action="store_true", help="--impl reference: score every pair instead of a 131072-pair sample")
     ap.add_argument("--unfused-loss", action="store_true",
                     help="separate nll_loss op: the dense d scores tensor is written and re-read (default: fused into the scorer backward)")
     args = ap.parse_args()

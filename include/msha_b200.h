@@ -88,9 +88,10 @@ int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_rows, cons
                  int act, float* lse_out, float drop_p, uint64_t drop_seed, const msha_hub_t* hub, float* hub_scratch,
                  void* stream);
 /* Partitioned forward (no reference counterpart, train.py:18 is single-device): the same arithmetic as
- * msha_gat_fwd split into (1) the row log-sum-exp of the logits, which needs only the H scores per node, and (2) one
- * aggregation pass per owner block of columns -- edges [rowbeg[i], rowend[i]) of row i -- so that a block is consumed as
- * soon as its feature rows have arrived from the owning GPU.  alpha = exp(logit - lse) is final in every block.
+ * msha_gat_fwd split into (1) the row statistics of the logits -- lse[row] = (H maxima, H sums of exp(e - max)), float[n_rows,
+ * 2, H] --, which need only the H scores per node, and (2) one aggregation pass per owner block of columns -- edges
+ * [rowbeg[i], rowend[i]) of row i -- so that a block is consumed as soon as its feature rows have arrived from the owning
+ * GPU.  alpha = exp(logit - max) / sum is final in every block (the fused kernel's own expression).
  * H a power of two <= 32, D % 4 == 0.  hub_scratch of the stats call: float[2 * H * hub->n_segs]. */
 int msha_gat_softmax_stats(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
                            const float* s_self, int H, float slope, float* lse, const msha_hub_t* hub,

@@ -13,6 +13,7 @@
 // loads), VPL vectors per lane.  Per-edge weights of the current 32-edge chunk are staged in shared memory.
 // Masked edges (col < 0, j = ~col) are the reference's isolated-row semantics: logit = -9e15, no gradient.
 #include "common.cuh"
+#include <stdlib.h>
 
 MSHA_DEFINE_DROP_EPOCH_HOOK(gat)
 #include "msha_b200.h"
@@ -67,8 +68,8 @@ struct DropArgs {
 // the slots whose neighbour lives in one owner block --, the softmax statistics come in as the row's log-sum-exp over
 // ALL its edges (gat_stats_kernel), alpha = exp(logit - lse) is final, and the aggregate is added to `out`
 // (accumulate != 0: read-modify-write; hub segments: atomics) so that the blocks can be processed as they arrive.
-template <int VW, int VPL, bool PIPE = false>
-__global__ void __launch_bounds__(GAT_THREADS)
+template <int VW, int VPL, bool PIPE = false, int WPC = GAT_WARPS, int MINB = 1, int UNR = 4>
+__global__ void __launch_bounds__(WPC * 32, MINB)
 gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowend,
                const int32_t* __restrict__ col, int n_rows,
                const float* __restrict__ s_nbr, const float* __restrict__ s_self,
@@ -78,7 +79,7 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ r
                float* __restrict__ part, const float* __restrict__ lse_in = nullptr, int accumulate = 0) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * GAT_WARPS + warp;
+    const int w = blockIdx.x * WPC + warp;
     int row, beg, end, seg = -1;
     if (w < n_rows) {
         row = w; beg = rowptr[row]; end = rowend[row];
@@ -108,7 +109,11 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ r
     const int hh = lane & (H - 1), es = hp2 ? lane / H : 0, EPI = hp2 ? 32 / H : 1;
     float m_stat = 0.f, l_stat = 1.f;
     if (PIPE) {
-        m_stat = lse_in[(int64_t)row * H + hh];          // hp2 only (checked on the host): a = exp(lg - lse), final
+        // hp2 only (checked on the host).  The row's (max, sum) over ALL its edges: a = exp(lg - m) / l is the very
+        // expression of the fused kernel -- a log-sum-exp would bias sum_j alpha_ij by ~1e-6 (one rounding of m + log l
+        // shared by the whole row), which the softmax backward turns into a spurious d s_self = r_i (1 - sum alpha).
+        m_stat = lse_in[(int64_t)row * 2 * H + hh];
+        l_stat = lse_in[(int64_t)row * 2 * H + H + hh];
     } else if (alpha_in == nullptr && hp2) {
         const float ss = s_self[(int64_t)row * H + hh];
         float m = -INFINITY, l = 0.f;
@@ -149,7 +154,7 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ r
         if (!part_mode && lse_out != nullptr && lane < H)
             lse_out[(int64_t)row * H + lane] = (end > beg) ? m_stat + logf(l_stat) : -INFINITY;
     }
-    int* sm_j = reinterpret_cast<int*>(smem + GAT_WARPS * 32 * H) + warp * 32;     // neighbour ids of the current chunk
+    int* sm_j = reinterpret_cast<int*>(smem + WPC * 32 * H) + warp * 32;     // neighbour ids of the current chunk
 
     float acc[VPL][VW];
 #pragma unroll
@@ -175,7 +180,7 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ r
                     } else {
                         const float lg = masked ? NEG_MASK_F
                                                 : lrelu(__ldg(s_nbr + (int64_t)jj * H + hh) + s_self[(int64_t)row * H + hh], slope);
-                        a = (part_mode || PIPE) ? expf(lg - m_stat) : expf(lg - m_stat) / l_stat;
+                        a = (part_mode && !PIPE) ? expf(lg - m_stat) : expf(lg - m_stat) / l_stat;
                         if (alpha_out) alpha_out[(int64_t)e * H + hh] = a;            // coalesced
                     }
                     if (drop.thr) a *= dropout_scale(drop.seed, drop.stream, (uint64_t)e * H + hh, drop.thr, drop.inv_keep);
@@ -210,7 +215,7 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ r
         }
         __syncwarp();
         const int cnt = min(32, end - e0);
-#pragma unroll 4
+#pragma unroll UNR
         for (int t = 0; t < cnt; ++t) {
             const int jt = sm_j[t];
             const float* f = feat + (int64_t)jt * C;
@@ -343,8 +348,8 @@ __global__ void gat_fwd_rescale_kernel(HubArgs hub, const float* __restrict__ pa
 // LPH_T > 0 (VW == 4, no dT/fT term): lanes per head known at compile time -- the per-edge dot products of EB edges are
 // reduced together by a transposing butterfly (EB/2 + EB/4 + ... shuffles for EB edges instead of log2(LPH) each) and
 // every (edge, head) sum is stored once, by the lane that ends up owning it.
-template <int VW, int VPL, int EB, int MINB, int LPH_T = 0>
-__global__ void __launch_bounds__(GAT_THREADS, MINB)
+template <int VW, int VPL, int EB, int MINB, int LPH_T = 0, int WPC = GAT_WARPS>
+__global__ void __launch_bounds__(WPC * 32, MINB)
 gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_rows,
                     const float* __restrict__ s_nbr, const float* __restrict__ s_self, float slope,
                     const float* __restrict__ alpha, const float* __restrict__ feat,
@@ -358,7 +363,7 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
     // phase 2 (softmax / LeakyReLU backward with the complete r, partial d s_self -> atomics)
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * GAT_WARPS + warp;
+    const int w = blockIdx.x * WPC + warp;
     int row, beg, end;
     if (mode == 0) {
         if (w >= n_rows) return;
@@ -657,8 +662,8 @@ gat_bwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
 // ---------------------------------------------------------------------------------------------
 // column pass (CSC + perm)
 // ---------------------------------------------------------------------------------------------
-template <int VW, int VPL>
-__global__ void __launch_bounds__(GAT_THREADS)
+template <int VW, int VPL, int WPC = GAT_WARPS, int MINB = 1, int UNR = 4>
+__global__ void __launch_bounds__(WPC * 32, MINB)
 spmm_csc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowidx,
                 const int32_t* __restrict__ perm, int n_cols,
                 const float* __restrict__ w, const float* __restrict__ feat, int H, int D,
@@ -666,7 +671,7 @@ spmm_csc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ 
                 const float* __restrict__ esum_in, float* __restrict__ esum_out, DropArgs drop, HubArgs hub) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w0 = blockIdx.x * GAT_WARPS + warp;
+    const int w0 = blockIdx.x * WPC + warp;
     int cidx, beg, end;
     bool part_mode = false;
     if (w0 < n_cols) {
@@ -716,7 +721,7 @@ spmm_csc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ 
         __syncwarp();
         if (w) {
             const int cnt = min(32, end - k0);
-#pragma unroll 4
+#pragma unroll UNR
             for (int t = 0; t < cnt; ++t) {
                 const int it = __shfl_sync(FULL_MASK, i, t);
                 const float* f = feat + (int64_t)it * C;
@@ -808,6 +813,38 @@ static DropArgs make_drop(float p, uint64_t seed, uint32_t stream) {
     else if (VWv == 1 && VPLv == 4) { CALL(1, 4); }             \
     else { CALL(1, 8); }
 
+// Warps per CTA of the three edge kernels on the 256-channel layout.  A CTA lives as long as its longest row: on power-law
+// graphs 8 consecutive rows per CTA leave most warps of a resident CTA finished and idle behind one long row (ncu, round
+// 1: 17 % of the warp slots active in the row pass).  Fewer warps per CTA free the slots as rows finish.
+// Measured on the 100 M-edge R-MAT graph (profiles/r02_gat_variant_sweep.txt): 8 -> 1 warps per CTA together with the
+// register budget of 32 resident warps per SM takes the row pass from 38.3 to 15.4 ms, the column pass from 26.3 to 12.9 ms
+// and the forward from 24.4 to 19.6 ms per layer.  MSHA_GAT_WPC = 1 (default) | 2 | 8, MSHA_GAT_ROWS_EB = 4 (default) | 8 | 2,
+// MSHA_GAT_FWD_VAR / MSHA_GAT_CSC_VAR = 3 (default: 2 edges unrolled, 32 CTAs / SM) | 0 | 1 | 2 -- tuning knobs, read once.
+static int gat_wpc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MSHA_GAT_WPC");
+        v = e ? atoi(e) : 1;
+        if (v != 8 && v != 2) v = 1;
+    }
+    return v;
+}
+static int gat_env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static int gat_fwd_var() { static int v = -1; if (v < 0) v = gat_env_int("MSHA_GAT_FWD_VAR", 3); return v; }
+static int gat_csc_var() { static int v = -1; if (v < 0) v = gat_env_int("MSHA_GAT_CSC_VAR", 3); return v; }
+static int gat_rows_eb() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MSHA_GAT_ROWS_EB");
+        v = e ? atoi(e) : 4;
+        if (v != 8 && v != 2) v = 4;
+    }
+    return v;
+}
+
 // host view of the hub description (include/msha_b200.h: msha_hub_t)
 struct msha_hub_host {
     int32_t seg_limit, n_segs;
@@ -851,13 +888,26 @@ MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_r
     MSHA_REQUIRE(hub.n_segs == 0 || hub_scratch != nullptr, "gat_fwd: hub rows need scratch");
     MSHA_REQUIRE(hub.n_segs == 0 || alpha_in != nullptr || alpha_out != nullptr, "gat_fwd: hub rows need alpha_out");
     DropArgs drop = make_drop(drop_p, drop_seed, 2u);
-    const unsigned grid = (unsigned)msha_cdiv(n_rows + hub.n_segs, GAT_WARPS);
-    const size_t smem = (size_t)GAT_WARPS * (32 * H + 32) * sizeof(float);
+    const int wpc = (vw == 4 && vpl == 2) ? gat_wpc() : GAT_WARPS;
+    const unsigned grid = (unsigned)msha_cdiv(n_rows + hub.n_segs, wpc);
+    const size_t smem = (size_t)wpc * (32 * H + 32) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(A, B)                                                                                             \
     gat_fwd_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(rowptr, rowptr + 1, col, (int)n_rows, s_nbr, s_self, feat, H, D, \
                                                           slope, alpha_in, alpha_out, out, act, lse_out, drop, hub, hub_scratch)
-    DISPATCH_LAYOUT(vw, vpl, CALL)
+#define CALLWU(W, MB, U)                                                                                                       \
+    gat_fwd_kernel<4, 2, false, W, MB, U><<<grid, W * 32, smem, st>>>(rowptr, rowptr + 1, col, (int)n_rows, s_nbr, s_self, feat, \
+                                                                   H, D, slope, alpha_in, alpha_out, out, act, lse_out, drop, \
+                                                                   hub, hub_scratch)
+#define CALLW(W, MB) CALLWU(W, MB, 4)
+    if (wpc == 1 && gat_fwd_var() == 1) { CALLWU(1, 24, 4); }
+    else if (wpc == 1 && gat_fwd_var() == 2) { CALLWU(1, 16, 8); }
+    else if (wpc == 1 && gat_fwd_var() == 3) { CALLWU(1, 32, 2); }
+    else if (wpc == 1) { CALLW(1, 16); }
+    else if (wpc == 2) { CALLW(2, 8); }
+    else { DISPATCH_LAYOUT(vw, vpl, CALL) }
+#undef CALLW
+#undef CALLWU
 #undef CALL
     MSHA_LAUNCH_OK();
     if (hub.n_hub > 0) {
@@ -876,8 +926,8 @@ MSHA_API int msha_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_r
 // ---------------------------------------------------------------------------------------------
 // partitioned forward (dist.py): softmax statistics first, then one aggregation pass per owner block of columns
 // ---------------------------------------------------------------------------------------------
-// lse[row, h] = log sum_j exp(e_ij) over the whole row (needs only the H scores per node, which are exchanged before the
-// features).  H a power of two <= 32: lanes are (edge slot, head) pairs.  Hub rows: one warp per segment writes a partial
+// stats[row] = (max_j e_ij [H], sum_j exp(e_ij - max) [H]) over the whole row (needs only the H scores per node, which
+// are exchanged before the features).  H a power of two <= 32: lanes are (edge slot, head) pairs.  Hub rows: one warp per segment writes a partial
 // (m, l) pair, gat_stats_merge_kernel folds them.
 __global__ void __launch_bounds__(GAT_THREADS)
 gat_stats_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_rows,
@@ -921,8 +971,9 @@ gat_stats_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
         m = M;
     }
     if (lane < H) {
-        if (seg >= 0) { part[(int64_t)seg * 2 * H + lane] = m; part[(int64_t)seg * 2 * H + H + lane] = l; }
-        else lse_out[(int64_t)row * H + lane] = (end > beg) ? m + logf(l) : -INFINITY;
+        float* o = seg >= 0 ? part + (int64_t)seg * 2 * H : lse_out + (int64_t)row * 2 * H;
+        o[lane] = m;
+        o[H + lane] = l;
     }
 }
 
@@ -937,10 +988,12 @@ __global__ void gat_stats_merge_kernel(HubArgs hub, const float* __restrict__ pa
         const float m = part[(int64_t)s * 2 * H + h];
         if (m != -INFINITY) L += part[(int64_t)s * 2 * H + H + h] * expf(m - M);
     }
-    lse_out[(int64_t)hub.hub_ids[i] * H + h] = M + logf(L);
+    lse_out[(int64_t)hub.hub_ids[i] * 2 * H + h] = M;
+    lse_out[(int64_t)hub.hub_ids[i] * 2 * H + H + h] = L;
 }
 
-// hub_scratch: float[2 * H * hub->n_segs] when the graph has hub rows.  H must be a power of two <= 32.
+// lse: float[n_rows, 2, H] = per row the H maxima then the H sums.  hub_scratch: float[2 * H * hub->n_segs] when the graph
+// has hub rows.  H must be a power of two <= 32.
 MSHA_API int msha_gat_softmax_stats(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* s_nbr,
                                     const float* s_self, int H, float slope, float* lse, const msha_hub_t* hub_p,
                                     float* hub_scratch, void* stream) {
@@ -982,14 +1035,22 @@ MSHA_API int msha_gat_fwd_block(const int32_t* rowbeg, const int32_t* rowend, co
         zero_rows_kernel<<<hub.n_hub, 128, 0, st>>>(out, hub.hub_ids, hub.n_hub, H * D);
         MSHA_LAUNCH_OK();
     }
-    const unsigned grid = (unsigned)msha_cdiv(n_rows + hub.n_segs, GAT_WARPS);
-    const size_t smem = (size_t)GAT_WARPS * (32 * H + 32) * sizeof(float);
+    const int wpc = vpl == 2 ? gat_wpc() : GAT_WARPS;
+    const unsigned grid = (unsigned)msha_cdiv(n_rows + hub.n_segs, wpc);
+    const size_t smem = (size_t)wpc * (32 * H + 32) * sizeof(float);
+#define CALLPW(W, MB)                                                                                                      \
+    gat_fwd_kernel<4, 2, true, W, MB, (W == 1 ? 2 : 4)><<<grid, W * 32, smem, st>>>(rowbeg, rowend, col, (int)n_rows, s_nbr, s_self, feat,    \
+                                                                  H, D, slope, nullptr, alpha_out, out, 0, nullptr, drop,   \
+                                                                  hub, nullptr, lse, accumulate)
 #define CALLP(B)                                                                                                        \
     gat_fwd_kernel<4, B, true><<<grid, GAT_THREADS, smem, st>>>(rowbeg, rowend, col, (int)n_rows, s_nbr, s_self, feat, \
                                                                 H, D, slope, nullptr, alpha_out, out, 0, nullptr, drop, \
                                                                 hub, nullptr, lse, accumulate)
-    if (vpl == 1) { CALLP(1); } else if (vpl == 2) { CALLP(2); } else { CALLP(4); }
+    if (vpl == 2 && wpc == 1) { CALLPW(1, 32); }
+    else if (vpl == 2 && wpc == 2) { CALLPW(2, 8); }
+    else if (vpl == 1) { CALLP(1); } else if (vpl == 2) { CALLP(2); } else { CALLP(4); }
 #undef CALLP
+#undef CALLPW
     MSHA_LAUNCH_OK();
     return 0;
 }
@@ -1012,7 +1073,11 @@ MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_
     HubArgs hub = make_hub(hub_p);
     MSHA_REQUIRE(hub.n_segs == 0 || r_buf != nullptr, "gat_bwd_rows: hub rows need r_buf");
     DropArgs drop = make_drop(drop_p, drop_seed, 2u);
-    const size_t smem = (size_t)GAT_WARPS * (32 * H + 2 * H) * sizeof(float);
+    // 256 channels in 128-bit vectors, no second (dT, fT) term: compile-time lanes-per-head variants
+    const int lph = (vw == 4 && vpl == 2 && dT == nullptr && H * D == 256) ? D / 4 : 0;
+    const int wpc = (lph == 8 || lph == 64) ? gat_wpc() : GAT_WARPS;
+    const int eb = gat_rows_eb();
+    const size_t smem = (size_t)wpc * (32 * H + 2 * H) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     if (hub.n_segs > 0) {
         MSHA_CUDA(cudaMemsetAsync(r_buf, 0, (size_t)n_rows * H * sizeof(float), st));
@@ -1033,23 +1098,29 @@ MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_
                                                                          alpha, feat, dout, out, act, dz_out, dT, fT,    \
                                                                          dalpha_extra, dlse, H, D, dlogit, ds_self,      \
                                                                          drop, hub, mode, r_buf)
-    // 256 channels in 128-bit vectors, no second (dT, fT) term: compile-time lanes-per-head variants
-    const int lph = (vw == 4 && vpl == 2 && dT == nullptr && H * D == 256) ? D / 4 : 0;
-#define CALL_FAST(LPH)                                                                                                   \
-    gat_bwd_rows_kernel<4, 2, 8, 2, LPH><<<grid, GAT_THREADS, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, slope, \
+#define CALL_FASTW(LPH, EBv, MB, W)                                                                                       \
+    gat_bwd_rows_kernel<4, 2, EBv, MB, LPH, W><<<grid, W * 32, smem, st>>>(rowptr, col, (int)n_rows, s_nbr, s_self, slope, \
                                                                           alpha, feat, dout, out, act, dz_out, dT, fT,    \
                                                                           dalpha_extra, dlse, H, D, dlogit, ds_self,      \
                                                                           drop, hub, mode, r_buf)
+#define CALL_FAST(LPH)                                                          \
+    if (wpc == 1 && eb == 2) { CALL_FASTW(LPH, 2, 32, 1); }                     \
+    else if (wpc == 1 && eb == 4) { CALL_FASTW(LPH, 4, 24, 1); }                \
+    else if (wpc == 1) { CALL_FASTW(LPH, 8, 16, 1); }                           \
+    else if (wpc == 2 && eb == 4) { CALL_FASTW(LPH, 4, 12, 2); }                \
+    else if (wpc == 2) { CALL_FASTW(LPH, 8, 8, 2); }                            \
+    else if (eb == 4) { CALL_FASTW(LPH, 4, 3, 8); }                             \
+    else { CALL_FASTW(LPH, 8, 2, 8); }
 #define LAUNCH_ROWS()                                   \
-    if (lph == 8) { CALL_FAST(8); }                     \
-    else if (lph == 64) { CALL_FAST(64); }              \
+    if (lph == 8) { CALL_FAST(8) }                      \
+    else if (lph == 64) { CALL_FAST(64) }               \
     else { DISPATCH_LAYOUT(vw, vpl, CALL) }
-    unsigned grid = (unsigned)msha_cdiv(n_rows, GAT_WARPS);
+    unsigned grid = (unsigned)msha_cdiv(n_rows, wpc);
     int mode = 0;
     LAUNCH_ROWS()
     MSHA_LAUNCH_OK();
     if (hub.n_segs > 0) {
-        grid = (unsigned)msha_cdiv(hub.n_segs, GAT_WARPS);
+        grid = (unsigned)msha_cdiv(hub.n_segs, wpc);
         mode = 1;
         LAUNCH_ROWS()
         MSHA_LAUNCH_OK();
@@ -1061,6 +1132,7 @@ MSHA_API int msha_gat_bwd_rows(const int32_t* rowptr, const int32_t* col, int64_
     }
 #undef LAUNCH_ROWS
 #undef CALL_FAST
+#undef CALL_FASTW
 #undef CALL
     return 0;
 }
@@ -1079,8 +1151,9 @@ MSHA_API int msha_spmm_csc(const int32_t* colptr, const int32_t* rowidx, const i
     if (n_cols == 0) return 0;
     HubArgs hub = make_hub(hub_p);
     DropArgs drop = make_drop(drop_p, drop_seed, 2u);
-    const unsigned grid = (unsigned)msha_cdiv(n_cols + hub.n_segs, GAT_WARPS);
-    const size_t smem = (size_t)GAT_WARPS * (32 * H + H) * sizeof(float);
+    const int wpc = (vw == 4 && vpl == 2) ? gat_wpc() : GAT_WARPS;
+    const unsigned grid = (unsigned)msha_cdiv(n_cols + hub.n_segs, wpc);
+    const size_t smem = (size_t)wpc * (32 * H + H) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     if (hub.n_hub > 0) {
         if (w != nullptr && !accumulate) {
@@ -1095,7 +1168,18 @@ MSHA_API int msha_spmm_csc(const int32_t* colptr, const int32_t* rowidx, const i
 #define CALL(A, B)                                                                                             \
     spmm_csc_kernel<A, B><<<grid, GAT_THREADS, smem, st>>>(colptr, rowidx, perm, (int)n_cols, w, feat, H, D,   \
                                                            out, accumulate, esum_in, esum_out, drop, hub)
-    DISPATCH_LAYOUT(vw, vpl, CALL)
+#define CALLWU(W, MB, U)                                                                                           \
+    spmm_csc_kernel<4, 2, W, MB, U><<<grid, W * 32, smem, st>>>(colptr, rowidx, perm, (int)n_cols, w, feat, H, D,  \
+                                                                out, accumulate, esum_in, esum_out, drop, hub)
+#define CALLW(W, MB) CALLWU(W, MB, 4)
+    if (wpc == 1 && gat_csc_var() == 1) { CALLWU(1, 24, 4); }
+    else if (wpc == 1 && gat_csc_var() == 2) { CALLWU(1, 16, 8); }
+    else if (wpc == 1 && gat_csc_var() == 3) { CALLWU(1, 32, 2); }
+    else if (wpc == 1) { CALLW(1, 16); }
+    else if (wpc == 2) { CALLW(2, 8); }
+    else { DISPATCH_LAYOUT(vw, vpl, CALL) }
+#undef CALLW
+#undef CALLWU
 #undef CALL
     MSHA_LAUNCH_OK();
     return 0;

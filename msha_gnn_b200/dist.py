@@ -535,7 +535,7 @@ class _P2PAttention(torch.autograd.Function):
         N, E = graph.n_rows, col.numel()
         s_nbr_g, Wh_g = exS.buf.local, exW.buf.local
         s_self = s_self.contiguous()
-        lse = torch.empty((N, H), dtype=torch.float32, device=dev)
+        lse = torch.empty((N, 2 * H), dtype=torch.float32, device=dev)      # per row: H maxima, H sums
         alpha = torch.empty((E, H), dtype=torch.float32, device=dev)
         out = torch.empty((N, C), dtype=torch.float32, device=dev)
         hub = graph.hub_rows()

@@ -356,6 +356,26 @@ def gat_layer(x, W, a_nbr, a_self, rowptr, col, heads: int, concat=True, apply_e
     return (out, alpha) if return_alpha else out
 
 
+def gat_layer_rows(x_nodes, W, a_nbr, a_self, self_idx, nbr_ptr, nbr_idx, heads: int, apply_elu=True):
+    """``gat_layer`` restricted to a sample of rows (parity at benchmark scale, SURVEY.md section 8c: "check the GPU
+    result on sampled rows"): ``x_nodes`` (n_sub, F) holds the input features of every node the sampled rows touch,
+    row k of the sample is node ``self_idx[k]`` and attends to ``nbr_idx[nbr_ptr[k]:nbr_ptr[k+1]]`` (indices into
+    ``x_nodes``).  Same arithmetic as above (Ablation.py:262-271 + ``alpha @ h1`` :274); heads concatenated."""
+    x, W, a_nbr, a_self = _t(x_nodes), _t(W), _t(a_nbr), _t(a_self)
+    self_idx = torch.as_tensor(np.asarray(self_idx), dtype=torch.int64)
+    nbr_ptr = np.asarray(nbr_ptr, dtype=np.int64)
+    c = torch.as_tensor(np.asarray(nbr_idx), dtype=torch.int64)
+    K = self_idx.numel()
+    Wh = (x @ W).view(x.shape[0], heads, -1)
+    r = torch.repeat_interleave(torch.arange(K), torch.as_tensor(np.diff(nbr_ptr)))
+    s_nbr = (Wh * a_nbr[None]).sum(-1)
+    s_self = (Wh[self_idx] * a_self[None]).sum(-1)
+    e = F.leaky_relu(s_nbr[c] + s_self[r], 0.2)
+    alpha = segment_softmax(e, r, K)
+    out = torch.zeros((K,) + Wh.shape[1:], dtype=Wh.dtype).index_add(0, r, alpha[:, :, None] * Wh[c]).reshape(K, -1)
+    return F.elu(out) if apply_elu else out
+
+
 # --------------------------------------------------------------------------------------
 # a-6  HGANE.GraphAttentionLayer                                                HGANE.py:37-76
 # --------------------------------------------------------------------------------------

@@ -76,7 +76,7 @@ def test_blockwise_forward_equals_fused_forward(seg_limit, monkeypatch):
     feat = torch.randn(N, C, device=DEV)
     ref_out, ref_alpha = Fn.attention_block(g, s_nbr, s_self, feat, heads=H)
     rp, col = g.attention_csr()
-    lse = torch.empty(N, H, device=DEV)
+    lse = torch.empty(N, 2 * H, device=DEV)
     hub = g.hub_rows()
     assert hub.n_segs > 0                                      # adaptive limit (64) or 16: hub rows either way
     scr = torch.empty(max(1, 2 * H * hub.n_segs), device=DEV)

@@ -67,3 +67,26 @@ def test_csr_from_dense_equals_torch_nonzero_and_attention_edges(c):
     colsum = dense.sum(axis=0)
     want = (dense / np.where(colsum > 0, colsum, 1.0))[dense > 0]
     np.testing.assert_allclose(vals, want, rtol=2e-6)
+
+
+def test_gat_layer_rows_equals_gat_layer_on_the_sampled_rows():
+    """The rows-restricted restatement bench.py's parity block uses == the whole-graph one (itself pinned to the reference's
+    OursLayer3 lines by tests/test_oracle.py::test_generic_gat) on the rows it samples."""
+    import torch
+    from oracle import msha_oracle as O
+    rng = np.random.default_rng(0)
+    N, Fin, H, d = 60, 7, 4, 3
+    adj = (rng.random((N, N)) < 0.15).astype(np.float32)
+    adj[np.arange(N), np.arange(N)] = 1
+    rowptr, col, _ = O.csr_from_dense(adj)
+    x = torch.tensor(rng.standard_normal((N, Fin)))
+    W = torch.tensor(rng.standard_normal((Fin, H * d)))
+    an, as_ = torch.tensor(rng.standard_normal((H, d))), torch.tensor(rng.standard_normal((H, d)))
+    full = O.gat_layer(x, W, an, as_, rowptr, col, H)
+    S = np.array([3, 17, 17, 59, 0])
+    nbrs = [col[rowptr[i]:rowptr[i + 1]] for i in S]
+    nodes, inv = np.unique(np.concatenate(nbrs + [S]), return_inverse=True)
+    nbr_ptr = np.concatenate([[0], np.cumsum([len(n) for n in nbrs])])
+    nbr_idx, self_idx = inv[:nbr_ptr[-1]], inv[nbr_ptr[-1]:]
+    got = O.gat_layer_rows(x[nodes], W, an, as_, self_idx, nbr_ptr, nbr_idx, H)
+    assert torch.allclose(got, full[S], atol=1e-12)

@@ -8,10 +8,13 @@ are excluded: with all logits on one LeakyReLU branch softmax shift-invariance m
 either side in the two summation orders, which moves gradients by ~1e-3 of their norm (the reference has the same
 sensitivity) -- tolerance 5e-3, all parameters included."""
 import os, sys
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")       # peer path: kernels wait on kernels (msha_gnn_b200/peer.py)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import msha_gnn_b200 as mg
 from msha_gnn_b200 import dist as md
+from msha_gnn_b200 import peer
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
@@ -29,6 +32,8 @@ part = md.Partition(N, world, rank)
 keep = (rows >= part.lo) & (rows < part.hi)
 pg = md.partition_graph(torch.from_numpy(rows[keep]).to(dev), torch.from_numpy(cols[keep]).to(dev), part)
 lo, hi = (P * rank) // world, (P * (rank + 1)) // world
+fabric = peer.SymmFabric() if world > 1 else None
+labels = torch.from_numpy(rng.integers(0, 2, P)).to(dev)
 
 
 def rel(a, b):
@@ -52,11 +57,22 @@ for construction, tol in (("positive", 1e-4), ("signed", 5e-3)):
     gref = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}   # the last Linear is never applied
     gx_ref = xf.grad.clone()
     model.zero_grad(set_to_none=True)
-    for overlap in (True, False):
+    modes = [("nccl+early-rs", None), ("nccl", None)]
+    if fabric is not None:
+        modes += [("p2p-flat", (1 << 40, 1 << 40)), ("p2p-pipelined", (0, 0))]
+    for overlap, thresholds in modes:
         xl = x_full[part.lo:part.hi].clone().requires_grad_(True)
-        h = md.gat_encode(model.convs, xl, pg, part, overlap=overlap)
-        out = md.score_pairs(model.predictor, h, src_d[lo:hi], dst_d[lo:hi], part)
+        if thresholds is None:
+            h = md.gat_encode(model.convs, xl, pg, part, overlap=(overlap == "nccl+early-rs"))
+            out = md.score_pairs(model.predictor, h, src_d[lo:hi], dst_d[lo:hi], part)
+        else:
+            md.PIPELINE_MIN_BLOCK_BYTES, peer.CE_MIN_BYTES = thresholds
+            p2p = md.P2P(fabric.group, part)
+            h = md.gat_encode_p2p(model.convs, xl, pg, part, p2p)
+            out = md.score_pairs(model.predictor, h, src_d[lo:hi], dst_d[lo:hi], part, p2p=p2p)
         (out * G[lo:hi]).sum().backward()
+        if thresholds is not None:
+            p2p.pg.check()
         md.allreduce_gradients([p for p in model.parameters() if p.grad is not None], world=world)
         errs = {"out": rel(out.detach(), out_ref.detach()[lo:hi]), "dx": rel(xl.grad, gx_ref[part.lo:part.hi])}
         for n, p in model.named_parameters():
@@ -66,10 +82,31 @@ for construction, tol in (("positive", 1e-4), ("signed", 5e-3)):
         worst = torch.tensor([max(checked.values())], device=dev)
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"{construction:8s} overlap={overlap} world={world} hub_rows={pg.hub_rows().n_hub} worst checked rel err "
+            print(f"{construction:8s} mode={overlap} world={world} hub_rows={pg.hub_rows().n_hub} worst checked rel err "
                   f"{float(worst):.3e} (tol {tol:g})", {k: f"{v:.1e}" for k, v in errs.items()}, flush=True)
         ok = ok and float(worst) < tol
         model.zero_grad(set_to_none=True)
+    # mean nll read-out: the ranks' shares add up to the single-GPU loss, gradients equal the single-GPU ones
+    xf = x_full.clone().requires_grad_(True)
+    hf = model.encode(xf, g_full)
+    loss_ref = model.predictor.nll_loss_pairs(hf, hf, src_d, dst_d, labels)
+    loss_ref.backward()
+    gW_ref, gx_ref2 = model.convs[0].W.grad.clone(), xf.grad.clone()
+    model.zero_grad(set_to_none=True)
+    xl = x_full[part.lo:part.hi].clone().requires_grad_(True)
+    h = md.gat_encode(model.convs, xl, pg, part)
+    loss = md.score_pairs(model.predictor, h, src_d[lo:hi], dst_d[lo:hi], part, target=labels[lo:hi], global_pairs=P)
+    loss.backward()
+    md.allreduce_gradients(list(model.parameters()), world=world)
+    tot = loss.detach().clone()
+    dist.all_reduce(tot)
+    e = torch.tensor([abs(float(tot) - float(loss_ref)) / abs(float(loss_ref)), rel(model.convs[0].W.grad, gW_ref),
+                      rel(xl.grad, gx_ref2[part.lo:part.hi])], device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"{construction:8s} mean-nll over ranks: loss rel err {float(e[0]):.2e}, dW0 {float(e[1]):.2e}, dx {float(e[2]):.2e}", flush=True)
+    ok = ok and float(e.max()) < tol
+    model.zero_grad(set_to_none=True)
 dist.destroy_process_group()
 if rank == 0:
     print("PARITY OK" if ok else "PARITY FAILED", flush=True)
