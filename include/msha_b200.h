@@ -153,6 +153,14 @@ int msha_group_gather_sum(const int32_t* rowptr, const int32_t* col, const int32
                           int64_t B, int64_t n_nodes, const float* dout, int H, int D, float* G, float drop_p,
                           uint64_t drop_seed, uint32_t drop_stream, void* stream);
 
+/* Group-sum form of the intra-scale block (no dropout on the intra attention): attention3[b, n] = coef3[b] for every member
+ * n of the batch row's city (Ours.py:71-75,87), so att3.t() @ h2_ (Ours.py:99) is the same row for all members of a group:
+ * IntraNC[n] = G3[city(n)] + G4[province(n)] with G[g] = sum_{b in group g} coef[b] * h2[src_b].  O(B + N), and a partitioned
+ * graph exchanges only the (n_groups, C) tables.  G is zeroed by the sum; the two calls are each other's backward. */
+int msha_group_rows_sum(const float* x, const int64_t* gid, int64_t n, int64_t C, int64_t n_groups, float* G, void* stream);
+int msha_group_rows_add(float* out, const float* G3, const int64_t* gid3, const float* G4, const int64_t* gid4, int64_t n,
+                        int64_t C, int accumulate, void* stream);
+
 /* ---- activations (F.elu / F.leaky_relu / relu / sigmoid call sites) ---- */
 int msha_act_fwd(const float* x, float* y, int64_t n, int act, float slope, void* stream);
 int msha_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, float slope, void* stream);
@@ -170,6 +178,19 @@ int msha_bn_lrelu_fwd(const float* x, int64_t n, int C, const float* gamma, cons
 int msha_bn_lrelu_bwd(const float* dy, const float* y, const float* x, int64_t n, int C, const float* gamma,
                       const float* save_mean, const float* save_invstd, int training, float slope, float* dx,
                       float* xhat, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+/* The same BatchNorm when the node axis is partitioned over GPUs: statistics pass -> the caller
+ * all-reduces sums (double[2*C]: column sums of x and x^2; backward: of g and g*xhat) over the ranks -> apply pass with the
+ * global row count n_total.  dgamma / dbeta come out global (identical on every rank). */
+int msha_bn_stats(const float* x, int64_t n, int C, double* sums, void* ws, size_t ws_bytes, void* stream);
+int msha_bn_lrelu_apply(const float* x, int64_t n, int C, const double* sums, int64_t n_total, const float* gamma,
+                        const float* beta, float* running_mean, float* running_var, int training, float momentum,
+                        float eps, float slope, float* y, float* save_mean, float* save_invstd, void* stream);
+int msha_bn_lrelu_bwd_stats(const float* dy, const float* y, const float* x, int64_t n, int C, const float* save_mean,
+                            const float* save_invstd, float slope, float* dx, float* xhat, double* sums, void* ws,
+                            size_t ws_bytes, void* stream);
+int msha_bn_lrelu_bwd_apply(float* dx, const float* xhat, int64_t n, int C, const float* gamma, const float* save_invstd,
+                            const double* sums, int64_t n_total, int training, float* dgamma, float* dbeta, void* stream);
 
 /* ---- read-out: log_softmax(elu(x)) rows, Ours.py:166-167 / GAT.py:57-58 ---- */
 int msha_log_softmax_fwd(const float* x, int64_t n, int64_t M, int pre_elu, float* y, void* stream);
@@ -256,6 +277,28 @@ int msha_peer_pull_rows(float* dst, const uint64_t* src_tab, int world, int rank
                         const int64_t* row_ptr, int64_t max_rows_per_peer, int64_t C, int max_ctas, void* stream);
 /* out[i] = sum_k src_ptrs[k][i] in table order; src_ptrs is a HOST array of n_src (<= 32) device addresses */
 int msha_peer_sum(float* out, const uint64_t* src_ptrs, int n_src, int64_t n, int max_ctas, void* stream);
+
+/* Fused exchanges for small blocks: flag waits and the completion signal inside the data kernel (one launch per gather /
+ * reduce-scatter of up to two buffers).  wait: every CTA waits for the flag of the peer it reads (pull) or of all peers
+ * (sum); guard: flags that must hold before this rank may overwrite what its peers read in the opposite direction (checked
+ * by the last CTA); done: published to every peer by the last CTA.  A channel < 0 skips that part.  counter: one device
+ * word, zero on entry, left zero.  dst / src_tab / ... are HOST arrays of n_bufs (1 or 2) entries; src_tab[k] is a device
+ * table uint64[world]. */
+int msha_peer_exchange_pull(int n_bufs, void* const* dst, const uint64_t* const* src_tab, const int64_t* block_bytes,
+                            const int64_t* nbytes, const uint32_t* flags, const uint64_t* flag_tab, int world, int rank,
+                            int wait_ch, uint32_t wait_val, int guard_ch, uint32_t guard_val, int done_ch,
+                            uint32_t done_val, uint64_t timeout_ns, int32_t* status, uint32_t* counter, int max_ctas,
+                            void* stream);
+int msha_peer_exchange_sum(int n_bufs, float* const* out, const uint64_t* const* src_tab, const int64_t* offset_bytes,
+                           const int64_t* n_floats, const uint32_t* flags, const uint64_t* flag_tab, int world, int rank,
+                           int wait_ch, uint32_t wait_val, int guard_ch, uint32_t guard_val, int done_ch, uint32_t done_val,
+                           uint64_t timeout_ns, int32_t* status, uint32_t* counter, int max_ctas, void* stream);
+
+/* all-reduce (sum, rank order) of a small fp64 vector living at offset_bytes of every rank's peer-mapped buffer -- the
+ * BatchNorm column statistics of a partitioned node axis; waits for every peer's flag first */
+int msha_peer_allreduce_f64(double* out, const uint64_t* src_tab, int64_t offset_bytes, int64_t n, const uint32_t* flags,
+                            const uint64_t* flag_tab, int world, int rank, int wait_ch, uint32_t wait_val,
+                            uint64_t timeout_ns, int32_t* status, void* stream);
 
 /* ==== callers either side of the path ==== */
 

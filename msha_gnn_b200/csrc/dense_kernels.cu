@@ -442,6 +442,122 @@ MSHA_API int msha_bn_lrelu_bwd(const float* dy, const float* y, const float* x, 
     return 0;
 }
 
+// ---- the same BatchNorm over a node axis that is partitioned across GPUs ("ncclAllReduce of the
+// tiny BN statistics"): the column sums leave the library between the statistics pass and the apply pass, the caller
+// all-reduces the 2*C doubles over the ranks and passes the GLOBAL row count.  Same kernels as the fused entry points.
+__global__ void bn_sums_kernel(const double* __restrict__ partial, int nblocks, int C, double* __restrict__ sums) {
+    int c;
+    double s1, s2;
+    if (!bn_column_sums(partial, nblocks, C, c, s1, s2)) return;
+    sums[c] = s1;
+    sums[C + c] = s2;
+}
+__global__ void bn_finalize_sums_kernel(const double* __restrict__ sums, int64_t n, int C, int training, float momentum,
+                                        float eps, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                        float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (training) {
+        const double mean = sums[c] / (double)n;
+        double var = sums[C + c] / (double)n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        save_mean[c] = (float)mean;
+        save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean) {
+            const double var_u = n > 1 ? var * (double)n / (double)(n - 1) : var;
+            running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+            running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * var_u);
+        }
+    } else {
+        save_mean[c] = running_mean[c];
+        save_invstd[c] = 1.f / sqrtf(running_var[c] + eps);
+    }
+}
+__global__ void bn_bwd_apply_sums_kernel(float* __restrict__ g_io, const float* __restrict__ xhat, int64_t n, int C,
+                                         const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                         const double* __restrict__ sums, double inv_n_total, int training) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, tot = n * C;
+    for (; i < tot; i += stride) {
+        const int c = (int)(i % C);
+        float g = g_io[i];
+        if (training) g = g - (float)(sums[c] * inv_n_total) - xhat[i] * (float)(sums[C + c] * inv_n_total);
+        g_io[i] = g * gamma[c] * invstd[c];
+    }
+}
+__global__ void bn_sums_to_grads_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
+                                        float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    dbeta[c] = (float)sums[c];
+    dgamma[c] = (float)sums[C + c];
+}
+
+// sums: double[2*C] = (sum_rows x, sum_rows x^2) of the LOCAL rows (n may be 0: zeros)
+MSHA_API int msha_bn_stats(const float* x, int64_t n, int C, double* sums, void* ws, size_t ws_bytes, void* stream) {
+    MSHA_REQUIRE(n >= 0 && C >= 1 && sums != nullptr, "bn_stats: bad arguments");
+    MSHA_REQUIRE(ws_bytes >= msha_bn_workspace_bytes(C), "bn_stats: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int nb = (int)(n < BN_BLOCKS ? n : BN_BLOCKS);
+    if (nb > 0) {
+        bn_partial_kernel<<<nb, 256, 0, st>>>(x, nullptr, n, C, (double*)ws);
+        MSHA_LAUNCH_OK();
+    }
+    bn_sums_kernel<<<(unsigned)msha_cdiv(C, 32), 256, 0, st>>>((const double*)ws, nb, C, sums);
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+// y = lrelu(bn(x)) of the n local rows with the statistics of all n_total rows (sums already reduced over the ranks)
+MSHA_API int msha_bn_lrelu_apply(const float* x, int64_t n, int C, const double* sums, int64_t n_total, const float* gamma,
+                                 const float* beta, float* running_mean, float* running_var, int training, float momentum,
+                                 float eps, float slope, float* y, float* save_mean, float* save_invstd, void* stream) {
+    MSHA_REQUIRE(n >= 0 && C >= 1 && n_total >= 1, "bn_apply: bad shape");
+    MSHA_REQUIRE(training || (running_mean && running_var), "bn_apply: eval mode needs running stats");
+    MSHA_REQUIRE(!training || sums != nullptr, "bn_apply: training mode needs the column sums");
+    cudaStream_t st = (cudaStream_t)stream;
+    bn_finalize_sums_kernel<<<(unsigned)msha_cdiv(C, 128), 128, 0, st>>>(sums, n_total, C, training, momentum, eps, running_mean,
+                                                                        running_var, save_mean, save_invstd);
+    MSHA_LAUNCH_OK();
+    if (n > 0) {
+        bn_apply_kernel<<<ew_grid(n * C), 256, 0, st>>>(x, n, C, save_mean, save_invstd, gamma, beta, slope, y);
+        MSHA_LAUNCH_OK();
+    }
+    return 0;
+}
+// backward, first half: g = dy * lrelu'(y) -> dx (scratch), xhat, and sums = (sum g, sum g*xhat) of the local rows
+MSHA_API int msha_bn_lrelu_bwd_stats(const float* dy, const float* y, const float* x, int64_t n, int C,
+                                     const float* save_mean, const float* save_invstd, float slope, float* dx, float* xhat,
+                                     double* sums, void* ws, size_t ws_bytes, void* stream) {
+    MSHA_REQUIRE(n >= 0 && C >= 1 && sums != nullptr, "bn_bwd_stats: bad arguments");
+    MSHA_REQUIRE(ws_bytes >= msha_bn_workspace_bytes(C), "bn_bwd_stats: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int nb = (int)(n < BN_BLOCKS ? n : BN_BLOCKS);
+    if (n > 0) {
+        bn_bwd_prep_kernel<<<ew_grid(n * C), 256, 0, st>>>(dy, y, x, n, C, save_mean, save_invstd, slope, dx, xhat);
+        MSHA_LAUNCH_OK();
+        bn_partial_kernel<<<nb, 256, 0, st>>>(dx, xhat, n, C, (double*)ws);
+        MSHA_LAUNCH_OK();
+    }
+    bn_sums_kernel<<<(unsigned)msha_cdiv(C, 32), 256, 0, st>>>((const double*)ws, nb, C, sums);
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+// backward, second half with the reduced sums: dx in place, dgamma / dbeta (the global ones, identical on every rank)
+MSHA_API int msha_bn_lrelu_bwd_apply(float* dx, const float* xhat, int64_t n, int C, const float* gamma,
+                                     const float* save_invstd, const double* sums, int64_t n_total, int training,
+                                     float* dgamma, float* dbeta, void* stream) {
+    MSHA_REQUIRE(n >= 0 && C >= 1 && n_total >= 1 && sums != nullptr, "bn_bwd_apply: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    bn_sums_to_grads_kernel<<<(unsigned)msha_cdiv(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
+    MSHA_LAUNCH_OK();
+    if (n > 0) {
+        bn_bwd_apply_sums_kernel<<<ew_grid(n * C), 256, 0, st>>>(dx, xhat, n, C, gamma, save_invstd, sums, 1.0 / (double)n_total,
+                                                                 training);
+        MSHA_LAUNCH_OK();
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // row log_softmax with optional leading ELU (Ours.py:166-167: log_softmax(elu(x)))
 // ---------------------------------------------------------------------------------------------

@@ -162,3 +162,96 @@ MSHA_API int msha_group_gather_sum(const int32_t* rowptr, const int32_t* col, co
     MSHA_LAUNCH_OK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Group-sum form of the same block (no dropout on the intra attention): every member of a group receives the SAME row
+//     IntraNC[n] = G3[city(n)] + G4[province(n)],   G3[g] = sum_{b : city(src_b) = g} coef3[b] * h2[src_b]       Ours.py:99
+// (attention3[b, n] = coef3[b] for every member n of the batch row's city, Ours.py:71-75,87).  O(B + N) work instead of
+// O(B x |group|), and the only thing ranks of a partitioned graph have to exchange is the (n_groups, C) table.
+//   group_rows_sum   G[gid[i]] += x[i]            (forward of the table, backward of the broadcast)
+//   group_rows_add   out[i] (+)= G[gid[i]]        (forward of the broadcast, backward of the table)
+// ---------------------------------------------------------------------------------------------
+constexpr int GRS_THREADS = 256;
+
+// few groups (table fits in shared memory): per-CTA partial table in shared memory, one atomic flush per CTA
+__global__ void __launch_bounds__(GRS_THREADS)
+group_rows_sum_smem_kernel(const float* __restrict__ x, const int64_t* __restrict__ gid, int64_t n, int C, int n_groups,
+                           float* __restrict__ G) {
+    extern __shared__ float sm[];
+    const int tot = n_groups * C;
+    for (int i = threadIdx.x; i < tot; i += GRS_THREADS) sm[i] = 0.f;
+    __syncthreads();
+    const int64_t rows_per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = blockIdx.x * rows_per, r1 = r0 + rows_per < n ? r0 + rows_per : n;
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t g = gid[r];
+        if (g < 0 || g >= n_groups) continue;
+        for (int c = threadIdx.x; c < C; c += GRS_THREADS) atomicAdd(&sm[g * C + c], x[r * C + c]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < tot; i += GRS_THREADS) {
+        const float v = sm[i];
+        if (v != 0.f) atomicAdd(&G[i], v);
+    }
+}
+// many groups: one warp per row, 128-bit vector atomics straight into the (L2-resident) table
+__global__ void __launch_bounds__(GRS_THREADS)
+group_rows_sum_kernel(const float* __restrict__ x, const int64_t* __restrict__ gid, int64_t n, int C4, int n_groups,
+                      float* __restrict__ G) {
+    const int64_t row = ((int64_t)blockIdx.x * GRS_THREADS + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const int64_t g = gid[row];
+    if (g < 0 || g >= n_groups) return;
+    const float4* __restrict__ xr = reinterpret_cast<const float4*>(x) + row * C4;
+    float4* Gr = reinterpret_cast<float4*>(G) + g * C4;
+    for (int c = lane; c < C4; c += 32) atomicAdd(Gr + c, __ldg(xr + c));
+}
+__global__ void __launch_bounds__(GRS_THREADS)
+group_rows_add_kernel(float* __restrict__ out, const float* __restrict__ G3, const int64_t* __restrict__ gid3,
+                      const float* __restrict__ G4, const int64_t* __restrict__ gid4, int64_t n, int C4, int accumulate) {
+    const int64_t idx = (int64_t)blockIdx.x * GRS_THREADS + threadIdx.x;
+    if (idx >= n * C4) return;
+    const int64_t row = idx / C4;
+    const int c = (int)(idx - row * C4);
+    float4 v = __ldg(reinterpret_cast<const float4*>(G3) + gid3[row] * C4 + c);
+    if (G4) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(G4) + gid4[row] * C4 + c);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    float4* o = reinterpret_cast<float4*>(out) + idx;
+    if (accumulate) { const float4 p = *o; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+    *o = v;
+}
+
+// G: float[n_groups, C], zeroed here.  gid: int64[n] group of every row (rows with an id outside [0, n_groups) are skipped).
+MSHA_API int msha_group_rows_sum(const float* x, const int64_t* gid, int64_t n, int64_t C, int64_t n_groups, float* G,
+                                 void* stream) {
+    MSHA_REQUIRE(n >= 0 && C >= 4 && C % 4 == 0 && n_groups >= 1 && G != nullptr, "group_rows_sum: bad shape (C % 4 == 0)");
+    cudaStream_t st = (cudaStream_t)stream;
+    MSHA_CUDA(cudaMemsetAsync(G, 0, (size_t)n_groups * C * sizeof(float), st));
+    if (n == 0) return 0;
+    const size_t tab = (size_t)n_groups * C * sizeof(float);
+    if (tab <= 40 * 1024) {
+        int64_t ctas = msha_cdiv(n, 64);
+        if (ctas > 4 * MSHA_NUM_SMS) ctas = 4 * MSHA_NUM_SMS;
+        group_rows_sum_smem_kernel<<<(unsigned)ctas, GRS_THREADS, tab, st>>>(x, gid, n, (int)C, (int)n_groups, G);
+    } else {
+        group_rows_sum_kernel<<<(unsigned)msha_cdiv(n * 32, GRS_THREADS), GRS_THREADS, 0, st>>>(x, gid, n, (int)(C / 4),
+                                                                                               (int)n_groups, G);
+    }
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+// out[i] (+)= G3[gid3[i]] (+ G4[gid4[i]]); ids must lie inside their tables.
+MSHA_API int msha_group_rows_add(float* out, const float* G3, const int64_t* gid3, const float* G4, const int64_t* gid4,
+                                 int64_t n, int64_t C, int accumulate, void* stream) {
+    MSHA_REQUIRE(n >= 0 && C >= 4 && C % 4 == 0 && out && G3 && gid3, "group_rows_add: bad arguments (C % 4 == 0)");
+    MSHA_REQUIRE((G4 == nullptr) == (gid4 == nullptr), "group_rows_add: G4 and gid4 go together");
+    if (n == 0) return 0;
+    group_rows_add_kernel<<<(unsigned)msha_cdiv(n * (C / 4), GRS_THREADS), GRS_THREADS, 0, (cudaStream_t)stream>>>(
+        out, G3, gid3, G4, gid4, n, (int)(C / 4), accumulate);
+    MSHA_LAUNCH_OK();
+    return 0;
+}

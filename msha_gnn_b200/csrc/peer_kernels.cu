@@ -37,7 +37,7 @@ __global__ void peer_signal_kernel(const uint64_t* __restrict__ flag_tab, int wo
     const int q = threadIdx.x;
     if (q >= world || !((peer_mask >> q) & 1u)) return;
     const uint32_t v = value + (epoch ? *epoch : 0u);
-    __threadfence_system();
+    // release at system scope is cumulative: the writes of the stream's earlier kernels happen-before this store
     uint32_t* f = reinterpret_cast<uint32_t*>(flag_tab[q]) + (int64_t)channel * world + rank;
     st_release_sys(f, v);
 }
@@ -212,6 +212,230 @@ MSHA_API int msha_peer_sum(float* out, const uint64_t* src_ptrs, int n_src, int6
         case 8: peer_sum_kernel<8><<<(unsigned)ctas, 256, 0, st>>>(o, tab, n_src, nvec); break;
         default: peer_sum_kernel<0><<<(unsigned)ctas, 256, 0, st>>>(o, tab, n_src, nvec); break;
     }
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Fused exchanges for the launch-latency regime (small blocks): the flag waits and the completion signal live inside
+// the data kernel, so one gather (or one reduce-scatter) of up to two buffers is ONE launch after the producer's
+// msha_peer_signal -- instead of wait / pull / pull / signal launches and a separate reuse-guard wait.
+//   * every CTA waits only for the peer whose block it copies (gather) / for all peers (sum);
+//   * the last CTA to finish (device counter) additionally waits for `guard` flags -- the peers' completion flags of the
+//     OPPOSITE direction's previous exchange, which must hold before this rank overwrites what they read; checking them
+//     here, long after they were set, replaces a dedicated wait launch -- and then publishes `done` to every peer.
+// ---------------------------------------------------------------------------------------------
+struct PeerFlagOps {
+    const uint32_t* flags;        // this rank's flag array
+    const uint64_t* flag_tab;     // device table of every rank's flag array
+    int world, rank;
+    int wait_ch;  uint32_t wait_val;      // data ready        (wait_ch < 0: none)
+    int guard_ch; uint32_t guard_val;     // reuse guard       (guard_ch < 0: none)
+    int done_ch;  uint32_t done_val;      // completion signal (done_ch < 0: none)
+    uint64_t timeout_ns;
+    int32_t* status;
+    unsigned int* counter;        // zero before the launch; left zero by it
+};
+
+__device__ __forceinline__ bool spin_flag(const uint32_t* f, uint32_t want, uint64_t timeout_ns, int32_t* status, int q) {
+    const uint64_t t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(f) - want) < 0) {
+        __nanosleep(32);
+        if (timeout_ns && globaltimer_ns() - t0 > timeout_ns) {
+            if (status) atomicExch(status, 0x100 | q);
+            return false;
+        }
+    }
+    return true;
+}
+
+// call by all threads of the CTA after its data work: the last CTA of the grid checks the guard and signals completion
+__device__ __forceinline__ void peer_finish(const PeerFlagOps& fo, unsigned int total_ctas) {
+    __shared__ unsigned int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(fo.counter, 1u) == total_ctas - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    const int q = threadIdx.x;
+    if (q < fo.world && q != fo.rank) {
+        if (fo.guard_ch >= 0) spin_flag(fo.flags + (int64_t)fo.guard_ch * fo.world + q, fo.guard_val, fo.timeout_ns, fo.status, q);
+        if (fo.done_ch >= 0) {
+            __threadfence();
+            st_release_sys(reinterpret_cast<uint32_t*>(fo.flag_tab[q]) + (int64_t)fo.done_ch * fo.world + fo.rank, fo.done_val);
+        }
+    }
+    if (threadIdx.x == 0) *fo.counter = 0u;
+}
+
+struct PullBufs { uint4* dst[2]; const uint64_t* tab[2]; int64_t stride_vec[2]; int64_t nvec[2]; };
+
+__global__ void __launch_bounds__(PULL_THREADS)
+peer_exchange_pull_kernel(PullBufs b, PeerFlagOps fo) {
+    const int q = (fo.rank + 1 + blockIdx.y) % fo.world;
+    const int k = blockIdx.z;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0)
+        s_ok = fo.wait_ch < 0 ? 1 : (int)spin_flag(fo.flags + (int64_t)fo.wait_ch * fo.world + q, fo.wait_val, fo.timeout_ns, fo.status, q);
+    __syncthreads();
+    if (s_ok) {
+        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(b.tab[k][q]) + (int64_t)q * b.stride_vec[k];
+        uint4* __restrict__ d = b.dst[k] + (int64_t)q * b.stride_vec[k];
+        const int64_t n = b.nvec[k];
+        const int64_t stride = (int64_t)gridDim.x * PULL_THREADS;
+        int64_t i = (int64_t)blockIdx.x * PULL_THREADS + threadIdx.x;
+        for (; i + (PULL_UNROLL - 1) * stride < n; i += PULL_UNROLL * stride) {
+            uint4 v[PULL_UNROLL];
+#pragma unroll
+            for (int u = 0; u < PULL_UNROLL; ++u) v[u] = src[i + u * stride];
+#pragma unroll
+            for (int u = 0; u < PULL_UNROLL; ++u) d[i + u * stride] = v[u];
+        }
+        for (; i < n; i += stride) d[i] = src[i];
+    }
+    peer_finish(fo, gridDim.x * gridDim.y * gridDim.z);
+}
+
+struct SumBufs { float4* out[2]; const uint64_t* tab[2]; int64_t offset_vec[2]; int64_t nvec[2]; };
+
+__global__ void __launch_bounds__(256)
+peer_exchange_sum_kernel(SumBufs b, PeerFlagOps fo) {
+    const int k = blockIdx.y;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (fo.wait_ch >= 0 && threadIdx.x < fo.world && threadIdx.x != fo.rank) {
+        if (!spin_flag(fo.flags + (int64_t)fo.wait_ch * fo.world + threadIdx.x, fo.wait_val, fo.timeout_ns, fo.status, threadIdx.x))
+            s_ok = 0;
+    }
+    __syncthreads();
+    if (s_ok) {
+        const int64_t n = b.nvec[k];
+        const int64_t stride = (int64_t)gridDim.x * 256;
+        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < fo.world; ++q) {                       // rank order: deterministic
+                const float4 v = (reinterpret_cast<const float4*>(b.tab[k][q]) + b.offset_vec[k])[i];
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            b.out[k][i] = a;
+        }
+    }
+    peer_finish(fo, gridDim.x * gridDim.y);
+}
+
+static int fill_flag_ops(PeerFlagOps& fo, const uint32_t* flags, const uint64_t* flag_tab, int world, int rank, int wait_ch,
+                         uint32_t wait_val, int guard_ch, uint32_t guard_val, int done_ch, uint32_t done_val,
+                         uint64_t timeout_ns, int32_t* status, uint32_t* counter) {
+    MSHA_REQUIRE(flags && flag_tab && counter && world >= 1 && world <= 32 && rank >= 0 && rank < world, "peer_exchange: bad arguments");
+    fo.flags = flags; fo.flag_tab = flag_tab; fo.world = world; fo.rank = rank;
+    fo.wait_ch = wait_ch; fo.wait_val = wait_val; fo.guard_ch = guard_ch; fo.guard_val = guard_val;
+    fo.done_ch = done_ch; fo.done_val = done_val; fo.timeout_ns = timeout_ns; fo.status = status; fo.counter = counter;
+    return 0;
+}
+
+// Gather of n_bufs (1 or 2) buffers in the gathered layout [world][block_bytes[k]]: the first nbytes[k] of every remote
+// block, each CTA after the owner's `wait` flag; `guard` / `done` as described above (channel < 0: skip).
+MSHA_API int msha_peer_exchange_pull(int n_bufs, void* const* dst, const uint64_t* const* src_tab, const int64_t* block_bytes,
+                                     const int64_t* nbytes, const uint32_t* flags, const uint64_t* flag_tab, int world,
+                                     int rank, int wait_ch, uint32_t wait_val, int guard_ch, uint32_t guard_val, int done_ch,
+                                     uint32_t done_val, uint64_t timeout_ns, int32_t* status, uint32_t* counter,
+                                     int max_ctas, void* stream) {
+    MSHA_REQUIRE(n_bufs == 1 || n_bufs == 2, "peer_exchange_pull: 1 or 2 buffers");
+    PeerFlagOps fo;
+    if (fill_flag_ops(fo, flags, flag_tab, world, rank, wait_ch, wait_val, guard_ch, guard_val, done_ch, done_val, timeout_ns,
+                      status, counter)) return -1;
+    if (world == 1) return 0;
+    PullBufs b;
+    int64_t max_vec = 0;
+    for (int k = 0; k < 2; ++k) {
+        const int kk = k < n_bufs ? k : 0;
+        MSHA_REQUIRE(block_bytes[kk] % 16 == 0 && nbytes[kk] % 16 == 0 && nbytes[kk] <= block_bytes[kk] && ((uintptr_t)dst[kk] & 15) == 0,
+                     "peer_exchange_pull: 16-byte granularity required");
+        b.dst[k] = reinterpret_cast<uint4*>(dst[kk]); b.tab[k] = src_tab[kk];
+        b.stride_vec[k] = block_bytes[kk] / 16; b.nvec[k] = nbytes[kk] / 16;
+        if (b.nvec[k] > max_vec) max_vec = b.nvec[k];
+    }
+    const int64_t cap = max_ctas > 0 ? max_ctas : 4 * MSHA_NUM_SMS;
+    int64_t per = msha_cdiv(max_vec, (int64_t)PULL_THREADS * PULL_UNROLL);
+    const int64_t lim = cap / ((world - 1) * n_bufs) + 1;
+    if (per > lim) per = lim;
+    if (per < 1) per = 1;
+    dim3 grid((unsigned)per, (unsigned)(world - 1), (unsigned)n_bufs);
+    peer_exchange_pull_kernel<<<grid, PULL_THREADS, 0, (cudaStream_t)stream>>>(b, fo);
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+// Reduce-scatter tail of n_bufs (1 or 2) buffers: out[k][i] = sum over ranks q (rank order) of rank q's buffer k at
+// offset_bytes[k] + i -- read in place over NVLink after every peer's `wait` flag; `guard` / `done` as above.
+MSHA_API int msha_peer_exchange_sum(int n_bufs, float* const* out, const uint64_t* const* src_tab, const int64_t* offset_bytes,
+                                    const int64_t* n_floats, const uint32_t* flags, const uint64_t* flag_tab, int world,
+                                    int rank, int wait_ch, uint32_t wait_val, int guard_ch, uint32_t guard_val, int done_ch,
+                                    uint32_t done_val, uint64_t timeout_ns, int32_t* status, uint32_t* counter, int max_ctas,
+                                    void* stream) {
+    MSHA_REQUIRE(n_bufs == 1 || n_bufs == 2, "peer_exchange_sum: 1 or 2 buffers");
+    PeerFlagOps fo;
+    if (fill_flag_ops(fo, flags, flag_tab, world, rank, wait_ch, wait_val, guard_ch, guard_val, done_ch, done_val, timeout_ns,
+                      status, counter)) return -1;
+    SumBufs b;
+    int64_t max_vec = 0;
+    for (int k = 0; k < 2; ++k) {
+        const int kk = k < n_bufs ? k : 0;
+        MSHA_REQUIRE(offset_bytes[kk] % 16 == 0 && n_floats[kk] % 4 == 0 && ((uintptr_t)out[kk] & 15) == 0,
+                     "peer_exchange_sum: 128-bit granularity required");
+        b.out[k] = reinterpret_cast<float4*>(out[kk]); b.tab[k] = src_tab[kk];
+        b.offset_vec[k] = offset_bytes[kk] / 16; b.nvec[k] = n_floats[kk] / 4;
+        if (b.nvec[k] > max_vec) max_vec = b.nvec[k];
+    }
+    const int64_t cap = max_ctas > 0 ? max_ctas : 4 * MSHA_NUM_SMS;
+    int64_t per = msha_cdiv(max_vec, 256);
+    if (per > cap / n_bufs + 1) per = cap / n_bufs + 1;
+    if (per < 1) per = 1;
+    dim3 grid((unsigned)per, (unsigned)n_bufs);
+    peer_exchange_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b, fo);
+    MSHA_LAUNCH_OK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// all-reduce (sum) of a SMALL fp64 vector: the BatchNorm column statistics of a partitioned node axis (2*C doubles,
+// SURVEY.md section 8e) keep their fp64 accumulation across ranks.  One CTA; every rank reads every rank's slot in
+// rank order (identical result everywhere) after its flag.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+peer_allreduce_f64_kernel(double* __restrict__ out, const uint64_t* __restrict__ tab, int64_t offset_bytes, int n,
+                          PeerFlagOps fo) {
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (fo.wait_ch >= 0 && threadIdx.x < fo.world && threadIdx.x != fo.rank) {
+        if (!spin_flag(fo.flags + (int64_t)fo.wait_ch * fo.world + threadIdx.x, fo.wait_val, fo.timeout_ns, fo.status, threadIdx.x))
+            s_ok = 0;
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        double a = 0.0;
+        for (int q = 0; q < fo.world; ++q)
+            a += reinterpret_cast<const double*>(tab[q] + offset_bytes)[i];
+        out[i] = a;
+    }
+}
+
+MSHA_API int msha_peer_allreduce_f64(double* out, const uint64_t* src_tab, int64_t offset_bytes, int64_t n,
+                                     const uint32_t* flags, const uint64_t* flag_tab, int world, int rank, int wait_ch,
+                                     uint32_t wait_val, uint64_t timeout_ns, int32_t* status, void* stream) {
+    MSHA_REQUIRE(out && src_tab && n >= 0 && n < (1 << 24) && offset_bytes % 8 == 0, "peer_allreduce_f64: bad arguments");
+    PeerFlagOps fo;
+    uint32_t dummy = 0;
+    if (fill_flag_ops(fo, flags, flag_tab, world, rank, wait_ch, wait_val, -1, 0, -1, 0, timeout_ns, status, &dummy)) return -1;
+    fo.counter = nullptr;
+    if (n == 0) return 0;
+    peer_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(out, src_tab, offset_bytes, (int)n, fo);
     MSHA_LAUNCH_OK();
     return 0;
 }

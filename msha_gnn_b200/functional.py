@@ -41,13 +41,14 @@ def _c(t):
 # ------------------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W, out=None):
+    def forward(ctx, x, W, out=None, precomputed=False):
         x, W = _c(x), _c(W)
         ctx.save_for_backward(x, W)
         if out is None:
             return ops.gemm(x, W)
-        ops.gemm(x, W, out=out)              # caller-owned destination (a rank's own block of a peer-mapped buffer)
-        ctx.mark_dirty(out)
+        if not precomputed:                  # precomputed: `out` already holds x @ W (issued early, row chunk by row chunk,
+            ops.gemm(x, W, out=out)          # by the producer of x -- dist_p2p.py); only the graph node is created here
+        ctx.mark_dirty(out)                  # caller-owned destination (a rank's own block of a peer-mapped buffer)
         return out
 
     @staticmethod
@@ -56,11 +57,11 @@ class _Linear(torch.autograd.Function):
         dy = _c(dy)
         dx = ops.gemm(dy, W, transB=True) if ctx.needs_input_grad[0] else None
         dW = ops.gemm(x, dy, transA=True) if ctx.needs_input_grad[1] else None
-        return dx, dW, None
+        return dx, dW, None, None
 
 
-def linear(x, W, out=None):
-    return _Linear.apply(x, W, out)
+def linear(x, W, out=None, precomputed=False):
+    return _Linear.apply(x, W, out, precomputed)
 
 
 class _LinearBiasAct(torch.autograd.Function):
@@ -153,14 +154,17 @@ def dropout(x, p, training):
 # ------------------------------------------------------------------------------------------------
 class _NodeScores(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat, a1, a2, H, D):
+    def forward(ctx, feat, a1, a2, H, D, pre=None):
         feat, a1 = _c(feat), _c(a1)
         n = feat.shape[0]
-        s1 = torch.empty((n, H), dtype=torch.float32, device=feat.device)
-        s2 = torch.empty((n, H), dtype=torch.float32, device=feat.device) if a2 is not None else None
         if a2 is not None:
             a2 = _c(a2)
-        call("msha_node_scores", ptr(feat), n, H, D, ptr(a1), ptr(s1), ptr(a2), ptr(s2), _stream())
+        if pre is not None:                  # (s1, s2) already computed from exactly these operands (dist_p2p.py chunk hook)
+            s1, s2 = pre
+        else:
+            s1 = torch.empty((n, H), dtype=torch.float32, device=feat.device)
+            s2 = torch.empty((n, H), dtype=torch.float32, device=feat.device) if a2 is not None else None
+            call("msha_node_scores", ptr(feat), n, H, D, ptr(a1), ptr(s1), ptr(a2), ptr(s2), _stream())
         ctx.H, ctx.D = H, D
         ctx.has2 = a2 is not None
         ctx.save_for_backward(feat, a1, a2 if a2 is not None else a1)
@@ -185,13 +189,13 @@ class _NodeScores(torch.autograd.Function):
             da1 = colsum(feat, None, ds1, D).view(H, D)
         if ctx.has2 and ctx.needs_input_grad[2]:
             da2 = colsum(feat, None, ds2, D).view(H, D)
-        return dfeat, da1, da2, None, None
+        return dfeat, da1, da2, None, None, None
 
 
-def node_scores(feat, a1, a2=None, H=1, D=None):
+def node_scores(feat, a1, a2=None, H=1, D=None, pre=None):
     """feat [n, H*D]; a1/a2 [H, D].  Returns s1 (and s2) of shape [n, H]."""
     D = D if D is not None else feat.shape[1] // H
-    return _NodeScores.apply(feat, a1, a2, H, D)
+    return _NodeScores.apply(feat, a1, a2, H, D, pre)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -432,6 +436,120 @@ def bn_lrelu(x, gamma, beta, running_mean, running_var, training, momentum=0.1, 
     if training and x.shape[0] < 2:
         raise ValueError("Expected more than 1 value per channel when training")   # nn.BatchNorm1d behaviour
     return _BnLrelu.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps)
+
+
+class _BnLreluDist(torch.autograd.Function):
+    """``leakyrelu(bn(x))`` over a node axis that is partitioned across ranks (Ours.py:100-101 at multi-GPU scale, SURVEY.md
+    section 8e): the 2*C column sums leave the library between the statistics and the apply pass, ``reduce`` (a callable
+    summing a small tensor over the ranks and returning the result) is applied to them, ``n_total`` is the global row
+    count.  Same kernels as ``_BnLrelu``; d gamma / d beta come out global, i.e. identical on every rank -- the caller
+    must NOT sum them over ranks again (they are returned divided by ``grad_replicas`` so that a gradient all-reduce that
+    sums every parameter's gradient over the ranks restores them)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, n_total, reduce, grad_replicas):
+        x = _c(x)
+        n, C = x.shape
+        dev = x.device
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        invstd = torch.empty(C, dtype=torch.float32, device=dev)
+        lib = ops._lib.lib()
+        sums = None
+        if training:
+            ws = workspace(lib.msha_bn_workspace_bytes(C), dev)
+            sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            call("msha_bn_stats", ptr(x), n, C, sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            sums = reduce(sums)
+        call("msha_bn_lrelu_apply", ptr(x), n, C, sums.data_ptr() if sums is not None else None, int(n_total),
+             ptr(_c(gamma)), ptr(_c(beta)), ptr(running_mean), ptr(running_var), int(training), float(momentum), float(eps),
+             LRELU_SLOPE, ptr(y), ptr(mean), ptr(invstd), _stream())
+        ctx.training, ctx.n_total, ctx.reduce, ctx.grad_replicas = training, int(n_total), reduce, grad_replicas
+        ctx.save_for_backward(x, y, gamma, mean, invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, mean, invstd = ctx.saved_tensors
+        n, C = x.shape
+        dev = x.device
+        dx = torch.empty_like(x)
+        xhat = torch.empty_like(x)
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        lib = ops._lib.lib()
+        ws = workspace(lib.msha_bn_workspace_bytes(C), dev)
+        sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        call("msha_bn_lrelu_bwd_stats", ptr(_c(dy)), ptr(y), ptr(x), n, C, ptr(mean), ptr(invstd), LRELU_SLOPE, ptr(dx),
+             ptr(xhat), sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        sums = ctx.reduce(sums)
+        call("msha_bn_lrelu_bwd_apply", ptr(dx), ptr(xhat), n, C, ptr(_c(gamma)), ptr(invstd), sums.data_ptr(), ctx.n_total,
+             int(ctx.training), ptr(dgamma), ptr(dbeta), _stream())
+        if ctx.grad_replicas != 1:
+            dgamma, dbeta = dgamma / ctx.grad_replicas, dbeta / ctx.grad_replicas
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
+def bn_lrelu_dist(x, gamma, beta, running_mean, running_var, training, n_total, reduce, momentum=0.1, eps=1e-5,
+                  grad_replicas=1):
+    if training and n_total < 2:
+        raise ValueError("Expected more than 1 value per channel when training")   # nn.BatchNorm1d behaviour
+    return _BnLreluDist.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps, n_total, reduce,
+                              grad_replicas)
+
+
+class _GroupRowsSum(torch.autograd.Function):
+    """G[g] = sum_{i : gid[i] = g} x[i]  -- the per-group sums of the intra-scale block in its group-sum form
+    (Ours.py:99: att3.t() @ h2_ is one row per group, see csrc/intra_kernels.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, gid, n_groups):
+        x = _c(x)
+        G = torch.empty((n_groups, x.shape[1]), dtype=torch.float32, device=x.device)
+        call("msha_group_rows_sum", ptr(x), ptr(gid, torch.int64), x.shape[0], x.shape[1], n_groups, ptr(G), _stream())
+        ctx.save_for_backward(gid)
+        return G
+
+    @staticmethod
+    def backward(ctx, dG):
+        (gid,) = ctx.saved_tensors
+        dG = _c(dG)
+        dx = torch.empty((gid.numel(), dG.shape[1]), dtype=torch.float32, device=dG.device)
+        call("msha_group_rows_add", ptr(dx), ptr(dG), ptr(gid, torch.int64), None, None, gid.numel(), dG.shape[1], 0, _stream())
+        return dx, None, None
+
+
+class _GroupRowsAdd(torch.autograd.Function):
+    """out[i] = G3[gid3[i]] + G4[gid4[i]]  (IntraNC of every node from the two group tables)."""
+
+    @staticmethod
+    def forward(ctx, G3, gid3, G4, gid4):
+        G3, G4 = _c(G3), _c(G4)
+        n, C = gid3.numel(), G3.shape[1]
+        out = torch.empty((n, C), dtype=torch.float32, device=G3.device)
+        call("msha_group_rows_add", ptr(out), ptr(G3), ptr(gid3, torch.int64), ptr(G4), ptr(gid4, torch.int64), n, C, 0, _stream())
+        ctx.shapes = (G3.shape[0], G4.shape[0])
+        ctx.save_for_backward(gid3, gid4)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        gid3, gid4 = ctx.saved_tensors
+        dout = _c(dout)
+        n, C = dout.shape
+        d3 = torch.empty((ctx.shapes[0], C), dtype=torch.float32, device=dout.device)
+        d4 = torch.empty((ctx.shapes[1], C), dtype=torch.float32, device=dout.device)
+        call("msha_group_rows_sum", ptr(dout), ptr(gid3, torch.int64), n, C, ctx.shapes[0], ptr(d3), _stream())
+        call("msha_group_rows_sum", ptr(dout), ptr(gid4, torch.int64), n, C, ctx.shapes[1], ptr(d4), _stream())
+        return d3, None, d4, None
+
+
+def group_rows_sum(x, gid, n_groups):
+    return _GroupRowsSum.apply(x, gid.contiguous(), int(n_groups))
+
+
+def group_rows_add(G3, gid3, G4, gid4):
+    return _GroupRowsAdd.apply(G3, gid3.contiguous(), G4, gid4.contiguous())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -163,3 +163,73 @@ def test_partitioned_gat_layer_equals_full_graph_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def _msha_worker(rank, world, port, ret):
+    """Partition algebra of the MSHA layer (OursLayer3, Ablation.py:260-277) through dist_msha's torch transports: gather of
+    h1, reduce-scatter of alpha.T @ h2 partials, BatchNorm statistics all-reduced -- against the oracle on the whole graph."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from msha_gnn_b200 import dist_msha as dm
+        F = torch.nn.functional
+        rng = np.random.default_rng(11)
+        N, M, Fin, d = 13, 7, 5, 4
+        adj = (rng.random((N, M)) < 0.4).astype(np.float32)
+        adj[np.arange(N), rng.integers(0, M, N)] = 1
+        S = torch.tensor(rng.random((N, Fin)))
+        R = torch.tensor(rng.random((M, Fin)))
+        p = {"W1": torch.tensor(rng.standard_normal((Fin, d))), "W2": torch.tensor(rng.standard_normal((Fin, d))),
+             "a": torch.tensor(rng.standard_normal((2 * d, 1)))}
+        for bn in ("bn1", "bn2"):
+            p[bn + ".weight"], p[bn + ".bias"] = torch.tensor(rng.random(d) + 0.5), torch.tensor(rng.standard_normal(d))
+            p[bn + ".running_mean"], p[bn + ".running_var"] = torch.zeros(d, dtype=torch.float64), torch.ones(d, dtype=torch.float64)
+        G = torch.tensor(rng.standard_normal((N, M)))
+        rowptr, col, _ = O.csr_from_dense(adj)
+        pf = {k: (v.clone().requires_grad_(True) if k in ("W1", "W2", "a") else v.clone()) for k, v in p.items()}
+        full = O.ours_layer3(S, R, pf, rowptr, col, training=True)
+        (full * G).sum().backward()
+        # ---- partitioned
+        ps, pr = Partition(N, world, rank), Partition(M, world, rank)
+        comm = dm.TorchComm()
+        W1, W2, a = (p[k].clone().requires_grad_(True) for k in ("W1", "W2", "a"))
+        h1 = R[pr.lo:pr.hi] @ W1
+        h2 = S[ps.lo:ps.hi] @ W2
+        h1_g = comm.gather_rows(h1, pr, "h1")
+        s_nbr_g = h1_g @ a[:d, 0]
+        s_self = h2 @ a[d:, 0]
+        r_loc, c_glob = np.nonzero(adj[ps.lo:ps.hi] > 0)
+        r, c = torch.from_numpy(r_loc), pr.to_padded(torch.from_numpy(c_glob))
+        alpha = O.segment_softmax(F.leaky_relu(s_nbr_g[c] + s_self[r], 0.2), r, ps.n_local)
+        u_in = torch.zeros(ps.n_local, d, dtype=torch.float64).index_add(0, r, alpha[:, None] * h1_g[c])
+        v_part = torch.zeros(pr.n_padded, d, dtype=torch.float64).index_add(0, c, alpha[:, None] * h2[r])
+        v_in = comm.reduce_scatter_rows(v_part, pr, "v")
+        assert v_in.shape == (pr.n_local, d)
+
+        def bn(x, w, b, n_total):                              # batch statistics over the GLOBAL node axis
+            sums = dm.all_reduce_sum(torch.cat([x.sum(0), (x * x).sum(0)]), comm)
+            mean = sums[:d] / n_total
+            var = sums[d:] / n_total - mean * mean
+            return F.leaky_relu((x - mean) / torch.sqrt(var + 1e-5) * w + b, 0.2)
+        v = bn(v_in, p["bn1.weight"], p["bn1.bias"], M)
+        u = bn(u_in, p["bn2.weight"], p["bn2.bias"], N)
+        v_g = comm.gather_rows(v, pr, "vg")
+        cols_p = pr.to_padded(torch.arange(M))
+        out = F.elu(u @ v_g[cols_p].t())
+        assert torch.allclose(out, full[ps.lo:ps.hi].detach(), atol=1e-10)
+        (out * G[ps.lo:ps.hi]).sum().backward()
+        allreduce_gradients([W1, W2, a])
+        for got, name in ((W1, "W1"), (W2, "W2"), (a, "a")):
+            assert torch.allclose(got.grad, pf[name].grad, atol=1e-9), (name, (got.grad - pf[name].grad).abs().max())
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_msha_layer_algebra_gloo():
+    world = 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_msha_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}

@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 
 import msha_gnn_b200 as mg
 from msha_gnn_b200 import dist as md
+from msha_gnn_b200 import dist_p2p as mp2p
 from msha_gnn_b200 import functional as Fn
 from msha_gnn_b200 import graph as mgraph
 from msha_gnn_b200 import peer
@@ -139,7 +140,7 @@ def _emulate(world, N, rows, cols, convs_ref, predictor_ref, x_full, src, dst, l
         st = dict(part=part, g=pgraph, p2p=md.P2P(fab.groups[r], part), convs=copy.deepcopy(convs_ref),
                   pred=copy.deepcopy(predictor_ref), x=x_full[part.lo:part.hi].clone().requires_grad_(True))
         lo, hi = (P * r) // world, (P * (r + 1)) // world
-        st["h"] = md.gat_encode_p2p(st["convs"], st["x"], pgraph, part, st["p2p"])
+        st["h"] = md.gat_encode_p2p(st["convs"], st["x"], pgraph, part, st["p2p"], score_key="score_h")
         st["loss"] = md.score_pairs(st["pred"], st["h"], src[lo:hi], dst[lo:hi], part, target=labels[lo:hi],
                                     global_pairs=P, p2p=st["p2p"])
         st["loss"].backward()
@@ -150,8 +151,7 @@ def _emulate(world, N, rows, cols, convs_ref, predictor_ref, x_full, src, dst, l
 
 @pytest.mark.parametrize("world,pipelined", [(2, False), (3, False), (2, True), (3, True)])
 def test_emulated_ranks_p2p_match_full_graph(world, pipelined, monkeypatch):
-    monkeypatch.setattr(md, "PIPELINE_MIN_BLOCK_BYTES", 0 if pipelined else 1 << 40)
-    monkeypatch.setattr(peer, "CE_MIN_BYTES", 0 if pipelined else 1 << 40)
+    monkeypatch.setattr(mp2p, "PIPELINE_MIN_BLOCK_BYTES", 0 if pipelined else 1 << 40)
     monkeypatch.setattr(mgraph, "SEG_LIMIT", 32)               # hub rows and hub columns on every rank
     N, Fin, H, d, P = 403, 24, 4, 8, 3000
     rows, cols = _power_law_graph(N, 11 + world)
@@ -191,8 +191,7 @@ def test_emulated_ranks_p2p_match_full_graph(world, pipelined, monkeypatch):
 
 def test_second_step_reuses_buffers(monkeypatch):
     """Two consecutive steps through the same exchanges (reuse guards, sequence numbers) give the same result twice."""
-    monkeypatch.setattr(md, "PIPELINE_MIN_BLOCK_BYTES", 0)
-    monkeypatch.setattr(peer, "CE_MIN_BYTES", 0)
+    monkeypatch.setattr(mp2p, "PIPELINE_MIN_BLOCK_BYTES", 0)
     world, N, Fin, H, d = 2, 200, 16, 2, 8
     rows, cols = _power_law_graph(N, 1)
     torch.manual_seed(0)
@@ -218,3 +217,76 @@ def test_second_step_reuses_buffers(monkeypatch):
     for r in range(world):
         assert torch.equal(res[r][0][0], res[r][1][0])
         assert rel_err(res[r][1][1].cpu().numpy(), res[r][0][1].cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("variant,world", [(3, 2), (1, 2), (1, 3)])
+def test_partitioned_msha_layer_matches_single_gpu(variant, world):
+    """dist_msha.ours_encode on emulated ranks (gather of h1, reduce-scatter of alpha.T @ h2, BN statistics and intra-scale
+    group tables all-reduced over peer memory) == layers.msha_heads_forward on one GPU: pair scores elu(u_i . v_j), and the
+    gradients of the features and of every layer parameter.  (Ours.py:54-109 / Ablation.py:260-277.)"""
+    from msha_gnn_b200 import dist_msha as dm
+    from msha_gnn_b200.layers import msha_heads_forward
+    dev = torch.device(DEV)
+    rng = np.random.default_rng(variant * 10 + world)
+    N, M, F, d, H, B, P = 301, 53, 16, 8, 2, 40, 500
+    adj = (rng.random((N, M)) < 0.12)
+    adj[np.arange(N), rng.integers(0, M, N)] = True                  # every source has a recipient
+    rows, cols = np.nonzero(adj)
+    city = rng.integers(0, 7, N)
+    prov = city % 3
+    torch.manual_seed(4)
+    cls = mg.OursLayer if variant == 1 else mg.OursLayer3
+    layers = torch.nn.ModuleList([cls(F, d, dropout=0.0) for _ in range(H)]).to(dev)
+    S = torch.rand(N, F, device=dev)
+    R = torch.rand(M, F, device=dev)
+    src_b = torch.from_numpy(rng.integers(0, N, B)).to(dev)
+    pi = torch.from_numpy(rng.integers(0, N, P)).to(dev)
+    pj = torch.from_numpy(rng.integers(0, M, P)).to(dev)
+    Gw = torch.from_numpy(rng.standard_normal((P, H)).astype(np.float32)).to(dev)
+    city_d, prov_d = torch.from_numpy(city).to(dev), torch.from_numpy(prov).to(dev)
+    # ---- single GPU
+    g_full = mg.Graph.from_coo(torch.from_numpy(rows).to(dev), torch.from_numpy(cols).to(dev), N, M)
+    ref_layers = copy.deepcopy(layers)
+    Sf, Rf = S.clone().requires_grad_(True), R.clone().requires_grad_(True)
+    out = msha_heads_forward(list(ref_layers), Sf, Rf, g_full, city_d if variant == 1 else None,
+                             prov_d if variant == 1 else None, src_b if variant == 1 else None, True)      # (N, H*M)
+    ref_scores = torch.stack([out[pi, h * M + pj] for h in range(H)], dim=1)
+    (ref_scores * Gw).sum().backward()
+    # ---- emulated ranks
+    fab = peer.LocalFabric(world, dev)
+    n3 = torch.bincount(city_d, minlength=7).float()
+    n4 = torch.bincount(prov_d, minlength=3).float()
+    res = [None] * world
+
+    def rank_step(r):
+        ps, pr = md.Partition(N, world, r), md.Partition(M, world, r)
+        keep = (rows >= ps.lo) & (rows < ps.hi)
+        pgraph = md.partition_graph(torch.from_numpy(rows[keep]).to(dev), torch.from_numpy(cols[keep]).to(dev), ps, col_part=pr)
+        comm = dm.PeerComm({id(ps): mp2p.P2P(fab.groups[r], ps), id(pr): mp2p.P2P(fab.groups[r], pr)})
+        my = copy.deepcopy(layers)
+        Sl = S[ps.lo:ps.hi].clone().requires_grad_(True)
+        Rl = R[pr.lo:pr.hi].clone().requires_grad_(True)
+        mine = (src_b >= ps.lo) & (src_b < ps.hi)
+        u, v = dm.ours_encode(list(my), Sl, Rl, pgraph, ps, pr, comm, source_index=(src_b[mine] - ps.lo),
+                              city_ids=city_d[ps.lo:ps.hi], province_ids=prov_d[ps.lo:ps.hi], group_sizes=(n3, n4))
+        pm = (pi >= ps.lo) & (pi < ps.hi)
+        sc = dm.score_uv_pairs(u, v, pi[pm] - ps.lo, pj[pm], pr, comm, heads=H)
+        (sc * Gw[pm]).sum().backward()
+        res[r] = dict(sc=sc.detach(), pm=pm, dS=Sl.grad, dR=Rl.grad, layers=my)
+    _run_ranks(fab, rank_step)
+    got = torch.empty_like(ref_scores)
+    for r in range(world):
+        got[res[r]["pm"]] = res[r]["sc"]
+    assert rel_err(got.cpu().numpy(), ref_scores.detach().cpu().numpy()) < 2e-5
+    assert rel_err(torch.cat([x["dS"] for x in res]).cpu().numpy(), Sf.grad.cpu().numpy()) < 1e-4
+    assert rel_err(torch.cat([x["dR"] for x in res]).cpu().numpy(), Rf.grad.cpu().numpy()) < 1e-4
+    for name, pf in ref_layers.named_parameters():
+        if pf.grad is None:
+            continue
+        tot = sum(dict(x["layers"].named_parameters())[name].grad for x in res)
+        assert rel_err(tot.cpu().numpy(), pf.grad.cpu().numpy()) < 2e-4, name
+    for name, bf in ref_layers.named_buffers():                       # BN running statistics: global, identical on every rank
+        if "num_batches" in name:
+            continue
+        for x in res:
+            assert rel_err(dict(x["layers"].named_buffers())[name].cpu().numpy(), bf.cpu().numpy()) < 1e-5, name

@@ -5,8 +5,9 @@ Two constructions.  "positive": non-negative features / weights and a positive s
 pre-activation away from 0, so the comparison measures arithmetic only (tolerance 1e-4; the attention vectors' gradients
 are excluded: with all logits on one LeakyReLU branch softmax shift-invariance makes them exactly 0 / pure cancellation).
 "signed": ordinary random parameters; a handful of the 77 M pre-activations lie within fp32 round-off of 0 and fall on
-either side in the two summation orders, which moves gradients by ~1e-3 of their norm (the reference has the same
-sensitivity) -- tolerance 5e-3, all parameters included."""
+either side in the two summation orders, which moves gradients by ~1e-3 .. 1e-2 of their norm -- more flips the more ranks
+the sums are split over; every exchange mode (NCCL or peer memory) shows the SAME figure, the reference has the same
+sensitivity -- tolerance 2e-2, all parameters included."""
 import os, sys
 os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")       # peer path: kernels wait on kernels (msha_gnn_b200/peer.py)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
@@ -14,7 +15,7 @@ import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import msha_gnn_b200 as mg
 from msha_gnn_b200 import dist as md
-from msha_gnn_b200 import peer
+from msha_gnn_b200 import peer, dist_p2p as mp2p
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
@@ -41,7 +42,7 @@ def rel(a, b):
 
 
 ok = True
-for construction, tol in (("positive", 1e-4), ("signed", 5e-3)):
+for construction, tol in (("positive", 1e-4), ("signed", 2e-2)):
     torch.manual_seed(3)
     model = mg.GATLinkModel(F, H * d, H, 2, 256, dropout=0.0).to(dev)
     if construction == "positive":
@@ -66,9 +67,9 @@ for construction, tol in (("positive", 1e-4), ("signed", 5e-3)):
             h = md.gat_encode(model.convs, xl, pg, part, overlap=(overlap == "nccl+early-rs"))
             out = md.score_pairs(model.predictor, h, src_d[lo:hi], dst_d[lo:hi], part)
         else:
-            md.PIPELINE_MIN_BLOCK_BYTES, peer.CE_MIN_BYTES = thresholds
+            mp2p.PIPELINE_MIN_BLOCK_BYTES = thresholds[0]
             p2p = md.P2P(fabric.group, part)
-            h = md.gat_encode_p2p(model.convs, xl, pg, part, p2p)
+            h = md.gat_encode_p2p(model.convs, xl, pg, part, p2p, score_key="score_h")
             out = md.score_pairs(model.predictor, h, src_d[lo:hi], dst_d[lo:hi], part, p2p=p2p)
         (out * G[lo:hi]).sum().backward()
         if thresholds is not None:

@@ -5,7 +5,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import msha_gnn_b200 as mg
-from msha_gnn_b200 import dist as md, peer
+from msha_gnn_b200 import dist as md, peer, dist_p2p as mp2p
 
 dev = torch.device("cuda:0")
 W_ = int(sys.argv[1]) if len(sys.argv) > 1 else 2
@@ -36,7 +36,7 @@ def rel(a, b):
 
 
 for name, thr in (("flat", (1 << 40, 1 << 40)), ("pipelined", (0, 0))):
-    md.PIPELINE_MIN_BLOCK_BYTES, peer.CE_MIN_BYTES = thr
+    mp2p.PIPELINE_MIN_BLOCK_BYTES = thr[0]
     fab = peer.LocalFabric(W_, dev)
     res = [None] * W_
 
