@@ -42,7 +42,35 @@ extern unsigned long long g_msha_launches;   // kernels launched by this library
 static inline int64_t msha_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t msha_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-constexpr int MSHA_NUM_SMS = 148;   // B200
+// SM count of the CURRENT device (148 on B200), queried once per device: grid sizes follow the device a call runs on.
+static inline int msha_num_sms() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+#define MSHA_NUM_SMS msha_num_sms()
+
+// Function attributes (cudaFuncSetAttribute: opt-in dynamic shared memory) are per DEVICE: a call site remembers, per
+// device, that it has set them -- a process that drives several GPUs would otherwise launch with the 48 KB default on all
+// but the first.  (A race between two host threads only repeats the harmless call.)
+struct MshaPerDeviceOnce {
+    unsigned long long done = 0ull;
+    bool need() const {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        return !((done >> dev) & 1ull);
+    }
+    void mark() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) done |= 1ull << dev;
+    }
+};
 
 #ifdef __CUDACC__
 constexpr unsigned FULL_MASK = 0xffffffffu;

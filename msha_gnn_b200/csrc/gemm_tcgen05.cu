@@ -298,10 +298,10 @@ template <int BN, bool AM, bool BM>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int M, int N, int K, int64_t ldc,
                   const float* bias, int act, float slope, int splits, int atomic_out, cudaStream_t st) {
     auto kern = gemm_tf32x3_kernel<BN, AM, BM>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static MshaPerDeviceOnce attr_set;
+    if (attr_set.need()) {
         MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
-        attr_set = true;
+        attr_set.mark();
     }
     const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
     int64_t n_work = (int64_t)m_tiles * n_tiles * splits;

@@ -936,10 +936,10 @@ int launch_fwd(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* hi_t
                cudaStream_t st) {
     using S = SCfg<BN, SCORE_CTAS>;
     auto kern = score_fwd_kernel<BN, SCORE_CTAS>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static MshaPerDeviceOnce attr_set;
+    if (attr_set.need()) {
         MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
-        attr_set = true;
+        attr_set.mark();
     }
     return launch_tiles(kern, FWD_THREADS, S::SMEM_BYTES, (P + BLOCK_M - 1) / BLOCK_M, st, tbh, tbl, hi_tab, hj_tab, src, dst, P, C, N, bias,
                         act, slope, out, ldo);
@@ -994,10 +994,10 @@ int launch_dz(const CUtensorMap& tbh, const CUtensorMap& tbl, const float* dout,
     if (rcm) return rcm;
     using S = SCfg<BN, SCORE_CTAS>;
     auto kern = score_bwd_dz_kernel<BN, SCORE_CTAS>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static MshaPerDeviceOnce attr_set;
+    if (attr_set.need()) {
         MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
-        attr_set = true;
+        attr_set.mark();
     }
     return launch_tiles(kern, NUM_THREADS, S::SMEM_BYTES, (P + BLOCK_M - 1) / BLOCK_M, st, tbh, tbl, td, ty, act, slope, G, db, hi_tab,
                         hj_tab, src, dst, P, Hd, C, dhi, dhj, nll_target, nll_gout);
@@ -1045,10 +1045,10 @@ static int score_mlp_bwd_impl(const float* dout, const int64_t* nll_target, cons
     const int64_t n_chunks = (P + dw_bk - 1) / dw_bk;
     if (dw_pairs) {
         auto kern = score_bwd_dw_kernel<2>;
-        static bool attr_set2 = false;
-        if (!attr_set2) {
+        static MshaPerDeviceOnce attr_set2;
+        if (attr_set2.need()) {
             MSHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<2>::SMEM_BYTES));
-            attr_set2 = true;
+            attr_set2.mark();
         }
         const int max_pairs = MSHA_NUM_SMS / 2;
         const int n_pairs = (int)(n_chunks < max_pairs ? n_chunks : max_pairs);
@@ -1068,10 +1068,10 @@ static int score_mlp_bwd_impl(const float* dout, const int64_t* nll_target, cons
         MSHA_LAUNCH_OK();
         return 0;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static MshaPerDeviceOnce attr_set;
+    if (attr_set.need()) {
         MSHA_CUDA(cudaFuncSetAttribute(score_bwd_dw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<1>::SMEM_BYTES));
-        attr_set = true;
+        attr_set.mark();
     }
     const int grid = (int)(n_chunks < MSHA_NUM_SMS ? n_chunks : MSHA_NUM_SMS);
     score_bwd_dw_kernel<1><<<grid, NUM_THREADS, WCfg<1>::SMEM_BYTES, st>>>(tg, hi_tab, hj_tab, src, dst, P, (int)Hd, (int)C, dW0);

@@ -319,8 +319,12 @@ def attention_block(graph: Graph, s_nbr, s_self, feat_nbr, feat_self=None, heads
     D = C // heads
     p = float(dropout_p) if training else 0.0
     seed = ops.next_seed() if p > 0 else 0
-    return _AttentionBlock.apply(s_nbr, s_self, feat_nbr, feat_self, graph, heads, D, act, p, seed, want_cols, want_lse,
-                                 grad_sink)
+    res = _AttentionBlock.apply(s_nbr, s_self, feat_nbr, feat_self, graph, heads, D, act, p, seed, want_cols, want_lse,
+                                grad_sink)
+    # the dropout stream of this block travels with alpha: consumers that must re-draw the same mask (the SUM_county term
+    # of the intra scales, Ours.py:86) read it from here -- also under no_grad, where alpha has no grad_fn
+    res[2 if want_cols else 1]._msha_drop = (p, seed)
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -614,6 +618,16 @@ def log_softmax(x, pre_elu=False):
     return _LogSoftmax.apply(x, pre_elu)
 
 
+CHECK_TARGETS = os.environ.get("MSHA_CHECK_TARGETS", "0") != "0"
+
+
+def _check_targets(status, n_classes):
+    """The read-out kernels never synchronise: an out-of-range target contributes 0 and sets a status word, where
+    F.nll_loss raises.  MSHA_CHECK_TARGETS=1 (debugging) reads the word back -- one host synchronisation per call."""
+    if CHECK_TARGETS and int(status.item()) != 0:
+        raise IndexError(f"nll_loss: a target lies outside [0, {n_classes})")
+
+
 class _NllLoss(torch.autograd.Function):
     """F.nll_loss(logp, target) (mean): gather + deterministic sum; backward streams the dense gradient."""
 
@@ -627,6 +641,7 @@ class _NllLoss(torch.autograd.Function):
         ws = workspace(lib.msha_nll_workspace_bytes(), logp.device)
         call("msha_nll_loss_fwd", ptr(logp), ptr(target, torch.int64), P, C, loss.data_ptr(), ptr(status, I32),
              ws.data_ptr(), ws.numel(), _stream())
+        _check_targets(status, C)
         ctx.shape = (P, C)
         ctx.save_for_backward(target)
         return loss
@@ -771,6 +786,7 @@ class _ScoreMLPNll(torch.autograd.Function):
         ws2 = workspace(lib.msha_nll_workspace_bytes(), dev)
         call("msha_nll_loss_fwd", ptr(out), ptr(target, torch.int64), P, Hd, loss.data_ptr(), ptr(status, I32),
              ws2.data_ptr(), ws2.numel(), _stream())
+        _check_targets(status, Hd)
         ctx.act, ctx.has_bias = act, b0 is not None
         ctx.grad_buffer = getattr(hi, "_msha_grad_buffer", None)
         ctx.order, ctx.order_owned = None, False

@@ -155,8 +155,12 @@ def intra_scales(layers, graph: Graph, h2, alpha, city_adj, province_adj, source
     n3 = cnt3(src).view(B, 1)
     n4 = cnt4(src).view(B, 1)
     if joint:
+        # (p, seed) of the dropout the producing attention block drew on alpha (Ours.py:69): attached to the tensor by
+        # functional.attention_block; the grad_fn route is kept for tensors that went through other wrappers
         fn = alpha.grad_fn
-        a_p, a_seed = (fn.p, fn.seed) if fn is not None and hasattr(fn, "seed") else (0.0, 0)
+        a_p, a_seed = getattr(alpha, "_msha_drop", None) or ((fn.p, fn.seed) if fn is not None and hasattr(fn, "seed") else (0.0, 0))
+        if training and layers[0].dropout > 0 and a_p == 0.0:
+            raise RuntimeError("intra_scales: the dropout stream of alpha is unknown (pass the tensor returned by attention_block)")
         T = _RowsumExp.apply(alpha, graph, src, a_p, a_seed)                                # Ours.py:86
         total = n3 * torch.exp(t3) + n4 * torch.exp(t4) + T                                 # Ours.py:84-86
         c3 = torch.exp(t3) / total                                                          # Ours.py:87
@@ -175,13 +179,14 @@ def intra_scales(layers, graph: Graph, h2, alpha, city_adj, province_adj, source
            + _GroupScatter.apply(c4, h2b, (rp4, col4, map4), src, N, H, d, p, seed4, 6))    # Ours.py:99
     coeffs = {}
     if want_coeffs:
-        coeffs["Coeff3"] = _dense_rows(c3.detach()[:, 0], rp3, col3, map3, src, N)
-        coeffs["Coeff4"] = _dense_rows(c4.detach()[:, 0], rp4, col4, map4, src, N)
+        # the reference's heads overwrite one another's export (Ours.py:92-96): the LAST head's coefficients survive
+        coeffs["Coeff3"] = _dense_rows(c3.detach()[:, -1], rp3, col3, map3, src, N)
+        coeffs["Coeff4"] = _dense_rows(c4.detach()[:, -1], rp4, col4, map4, src, N)
     return out, coeffs
 
 
 def _dense_rows(coef, rowptr, col, row_map, src, N):
-    """(B, N) dense attention rows for the explainer export (Ours.py:92-96); head 0 of the batched heads."""
+    """(B, N) dense attention rows for the explainer export (Ours.py:92-96)."""
     B = src.numel()
     out = torch.zeros((B, N), dtype=torch.float32, device=coef.device)
     rows = row_map.long()[src] if row_map is not None else src

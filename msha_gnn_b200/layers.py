@@ -216,7 +216,10 @@ def msha_heads_forward(layers, Sinput, Rinput, inter_adj, city_adj, province_adj
             if Coeff4 is not None:
                 Coeff4[source_index] = coeffs["Coeff4"]
     if record:
+        # per-head layout (H, N, M); the reference's heads overwrite one global (train.Coeff12new, Ours.py:94), so what its
+        # explainer sees is the LAST head: exported under the reference's name as well
         last_attention["Coeff12"] = dense_attention(graph, alpha, H)
+        last_attention["Coeff12new"] = last_attention["Coeff12"][-1]
     v = _bn_heads(v_in, [l.bn1 for l in layers], training)                      # Ours.py:100
     u = _bn_heads(u_in, [l.bn2 for l in layers], training)                      # Ours.py:101
     return Fn.matmul_nt_act(u, v, H, ACT_ELU)                                   # Ours.py:108-109
