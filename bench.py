@@ -1058,14 +1058,28 @@ def run_yearly(args):
     E_tot = sum(yr["graph"].nnz for yr in years)
     N_tot = sum(yr["N"] for yr in years)
 
+    # the four yearly graphs are independent until the shared scorer's gradient: each year's chain of small kernels (~30
+    # launches of 5-35 us, none of which fills the GPU) runs on its own stream, forked from and joined to the step's stream
+    # -- inside the captured graph these become four parallel branches
+    year_streams = [torch.cuda.Stream() for _ in years] if not args.no_year_streams else None
+
     def step(batch):
         opt.zero_grad(set_to_none=True)
-        total = None
+        cur = torch.cuda.current_stream()
+        losses = []
         for k, yr in enumerate(years):
             s_i, r_i = batch[k, 0], batch[k, 1]
-            h = yr["model"](yr["graph"])                                        # (N, M) log-probs, GAT.py:53-58
-            loss = predictor.nll_loss_pairs(h, h, s_i, r_i, r_i)                # LLP.py:233-235
-            total = loss if total is None else total + loss
+            if year_streams is not None:
+                year_streams[k].wait_stream(cur)
+            with torch.cuda.stream(year_streams[k] if year_streams is not None else cur):
+                h = yr["model"](yr["graph"])                                    # (N, M) log-probs, GAT.py:53-58
+                losses.append(predictor.nll_loss_pairs(h, h, s_i, r_i, r_i))    # LLP.py:233-235
+        if year_streams is not None:
+            for st in year_streams:
+                cur.wait_stream(st)
+        total = losses[0]
+        for l_ in losses[1:]:
+            total = total + l_
         total.backward()
         opt.step()
         return total
@@ -1125,6 +1139,7 @@ def run_yearly(args):
            "config": {"workload": f"yearly: 4 yearly graphs N={[yr['N'] for yr in years]}, M={M}, nnz={[yr['graph'].nnz for yr in years]} "
                                   f"(2015-shaped synthetic flows), GAT(n_features=32,n_classes=32,n_heads=8,p=0.5) per year + shared "
                                   f"LinkPredictor(mlp,32,32,1,2,0.5), batch {B} pairs per year, nll_loss, Adam (BASELINE.json configs[1])",
+                      "dropout": 0.5, "year_streams": year_streams is not None,
                       "l2_policy": "per-step working set (4 x N x 256 x 4 B x several tensors, ~0.5 GB) exceeds the 126 MB L2; no explicit flush"},
            "nodes_per_sec": N_tot / (ms_dev / 1e3), "pairs_per_sec": 4 * B / (ms_dev / 1e3),
            "e2e": {"value": E_tot * 2 / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
@@ -1316,6 +1331,7 @@ def main():
     ap.add_argument("--dense-nll-bwd", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: exchange over NVLink peer memory with this library's kernels (default) or NCCL collectives")
+    ap.add_argument("--no-year-streams", action="store_true", help="yearly: run the four yearly graphs one after the other")
     ap.add_argument("--no-strong-scaling", action="store_true",
                     help="skip the R-MAT (BASELINE.json configs[3]) block the default workload appends to its line")
     ap.add_argument("--full-pairs", action="store_true", help="--impl reference: score every pair instead of a 131072-pair sample")

@@ -175,7 +175,7 @@ class PeerComm:
         P, L, U = ctypes.c_void_p * 1, ctypes.c_int64 * 1, ctypes.c_uint64 * 1
         call("msha_peer_exchange_sum", 1, P(out.data_ptr()), U(st["buf"].tab.data_ptr()), L(slot * st["cap"]), L(n4),
              pg.flags.local.data_ptr(), pg.flags.tab.data_ptr(), pg.world, pg.rank, st["ch"], st["seq"] & 0xFFFFFFFF, -1, 0, -1, 0,
-             _peer.TIMEOUT_NS, pg.status.data_ptr(), st["counter"].data_ptr(), 0, _stream())
+             _peer.TIMEOUT_NS, pg.status.data_ptr(), st["counter"].data_ptr(), p2p.max_ctas, _stream())
         return out[:n].view(t.shape)
 
 

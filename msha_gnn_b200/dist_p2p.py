@@ -77,6 +77,9 @@ class P2P:
         self.ex = {}
         self.copy_stream = torch.cuda.Stream(device=pg.device)
         self.chunks = max(1, PIPELINE_CHUNKS if chunks is None else chunks)
+        # ranks emulated on ONE GPU share its SM slots: fused kernels whose CTAs spin on another rank's flag must not fill
+        # the GPU, or the kernels that would set the flag cannot be scheduled (real ranks have a GPU each: no cap)
+        self.max_ctas = 24 if getattr(pg.fabric, "emulated", False) else 0
         self._staging = {}
         self._row_hubs = {}
 
@@ -180,7 +183,7 @@ class P2P:
                  L(*[n_max * w * 4 for w in ex.widths]), L(*[n_max * w * 4 for w in ex.widths]),
                  *self._flag_args((ex.ch_ready, self.chunk_value(ex.seq, self.chunks - 1)), (ex.ch_gdone, ex.gcount),
                                   (ex.ch_done, ex.seq)),
-                 ex.counter.data_ptr(), 0, _stream())
+                 ex.counter.data_ptr(), self.max_ctas, _stream())
             if not ex.uses_g2:
                 ex.gdone_checked = ex.gcount          # the kernel verified the peers' gdone flags
             return
@@ -259,7 +262,7 @@ class P2P:
         P, L, U = ctypes.c_void_p * nb, ctypes.c_int64 * nb, ctypes.c_uint64 * nb
         call("msha_peer_exchange_sum", nb, P(*[outs[k].data_ptr() for k in ks]), U(*[ex.grads[k].tab.data_ptr() for k in ks]),
              L(*[r * n_max * ex.widths[k] * 4 for k in ks]), L(*[n_max * ex.widths[k] for k in ks]),
-             *self._flag_args((wait_ch, g), (ex.ch_done, ex.seq), (done_ch, g)), ex.counter.data_ptr(), 0, _stream())
+             *self._flag_args((wait_ch, g), (ex.ch_done, ex.seq), (done_ch, g)), ex.counter.data_ptr(), self.max_ctas, _stream())
         ex.done_checked = ex.seq                      # the kernel verified the peers' forward "done" flags
 
 

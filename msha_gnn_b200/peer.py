@@ -135,6 +135,8 @@ class LocalFabric:
         self.world, self.device = int(world), device
         self._allocs = []
         self._lock = threading.Lock()                      # the emulated ranks may run in one host thread each
+        self._alloc_stream = torch.cuda.Stream(device=device)
+        self.emulated = True
         self.groups = [None] * world
         self.streams = [torch.cuda.Stream(device=device) for _ in range(world)]
         for r in range(world):
@@ -143,9 +145,12 @@ class LocalFabric:
     def alloc(self, group, index, shape, dtype, zero):
         with self._lock:
             if index == len(self._allocs):
-                mk = torch.zeros if zero else torch.empty
-                self._allocs.append([mk(shape, dtype=dtype, device=self.device) for _ in range(self.world)])
-                torch.cuda.current_stream().synchronize()      # zero-fill done before another rank's stream touches it
+                # on a stream of its own: the calling rank's stream may hold kernels that wait for flags of ranks which are
+                # themselves queueing for this lock -- synchronising THAT stream here would deadlock the emulation
+                with torch.cuda.stream(self._alloc_stream):
+                    mk = torch.zeros if zero else torch.empty
+                    self._allocs.append([mk(shape, dtype=dtype, device=self.device) for _ in range(self.world)])
+                self._alloc_stream.synchronize()               # zero-fill done before any rank's stream touches it
             views = self._allocs[index]
         if tuple(views[0].shape) != shape or views[0].dtype != dtype:
             raise RuntimeError("LocalFabric: ranks must allocate the same buffers in the same order")
@@ -162,6 +167,7 @@ class SymmFabric:
         require_eager_module_loading()
         import torch.distributed as dist
         self.dist = dist
+        self.emulated = False
         self.pg = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.pg)
         self.rank = dist.get_rank(self.pg)
