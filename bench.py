@@ -210,8 +210,8 @@ class KernelTimer:
 
     def _mods(self):
         import msha_gnn_b200.functional as f, msha_gnn_b200.graph as g, msha_gnn_b200.intra as i
-        import msha_gnn_b200.dist as d, msha_gnn_b200.peer as p
-        return [f, g, i, d, p]
+        import msha_gnn_b200.dist as d, msha_gnn_b200.peer as p, msha_gnn_b200.dist_p2p as dp, msha_gnn_b200.dist_msha as dm
+        return [f, g, i, d, p, dp, dm]
 
     def __exit__(self, *exc):
         self.ops.call = self.orig

@@ -17,6 +17,7 @@
 // of gat_kernels.cu.
 #include "common.cuh"
 #include "msha_b200.h"
+#include <stdlib.h>
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -32,14 +33,27 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     return t;
 }
 
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// mode 0: st.release.sys (the PTX-model way; its system-scope fence was measured at up to 0.4 ms under copy-engine traffic)
+// mode 1: fence.acq_rel.gpu + st.relaxed.sys -- the data the flag publishes was written by EARLIER KERNELS of this stream
+//         (complete, device-visible at the kernel boundary) and is read by the peers through this GPU's L2, the point of
+//         coherence for peer accesses; only the flag itself crosses NVLink
+// mode 2: st.relaxed.sys alone
 __global__ void peer_signal_kernel(const uint64_t* __restrict__ flag_tab, int world, int rank, int channel,
-                                   uint32_t peer_mask, const uint32_t* __restrict__ epoch, uint32_t value) {
+                                   uint32_t peer_mask, const uint32_t* __restrict__ epoch, uint32_t value, int mode) {
     const int q = threadIdx.x;
     if (q >= world || !((peer_mask >> q) & 1u)) return;
     const uint32_t v = value + (epoch ? *epoch : 0u);
-    // release at system scope is cumulative: the writes of the stream's earlier kernels happen-before this store
     uint32_t* f = reinterpret_cast<uint32_t*>(flag_tab[q]) + (int64_t)channel * world + rank;
-    st_release_sys(f, v);
+    if (mode == 0) {
+        st_release_sys(f, v);
+    } else {
+        if (mode == 1) __threadfence();
+        st_relaxed_sys(f, v);
+    }
 }
 
 __global__ void peer_wait_kernel(const uint32_t* __restrict__ flags, int world, int channel, uint32_t peer_mask,
@@ -65,7 +79,13 @@ MSHA_API int msha_peer_signal(const uint64_t* flag_tab, int world, int rank, int
                               const uint32_t* epoch, uint32_t value, void* stream) {
     MSHA_REQUIRE(flag_tab != nullptr && world >= 1 && world <= 32 && rank >= 0 && rank < world && channel >= 0,
                  "peer_signal: bad arguments");
-    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag_tab, world, rank, channel, peer_mask, epoch, value);
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("MSHA_PEER_SIGNAL_MODE");
+        mode = e ? atoi(e) : 1;
+        if (mode < 0 || mode > 2) mode = 1;
+    }
+    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag_tab, world, rank, channel, peer_mask, epoch, value, mode);
     MSHA_LAUNCH_OK();
     return 0;
 }
@@ -264,8 +284,8 @@ __device__ __forceinline__ void peer_finish(const PeerFlagOps& fo, unsigned int 
     if (q < fo.world && q != fo.rank) {
         if (fo.guard_ch >= 0) spin_flag(fo.flags + (int64_t)fo.guard_ch * fo.world + q, fo.guard_val, fo.timeout_ns, fo.status, q);
         if (fo.done_ch >= 0) {
-            __threadfence();
-            st_release_sys(reinterpret_cast<uint32_t*>(fo.flag_tab[q]) + (int64_t)fo.done_ch * fo.world + fo.rank, fo.done_val);
+            __threadfence();                              // the CTAs' stores (counted in through the atomic) before the flag
+            st_relaxed_sys(reinterpret_cast<uint32_t*>(fo.flag_tab[q]) + (int64_t)fo.done_ch * fo.world + fo.rank, fo.done_val);
         }
     }
     if (threadIdx.x == 0) *fo.counter = 0u;

@@ -75,7 +75,10 @@ class P2P:
     def __init__(self, pg, part, chunks: int = None):
         self.pg, self.part = pg, part
         self.ex = {}
-        self.copy_stream = torch.cuda.Stream(device=pg.device)
+        # high priority: its flag kernels are single CTAs that must get an SM slot while an attention kernel with 10^5 CTAs
+        # is being dispatched on the main stream -- at equal priority they wait until that grid has drained (measured: the
+        # copy chain then starts milliseconds late and the transfers stop overlapping)
+        self.copy_stream = torch.cuda.Stream(device=pg.device, priority=-1)
         self.chunks = max(1, PIPELINE_CHUNKS if chunks is None else chunks)
         # ranks emulated on ONE GPU share its SM slots: fused kernels whose CTAs spin on another rank's flag must not fill
         # the GPU, or the kernels that would set the flag cannot be scheduled (real ranks have a GPU each: no cap)
