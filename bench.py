@@ -514,6 +514,14 @@ def run_job(args, wl_name, steps, warmup, full=True):
         step(10_001, pos_dev)
     if p2p is not None:
         p2p.pg.check()
+        if p2p.trace is not None:                      # MSHA_P2P_TRACE=1: phase timeline of one step, per rank, to stderr
+            p2p.dump_trace()
+            step(10_002, pos_dev)
+            tl = p2p.dump_trace()
+            for rk in range(world):
+                if rk == rank:
+                    print(f"[p2p trace rank {rank}] " + " | ".join(f"{lab} {ms}" for lab, ms in tl), file=sys.stderr, flush=True)
+                dist.barrier()
     if rank == 0:
         tf32_peak = measure_tf32_peak(dev)
         agg = kt.summary()

@@ -294,6 +294,17 @@ int msha_peer_exchange_sum(int n_bufs, float* const* out, const uint64_t* const*
                            int wait_ch, uint32_t wait_val, int guard_ch, uint32_t guard_val, int done_ch, uint32_t done_val,
                            uint64_t timeout_ns, int32_t* status, uint32_t* counter, int max_ctas, void* stream);
 
+/* Halo exchange (the north-star's "halo all-gather of boundary features"): per rank the columns are renumbered to
+ * [own block | halo rows of peer 0 | halo rows of peer 1 | ...]; gather_rows packs the listed rows of the peers' own blocks
+ * into this rank's halo segments, scatter_add_rows (its adjoint) adds the peers' halo-segment gradients onto the listed rows
+ * of this rank's block.  lists: int32 row ids inside the owner's block; the per-peer arrays are DEVICE int64[world]
+ * (list_ptr: [world + 1]); see csrc/peer_kernels.cu. */
+int msha_peer_gather_rows(float* dst, const uint64_t* src_tab, int world, int rank, const int32_t* lists,
+                          const int64_t* list_beg, const int64_t* list_end, const int64_t* list_first,
+                          const int64_t* local_off, int64_t max_rows_per_peer, int64_t C, int max_ctas, void* stream);
+int msha_peer_scatter_add_rows(float* dst, const uint64_t* src_tab, int world, int rank, const int32_t* lists,
+                               const int64_t* list_ptr, const int64_t* remote_off, int64_t max_rows_per_peer, int64_t C,
+                               int max_ctas, void* stream);
 /* all-reduce (sum, rank order) of a small fp64 vector living at offset_bytes of every rank's peer-mapped buffer -- the
  * BatchNorm column statistics of a partitioned node axis; waits for every peer's flag first */
 int msha_peer_allreduce_f64(double* out, const uint64_t* src_tab, int64_t offset_bytes, int64_t n, const uint32_t* flags,

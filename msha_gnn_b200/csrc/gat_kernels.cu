@@ -80,14 +80,17 @@ gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ r
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * WPC + warp;
+    // the hub segments (the longest work items, up to seg_limit edges each) come FIRST in the grid: dispatched last they
+    // were the tail of every launch
     int row, beg, end, seg = -1;
-    if (w < n_rows) {
-        row = w; beg = rowptr[row]; end = rowend[row];
-        if (hub.seg_limit && end - beg > hub.seg_limit) return;         // handled segment-wise below
+    if (w >= hub.n_segs) {
+        row = w - hub.n_segs;
+        if (row >= n_rows) return;
+        beg = rowptr[row]; end = rowend[row];
+        if (hub.seg_limit && end - beg > hub.seg_limit) return;         // handled segment-wise
         if (PIPE && accumulate && beg == end) return;                   // nothing to add from this block
     } else {
-        seg = w - n_rows;
-        if (seg >= hub.n_segs) return;
+        seg = w;
         row = hub.seg_item[seg]; beg = hub.seg_beg[seg]; end = hub.seg_end[seg];
     }
     const bool part_mode = seg >= 0;       // partial (un-normalised) result of one segment; merged by gat_fwd_merge_kernel
@@ -674,12 +677,13 @@ spmm_csc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ 
     const int w0 = blockIdx.x * WPC + warp;
     int cidx, beg, end;
     bool part_mode = false;
-    if (w0 < n_cols) {
-        cidx = w0; beg = colptr[cidx]; end = colptr[cidx + 1];
+    if (w0 >= hub.n_segs) {                  // hub segments first in the grid (longest items: not the launch's tail)
+        cidx = w0 - hub.n_segs;
+        if (cidx >= n_cols) return;
+        beg = colptr[cidx]; end = colptr[cidx + 1];
         if (hub.seg_limit && end - beg > hub.seg_limit) return;
     } else {
-        const int seg = w0 - n_cols;
-        if (seg >= hub.n_segs) return;
+        const int seg = w0;
         cidx = hub.seg_item[seg]; beg = hub.seg_beg[seg]; end = hub.seg_end[seg];
         part_mode = true;                   // partial sums of one segment: atomically added (rows zeroed beforehand)
     }

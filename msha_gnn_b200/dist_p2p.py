@@ -85,6 +85,23 @@ class P2P:
         self.max_ctas = 24 if getattr(pg.fabric, "emulated", False) else 0
         self._staging = {}
         self._row_hubs = {}
+        self.trace = [] if os.environ.get("MSHA_P2P_TRACE") else None      # (label, event on the current stream)
+
+    def mark(self, label):
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream())
+            self.trace.append((label, e))
+
+    def dump_trace(self):
+        """-> [(label, ms since the first mark)] of the marks recorded so far; clears them."""
+        if not self.trace:
+            return []
+        torch.cuda.synchronize()
+        t0 = self.trace[0][1]
+        out = [(lab, round(t0.elapsed_time(e), 3)) for lab, e in self.trace]
+        self.trace = []
+        return out
 
     # ---------------------------------------------------------------------------------------------- bookkeeping
     def exchange(self, key, widths) -> Exchange:
@@ -126,7 +143,21 @@ class P2P:
         return h[1]
 
     def own_rows(self, ex, k=0):
-        return _alias_rows(ex.bufs[k].local, self.part.rank * self.part.n_max, self.part.n_local)
+        lo = 0 if getattr(ex, "plan", None) is not None else self.part.rank * self.part.n_max     # compact layout: own block first
+        return _alias_rows(ex.bufs[k].local, lo, self.part.n_local)
+
+    def halo_plan(self, graph):
+        hp = self._row_hubs.get(("halo", id(graph)))
+        if hp is None or hp[0] is not graph:
+            hp = self._row_hubs[("halo", id(graph))] = (graph, HaloPlan(self, graph))
+        return hp[1]
+
+    def halo_exchange(self, key, plan, widths):
+        ex = self.ex.get(key)
+        if ex is None:
+            ex = self.ex[key] = HaloExchange(self.pg, plan, widths)
+        assert ex.widths == tuple(widths) and ex.plan is plan, key
+        return ex
 
     def all_rows(self, ex, k=0):
         return _alias_rows(ex.bufs[k].local, 0, self.part.n_padded)
@@ -193,19 +224,27 @@ class P2P:
         main = torch.cuda.current_stream()
         cs = self.copy_stream
         cs.wait_event(ex.ev_start)                    # the local copies of the remote blocks are free from here on
+        big = [self.pipelined(w) for w in ex.widths]
         with torch.cuda.stream(cs):
+            # one flag wait per chunk (the ranks run in lockstep), then that chunk of every peer back to back: a kernel
+            # <-> copy-engine hand-over costs ~10 us, per peer and chunk that was 1 ms per exchange
             for c in range(self.chunks):
+                pg.wait(ex.ch_ready, self.chunk_value(ex.seq, c))
                 for s in range(1, W):
                     q = (r + s) % W
-                    pg.wait(ex.ch_ready, self.chunk_value(ex.seq, c), 1 << q)
                     rows = self.chunk_rows(q, c)
-                    for b in ex.bufs:
-                        pg.pull_block(b, q, rows)
-                    if c == self.chunks - 1:
-                        pg.signal(ex.ch_done, ex.seq, 1 << q)
+                    for k, b in enumerate(ex.bufs):
+                        if big[k]:
+                            pg.pull_block(b, q, rows)
+                self.mark(f"cs pulled chunk {c}")
+            for k, b in enumerate(ex.bufs):           # the narrow tensors (H scores per node): one SM pull at the end
+                if not big[k]:
+                    pg.pull_blocks_sm(b, n_max)
+            pg.signal(ex.ch_done, ex.seq)
             ev = torch.cuda.Event()
             ev.record(cs)
         main.wait_event(ev)
+        self.mark("main: gather complete")
 
     def gather(self, x_local, key):
         """[n_local, C] -> [world * n_max, C] (autograd: the backward is the reduce-scatter of the gathered gradient)."""
@@ -234,13 +273,13 @@ class P2P:
             cs.wait_event(ev0)
             own = self.block_rows(r)
             with torch.cuda.stream(cs):
+                pg.wait(ex.ch_gready, g)
                 for s in range(1, W):
                     q = (r - s) % W
-                    pg.wait(ex.ch_gready, g, 1 << q)
                     for k in range(nb):
                         if big[k]:
                             self.staging(ex.widths[k])[q, :part.n_local].copy_(ex.grads[k].views[q][own], non_blocking=True)
-                    pg.signal(ex.ch_gdone, g, 1 << q)
+                pg.signal(ex.ch_gdone, g)
                 ev = torch.cuda.Event()
                 ev.record(cs)
         if small:
@@ -325,6 +364,7 @@ class _AttentionRows(torch.autograd.Function):
         C = H * D
         dev = Wh_own.device
         assert ex.produced and Wh_own.data_ptr() == p2p.own_rows(ex, 0).data_ptr()
+        p2p.mark("fwd: layer start")
         p2p.pull(ex)
         ex.produced = False
         rp, col = graph.attention_csr()
@@ -346,6 +386,7 @@ class _AttentionRows(torch.autograd.Function):
                      ptr(scr), _stream())
             if chunk_hook is not None:
                 chunk_hook(c, lo, hi, out)
+            p2p.mark(f"fwd: chunk {c} done")
         ctx.p2p, ctx.ex, ctx.graph = p2p, ex, graph
         ctx.H, ctx.D, ctx.act, ctx.p, ctx.seed = H, D, act, p, seed
         ctx.save_for_backward(s_nbr_g, s_self, Wh_g, alpha, out if act != ACT_NONE else None)
@@ -367,6 +408,7 @@ class _AttentionRows(torch.autograd.Function):
         dev = alpha.device
         main = torch.cuda.current_stream()
         d_out = d_out.contiguous()
+        p2p.mark("bwd: layer start")
         if act != ACT_NONE:
             dz = torch.empty_like(d_out)
             call("msha_act_bwd", ptr(d_out), ptr(out), ptr(dz), N * C, act, LRELU_SLOPE, _stream())
@@ -383,17 +425,19 @@ class _AttentionRows(torch.autograd.Function):
         call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), part.n_padded, ptr(alpha), ptr(dz), H, D,
              ptr(dWh_g), 0, None, None, p, seed, graph.hub_cols().ptr, _stream())
         pg.signal(ex.ch_gready, g)
+        p2p.mark("bwd: column pass done")
         # the owners' copy engines fetch their blocks while the row pass runs
         stg = p2p.staging(C)
         own = p2p.block_rows(r)
         cs = p2p.copy_stream
         cs.wait_event(ev0)
         with torch.cuda.stream(cs):
+            pg.wait(ex.ch_gready, g)
             for s in range(1, W):
                 q = (r - s) % W
-                pg.wait(ex.ch_gready, g, 1 << q)
                 stg[q, :part.n_local].copy_(ex.grads[0].views[q][own], non_blocking=True)
-                pg.signal(ex.ch_gdone, g, 1 << q)
+            pg.signal(ex.ch_gdone, g)
+            p2p.mark("cs: grad blocks pulled")
             ev_p = torch.cuda.Event()
             ev_p.record(cs)
         # row pass: d alpha, softmax / LeakyReLU backward, d s_self
@@ -409,12 +453,16 @@ class _AttentionRows(torch.autograd.Function):
         call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), part.n_padded, None, None, H, D, None, 0,
              ptr(dlogit), ptr(ds_g), p, seed, graph.hub_cols().ptr, _stream())
         pg.signal(ex.ch_gready2, g)
+        p2p.mark("bwd: row pass + score sums done")
         ds_nbr = torch.empty((n_max, H), dtype=torch.float32, device=dev)
         p2p._sum_small(ex, [1], [None, ds_nbr], g, ex.ch_gready2, ex.ch_gdone2)
+        p2p.mark("bwd: d s_nbr summed")
         main.wait_event(ev_p)
+        p2p.mark("bwd: grad blocks here")
         dWh = torch.empty((part.n_local, C), dtype=torch.float32, device=dev)
         addrs = [ex.grads[0].addr[r] + r * n_max * C * 4 if q == r else stg[q].data_ptr() for q in range(W)]
         pg.sum_into(dWh, addrs, part.n_local * C)
+        p2p.mark("bwd: d Wh summed")
         return (dWh, ds_nbr[:part.n_local], ds_self) + (None,) * 10
 
 
@@ -430,11 +478,17 @@ def gat_encode_p2p(convs, x_local, pgraph: Graph, part, p2p: P2P, training=True,
     pg = p2p.pg
     K = p2p.chunks
     chained = None                                        # exchange whose own blocks the previous layer's hook produced
+    def layer_exchange(l_, conv_):
+        H_, C_ = conv_.heads, conv_.heads * conv_.out_features
+        big = p2p.pipelined(C_) and (H_ & (H_ - 1)) == 0 and conv_.out_features % 4 == 0
+        if big and HALO and H_ % 4 == 0:
+            return p2p.halo_exchange(("gat-halo", l_), p2p.halo_plan(pgraph), (C_, H_)), big
+        return p2p.exchange(("gat", l_), (C_, H_)), big
+
     for l, conv in enumerate(convs):
         H, D = conv.heads, conv.out_features
         C = H * D
-        ex = p2p.exchange(("gat", l), (C, H))
-        large = p2p.pipelined(C) and (H & (H - 1)) == 0 and D % 4 == 0
+        ex, large = layer_exchange(l, conv)
         fuse_elu = conv.activation == "elu" and conv.concat
         act = ACT_ELU if fuse_elu else ACT_NONE
         p = float(conv.dropout) if training else 0.0
@@ -452,8 +506,8 @@ def gat_encode_p2p(convs, x_local, pgraph: Graph, part, p2p: P2P, training=True,
         if large:
             hook, out_buf = None, None
             nxt = convs[l + 1] if l + 1 < len(convs) else None
-            if nxt is not None and fuse_elu and p2p.pipelined(nxt.heads * nxt.out_features):
-                nex = p2p.exchange(("gat", l + 1), (nxt.heads * nxt.out_features, nxt.heads))
+            if nxt is not None and fuse_elu and layer_exchange(l + 1, nxt)[1]:
+                nex = layer_exchange(l + 1, nxt)[0]
                 hook = _conv_hook(p2p, nex, nxt)
                 chained = nex
             elif nxt is None and score_key is not None and conv.concat:
@@ -462,7 +516,10 @@ def gat_encode_p2p(convs, x_local, pgraph: Graph, part, p2p: P2P, training=True,
                 out_buf = p2p.own_rows(exh, 0)
                 hook = (lambda c, lo, hi, out, _e=exh: p2p.publish(_e, c))
             seed = ops.next_seed() if p > 0 else 0
-            out = _AttentionRows.apply(Wh, s_nbr, s_self, p2p, ex, pgraph, H, D, act, p, seed, hook, out_buf)
+            if isinstance(ex, HaloExchange):
+                out = _AttentionHalo.apply(Wh, s_nbr, s_self, p2p, ex, H, D, act, p, seed, hook, out_buf)
+            else:
+                out = _AttentionRows.apply(Wh, s_nbr, s_self, p2p, ex, pgraph, H, D, act, p, seed, hook, out_buf)
         else:
             Wh_g, s_nbr_g = _Gather.apply(p2p, ex, Wh, s_nbr)
             out, _ = Fn.attention_block(pgraph, s_nbr_g, s_self, Wh_g, heads=H, act=act, dropout_p=conv.dropout,
@@ -494,3 +551,252 @@ def _conv_hook(p2p: P2P, nex: Exchange, conv):
                  own1.data_ptr() + 4 * lo * H, ptr(conv.a_self.detach().contiguous()), nex.s_self.data_ptr() + 4 * lo * H, _stream())
         p2p.publish(nex, c)
     return hook
+
+
+# =================================================================================================
+# Halo exchange (the north-star's "NVLink halo all-gather of boundary features"): a rank fetches only the feature rows its
+# own edges reference.  SURVEY.md section 8e expected the halo of a randomly permuted power-law graph to be "about
+# everything"; on the 100 M-edge R-MAT graph it is 38 % of the remote rows at 8 GPUs (a third of the nodes has no in-edge
+# at all, the median in-degree is 2) -- and the exchange, not the kernels, bounds the 8-GPU step.
+# =================================================================================================
+HALO = os.environ.get("MSHA_HALO", "1") != "0"
+
+
+class HaloPlan:
+    """Per rank and graph: which rows of every peer's block this rank's edges reference (``need``), the compact column
+    numbering ``[own block | halo of peer 0 | halo of peer 1 | ...]`` with the graph rebuilt in it, the same lists seen from
+    the owner's side (``give``: what each peer takes from this rank's block, for the gradient's way back), and the row-chunk
+    boundaries of the pipelined pulls.  Built once; two barriers over the fabric exchange the counts and the lists."""
+
+    def __init__(self, p2p: P2P, pgraph: Graph):
+        pg, part = p2p.pg, p2p.part
+        W, r, n_max = part.world, part.rank, part.n_max
+        dev = pgraph.device
+        K = p2p.chunks
+        rp, col = pgraph.attention_csr()
+        colp = col.long()
+        uniq, inv = torch.unique(colp, return_inverse=True)            # sorted padded ids = sorted by (owner, local row)
+        owner = torch.div(uniq, n_max, rounding_mode="floor")
+        cnt = torch.bincount(owner, minlength=W)
+        cnt[r] = 0
+        cnt_h = [int(c) for c in cnt.tolist()]
+        # ---- counts of every rank (symmetric meta buffer), then the lists
+        meta = pg.alloc((W, W), torch.int64)
+        lists_sym = pg.alloc((part.n_padded,), I32)
+        meta.local[r].copy_(cnt)
+        remote = owner != r
+        need = (uniq[remote] - owner[remote] * n_max).to(I32)          # rows inside the owner's block, concatenated by owner
+        lists_sym.local[: need.numel()].copy_(need)
+        pg.barrier()
+        all_cnt = torch.stack([meta.views[q][q] for q in range(W)]).cpu().tolist()      # all_cnt[q][p]: rank q needs from p
+        pad4 = lambda v: (v + 3) // 4 * 4
+
+        def offsets(counts, q):                                        # halo segment starts of rank q's compact numbering
+            off, o = [], n_max
+            for p_ in range(W):
+                off.append(o)
+                if p_ != q:
+                    o += pad4(counts[p_])
+            return off, o
+        self.hoff, n_compact = offsets(all_cnt[r], r)
+        self.n_compact = max(offsets(all_cnt[q], q)[1] for q in range(W))      # same buffer shape on every rank
+        need_ptr = [0]
+        for q in range(W):
+            need_ptr.append(need_ptr[-1] + (cnt_h[q] if q != r else 0))
+        self.need, self.need_ptr, self.cnt = need, need_ptr, cnt_h
+        # ---- the graph in compact numbering
+        comp = torch.empty_like(uniq)
+        comp[~remote] = uniq[~remote] - r * n_max
+        hoff_t = torch.tensor(self.hoff, dtype=torch.int64, device=dev)
+        ptr_t = torch.tensor(need_ptr[:-1], dtype=torch.int64, device=dev)
+        ro = owner[remote]
+        comp[remote] = hoff_t[ro] + (torch.arange(int(remote.sum()), device=dev) - ptr_t[ro])
+        self.graph = Graph(pgraph.rowptr, comp[inv].to(I32).contiguous(), pgraph.val, pgraph.n_rows, self.n_compact, isolated="zero")
+        self.graph.col_padded = col                                    # the gathered-layout ids (bench.py's parity block)
+        # ---- chunk boundaries of the pulls: chunk c of peer q = its rows [(n_q c) // K, (n_q (c+1)) // K)
+        i64 = dict(dtype=torch.int64, device=dev)
+        need_l = need.long()
+        self.chunk_args = []
+        for c in range(K):
+            beg, end = [0] * W, [0] * W
+            for q in range(W):
+                if q == r:
+                    continue
+                seg = need_l[need_ptr[q]:need_ptr[q + 1]]
+                lo_, hi_ = (part.sizes[q] * c) // K, (part.sizes[q] * (c + 1)) // K
+                b, e = torch.searchsorted(seg, torch.tensor([lo_, hi_], **i64)).tolist()
+                beg[q], end[q] = need_ptr[q] + b, need_ptr[q] + e
+            self.chunk_args.append((torch.tensor(beg, **i64), torch.tensor(end, **i64),
+                                    max(e_ - b_ for b_, e_ in zip(beg, end))))
+        self.list_first = torch.tensor(need_ptr[:-1], **i64)
+        self.local_off = torch.tensor(self.hoff, **i64)
+        # ---- the owner's view: what every peer takes from this rank's block, and where it sits in the peer's buffer
+        give, give_ptr, remote_off = [], [0], [0] * W
+        for q in range(W):
+            n_q = all_cnt[q][r] if q != r else 0
+            if q != r:
+                start = sum(all_cnt[q][p_] for p_ in range(r) if p_ != q)
+                give.append(lists_sym.views[q][start:start + n_q].clone())
+                remote_off[q] = offsets(all_cnt[q], q)[0][r]
+            give_ptr.append(give_ptr[-1] + n_q)
+        self.give = torch.cat(give) if give else torch.empty(0, dtype=I32, device=dev)
+        self.give_ptr = torch.tensor(give_ptr, **i64)
+        self.remote_off = torch.tensor(remote_off, **i64)
+        self.max_give = max([give_ptr[q + 1] - give_ptr[q] for q in range(W)] + [0])
+        pg.barrier()                                                   # nobody frees / reuses the list buffer under a reader
+        torch.cuda.current_stream().synchronize()
+        self.halo_rows = sum(cnt_h)
+        self.full_rows = sum(part.sizes) - part.n_local
+
+
+class HaloExchange:
+    """Buffers of one gathered tensor group in the compact numbering: ``bufs[k]`` / ``grads[k]`` are [n_compact, w] on every
+    rank; rows < n_max are the rank's own block (the only part peers read of ``bufs``), the rest its halo segments (the part
+    peers read of ``grads``)."""
+
+    def __init__(self, pg, plan: HaloPlan, widths):
+        self.widths = tuple(int(w) for w in widths)
+        self.plan = plan
+        self.bufs = [pg.alloc((plan.n_compact, w)) for w in self.widths]
+        self.grads = [pg.alloc((plan.n_compact, w), zero=True) for w in self.widths]
+        (self.ch_ready, self.ch_done, self.ch_gready, self.ch_gdone, self.ch_gready2, self.ch_gdone2) = (
+            pg.new_channel() for _ in range(6))
+        self.seq = self.gcount = self.done_checked = self.gdone_checked = 0
+        self.produced = False
+        self.uses_g2 = True
+        self.ev_start = None
+        self.s_self = None
+
+
+def _halo_own_rows(p2p, ex, k=0):
+    return _alias_rows(ex.bufs[k].local, 0, p2p.part.n_local)
+
+
+class _AttentionHalo(torch.autograd.Function):
+    """``_AttentionRows`` with the halo exchange: the pulls are ``msha_peer_gather_rows`` launches (listed rows of every
+    peer, chunk by chunk, on the high-priority side stream), the gradient's way back is ``msha_peer_scatter_add_rows``."""
+
+    @staticmethod
+    def forward(ctx, Wh_own, s_nbr_own, s_self, p2p: P2P, ex: HaloExchange, H, D, act, p, seed, chunk_hook, out_buf):
+        pg, part, plan = p2p.pg, p2p.part, ex.plan
+        graph = plan.graph
+        W, r = part.world, part.rank
+        C = H * D
+        dev = Wh_own.device
+        assert ex.produced and Wh_own.data_ptr() == ex.bufs[0].local.data_ptr()
+        p2p.mark("fwd: layer start")
+        main = torch.cuda.current_stream()
+        cs = p2p.copy_stream
+        cs.wait_event(ex.ev_start)
+        with torch.cuda.stream(cs):
+            for c in range(p2p.chunks):
+                beg, end, mx = plan.chunk_args[c]
+                pg.wait(ex.ch_ready, p2p.chunk_value(ex.seq, c))
+                for k, w in enumerate(ex.widths):
+                    call("msha_peer_gather_rows", ex.bufs[k].local.data_ptr(), ex.bufs[k].tab.data_ptr(), W, r, ptr(plan.need, I32),
+                         beg.data_ptr(), end.data_ptr(), plan.list_first.data_ptr(), plan.local_off.data_ptr(), mx, w,
+                         p2p.max_ctas, _stream())
+                p2p.mark(f"cs pulled chunk {c}")
+            pg.signal(ex.ch_done, ex.seq)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        main.wait_event(ev)
+        p2p.mark("main: gather complete")
+        ex.produced = False
+        rp, col = graph.attention_csr()
+        N, E = graph.n_rows, col.numel()
+        Wh_g, s_nbr_g = ex.bufs[0].local, ex.bufs[1].local
+        s_self = s_self.contiguous()
+        alpha = torch.empty((E, H), dtype=torch.float32, device=dev)
+        out = out_buf if out_buf is not None else torch.empty((N, C), dtype=torch.float32, device=dev)
+        lib = ops._lib.lib()
+        for c in range(p2p.chunks):
+            lo, hi = p2p.local_chunk(c)
+            if hi > lo:
+                hub = p2p.row_chunk_hub(graph, c)
+                scr = None
+                if hub.n_segs:
+                    scr = torch.empty(lib.msha_gat_fwd_hub_scratch_floats(hub.n_segs, H, D), dtype=torch.float32, device=dev)
+                call("msha_gat_fwd", rp.data_ptr() + 4 * lo, ptr(col, I32), hi - lo, ptr(s_nbr_g), s_self.data_ptr() + 4 * lo * H,
+                     ptr(Wh_g), H, D, LRELU_SLOPE, None, ptr(alpha), out.data_ptr() + 4 * lo * C, act, None, p, seed, hub.ptr,
+                     ptr(scr), _stream())
+            if chunk_hook is not None:
+                chunk_hook(c, lo, hi, out)
+            p2p.mark(f"fwd: chunk {c} done")
+        ctx.p2p, ctx.ex = p2p, ex
+        ctx.H, ctx.D, ctx.act, ctx.p, ctx.seed = H, D, act, p, seed
+        ctx.save_for_backward(s_nbr_g, s_self, Wh_g, alpha, out if act != ACT_NONE else None)
+        if out_buf is not None:
+            ctx.mark_dirty(out_buf)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        s_nbr_g, s_self, Wh_g, alpha, out = ctx.saved_tensors
+        p2p, ex = ctx.p2p, ctx.ex
+        plan = ex.plan
+        graph = plan.graph
+        H, D, act, p, seed = ctx.H, ctx.D, ctx.act, ctx.p, ctx.seed
+        pg, part = p2p.pg, p2p.part
+        W, r = part.world, part.rank
+        C = H * D
+        rp, col = graph.attention_csr()
+        colptr, rowidx, perm = graph.attention_csc()
+        N, M = graph.n_rows, graph.n_cols
+        dev = alpha.device
+        main = torch.cuda.current_stream()
+        d_out = d_out.contiguous()
+        p2p.mark("bwd: layer start")
+        if act != ACT_NONE:
+            dz = torch.empty_like(d_out)
+            call("msha_act_bwd", ptr(d_out), ptr(out), ptr(dz), N * C, act, LRELU_SLOPE, _stream())
+        else:
+            dz = d_out
+        dWh_g = p2p.grad_buffer(ex, 0)
+        ds_g = p2p.grad_buffer(ex, 1)
+        ex.gcount += 1
+        g = ex.gcount
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(dz), H, D, ptr(dWh_g), 0,
+             None, None, p, seed, graph.hub_cols().ptr, _stream())
+        pg.signal(ex.ch_gready, g)
+        p2p.mark("bwd: column pass done")
+        ev1 = torch.cuda.Event()
+        ev1.record(main)
+        cs = p2p.copy_stream
+        cs.wait_event(ev1)                                    # this rank's own block of d Wh is complete: peers' rows add onto it
+        with torch.cuda.stream(cs):
+            pg.wait(ex.ch_gready, g)
+            call("msha_peer_scatter_add_rows", dWh_g.data_ptr(), ex.grads[0].tab.data_ptr(), W, r, ptr(plan.give, I32),
+                 plan.give_ptr.data_ptr(), plan.remote_off.data_ptr(), plan.max_give, C, p2p.max_ctas, _stream())
+            pg.signal(ex.ch_gdone, g)
+            p2p.mark("cs: grad rows added")
+            ev_p = torch.cuda.Event()
+            ev_p.record(cs)
+        E = alpha.shape[0]
+        dlogit = torch.empty_like(alpha)
+        ds_self = torch.empty((N, H), dtype=torch.float32, device=dev)
+        hub = graph.hub_rows()
+        r_buf = torch.empty((N, H), dtype=torch.float32, device=dev) if hub.n_segs else None
+        call("msha_gat_bwd_rows", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr_g), ptr(s_self), LRELU_SLOPE, ptr(alpha),
+             ptr(Wh_g), ptr(dz), None, ACT_NONE, None, None, None, None, None, H, D, ptr(dlogit), ptr(ds_self), p, seed,
+             hub.ptr, ptr(r_buf), int(E // max(N, 1)), _stream())
+        call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, None, None, H, D, None, 0,
+             ptr(dlogit), ptr(ds_g), p, seed, graph.hub_cols().ptr, _stream())
+        pg.signal(ex.ch_gready2, g)
+        p2p.mark("bwd: row pass + score sums done")
+        pg.wait(ex.ch_gready2, g)
+        call("msha_peer_scatter_add_rows", ds_g.data_ptr(), ex.grads[1].tab.data_ptr(), W, r, ptr(plan.give, I32),
+             plan.give_ptr.data_ptr(), plan.remote_off.data_ptr(), plan.max_give, H, p2p.max_ctas, _stream())
+        pg.signal(ex.ch_gdone2, g)
+        # the forward reuse guard of this exchange: the peers' "done" flags of gather ex.seq
+        pg.wait(ex.ch_done, ex.seq)
+        ex.done_checked = ex.seq
+        p2p.mark("bwd: d s_nbr summed")
+        main.wait_event(ev_p)
+        p2p.mark("bwd: grad rows here")
+        # the sums live in this rank's own block of the gradient buffers; hand out copies (the buffers are reused next step)
+        dWh = dWh_g[:part.n_local].clone()
+        ds_nbr = ds_g[:part.n_local].clone()
+        return (dWh, ds_nbr, ds_self) + (None,) * 9

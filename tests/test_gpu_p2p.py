@@ -149,9 +149,12 @@ def _emulate(world, N, rows, cols, convs_ref, predictor_ref, x_full, src, dst, l
     return state
 
 
-@pytest.mark.parametrize("world,pipelined", [(2, False), (3, False), (2, True), (3, True)])
+@pytest.mark.parametrize("world,pipelined", [(2, False), (3, False), (2, "rows"), (3, "rows"), (2, "halo"), (3, "halo")])
 def test_emulated_ranks_p2p_match_full_graph(world, pipelined, monkeypatch):
+    """flat: fused exchange kernels; rows: copy-engine pulls of whole blocks under row chunks; halo: only the referenced rows
+    (compact column numbering, msha_peer_gather_rows / msha_peer_scatter_add_rows)."""
     monkeypatch.setattr(mp2p, "PIPELINE_MIN_BLOCK_BYTES", 0 if pipelined else 1 << 40)
+    monkeypatch.setattr(mp2p, "HALO", pipelined == "halo")
     monkeypatch.setattr(mgraph, "SEG_LIMIT", 32)               # hub rows and hub columns on every rank
     N, Fin, H, d, P = 403, 24, 4, 8, 3000
     rows, cols = _power_law_graph(N, 11 + world)
@@ -192,7 +195,7 @@ def test_emulated_ranks_p2p_match_full_graph(world, pipelined, monkeypatch):
 def test_second_step_reuses_buffers(monkeypatch):
     """Two consecutive steps through the same exchanges (reuse guards, sequence numbers) give the same result twice."""
     monkeypatch.setattr(mp2p, "PIPELINE_MIN_BLOCK_BYTES", 0)
-    world, N, Fin, H, d = 2, 200, 16, 2, 8
+    world, N, Fin, H, d = 2, 200, 16, 4, 8
     rows, cols = _power_law_graph(N, 1)
     torch.manual_seed(0)
     convs = torch.nn.ModuleList([mg.GATConv(Fin, d, H)]).to(DEV)

@@ -35,8 +35,9 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-for name, thr in (("flat", (1 << 40, 1 << 40)), ("pipelined", (0, 0))):
+for name, thr in (("flat", (1 << 40, 1 << 40)), ("pipelined-rows", (0, 0)), ("pipelined-halo", (0, 1))):
     mp2p.PIPELINE_MIN_BLOCK_BYTES = thr[0]
+    mp2p.HALO = bool(thr[1])
     fab = peer.LocalFabric(W_, dev)
     res = [None] * W_
 
