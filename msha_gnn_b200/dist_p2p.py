@@ -35,7 +35,10 @@ from .ops import ACT_ELU, ACT_NONE, LRELU_SLOPE, _stream, call, ptr
 
 I32 = torch.int32
 PIPELINE_MIN_BLOCK_BYTES = int(os.environ.get("MSHA_PIPELINE_MIN_BYTES", str(16 << 20)))
-PIPELINE_CHUNKS = int(os.environ.get("MSHA_PIPELINE_CHUNKS", "4"))
+# row chunks of the pipelined regime; 0 = by exchange kind: 1 (sequential) with the halo exchange -- its volume is small and
+# its SM copy kernels interfere with the attention kernels they would overlap (8 GPUs: 46.8 ms overlapped in 4 chunks) -- and 4
+# with the whole-block copy-engine exchange
+PIPELINE_CHUNKS = int(os.environ.get("MSHA_PIPELINE_CHUNKS", "0"))
 
 
 def _alias_rows(base: torch.Tensor, lo: int, n: int) -> torch.Tensor:
@@ -79,7 +82,8 @@ class P2P:
         # is being dispatched on the main stream -- at equal priority they wait until that grid has drained (measured: the
         # copy chain then starts milliseconds late and the transfers stop overlapping)
         self.copy_stream = torch.cuda.Stream(device=pg.device, priority=-1)
-        self.chunks = max(1, PIPELINE_CHUNKS if chunks is None else chunks)
+        want = PIPELINE_CHUNKS if chunks is None else chunks
+        self.chunks = want if want >= 1 else (1 if HALO else 4)
         # ranks emulated on ONE GPU share its SM slots: fused kernels whose CTAs spin on another rank's flag must not fill
         # the GPU, or the kernels that would set the flag cannot be scheduled (real ranks have a GPU each: no cap)
         self.max_ctas = 24 if getattr(pg.fabric, "emulated", False) else 0
@@ -756,46 +760,68 @@ class _AttentionHalo(torch.autograd.Function):
         ds_g = p2p.grad_buffer(ex, 1)
         ex.gcount += 1
         g = ex.gcount
-        ev0 = torch.cuda.Event()
-        ev0.record(main)
-        call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(dz), H, D, ptr(dWh_g), 0,
-             None, None, p, seed, graph.hub_cols().ptr, _stream())
-        pg.signal(ex.ch_gready, g)
-        p2p.mark("bwd: column pass done")
-        ev1 = torch.cuda.Event()
-        ev1.record(main)
-        cs = p2p.copy_stream
-        cs.wait_event(ev1)                                    # this rank's own block of d Wh is complete: peers' rows add onto it
-        with torch.cuda.stream(cs):
-            pg.wait(ex.ch_gready, g)
-            call("msha_peer_scatter_add_rows", dWh_g.data_ptr(), ex.grads[0].tab.data_ptr(), W, r, ptr(plan.give, I32),
-                 plan.give_ptr.data_ptr(), plan.remote_off.data_ptr(), plan.max_give, C, p2p.max_ctas, _stream())
-            pg.signal(ex.ch_gdone, g)
-            p2p.mark("cs: grad rows added")
-            ev_p = torch.cuda.Event()
-            ev_p.record(cs)
         E = alpha.shape[0]
         dlogit = torch.empty_like(alpha)
         ds_self = torch.empty((N, H), dtype=torch.float32, device=dev)
         hub = graph.hub_rows()
         r_buf = torch.empty((N, H), dtype=torch.float32, device=dev) if hub.n_segs else None
-        call("msha_gat_bwd_rows", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr_g), ptr(s_self), LRELU_SLOPE, ptr(alpha),
-             ptr(Wh_g), ptr(dz), None, ACT_NONE, None, None, None, None, None, H, D, ptr(dlogit), ptr(ds_self), p, seed,
-             hub.ptr, ptr(r_buf), int(E // max(N, 1)), _stream())
-        call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, None, None, H, D, None, 0,
-             ptr(dlogit), ptr(ds_g), p, seed, graph.hub_cols().ptr, _stream())
-        pg.signal(ex.ch_gready2, g)
-        p2p.mark("bwd: row pass + score sums done")
-        pg.wait(ex.ch_gready2, g)
-        call("msha_peer_scatter_add_rows", ds_g.data_ptr(), ex.grads[1].tab.data_ptr(), W, r, ptr(plan.give, I32),
-             plan.give_ptr.data_ptr(), plan.remote_off.data_ptr(), plan.max_give, H, p2p.max_ctas, _stream())
-        pg.signal(ex.ch_gdone2, g)
-        # the forward reuse guard of this exchange: the peers' "done" flags of gather ex.seq
-        pg.wait(ex.ch_done, ex.seq)
-        ex.done_checked = ex.seq
-        p2p.mark("bwd: d s_nbr summed")
-        main.wait_event(ev_p)
-        p2p.mark("bwd: grad rows here")
+
+        def row_pass():
+            call("msha_gat_bwd_rows", ptr(rp, I32), ptr(col, I32), N, ptr(s_nbr_g), ptr(s_self), LRELU_SLOPE, ptr(alpha),
+                 ptr(Wh_g), ptr(dz), None, ACT_NONE, None, None, None, None, None, H, D, ptr(dlogit), ptr(ds_self), p, seed,
+                 hub.ptr, ptr(r_buf), int(E // max(N, 1)), _stream())
+
+        def add_rows(k, w):
+            call("msha_peer_scatter_add_rows", ex.grads[k].local.data_ptr(), ex.grads[k].tab.data_ptr(), W, r, ptr(plan.give, I32),
+                 plan.give_ptr.data_ptr(), plan.remote_off.data_ptr(), plan.max_give, w, p2p.max_ctas, _stream())
+
+        if p2p.chunks == 1:
+            # sequential: the halo is small (38 % of the remote rows at 8 GPUs), so the overlapped order below -- which has to
+            # split the column pass in two and lets an SM copy kernel run beside the row pass -- costs more than it hides
+            row_pass()
+            call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(dz), H, D, ptr(dWh_g), 0,
+                 ptr(dlogit), ptr(ds_g), p, seed, graph.hub_cols().ptr, _stream())
+            pg.signal(ex.ch_gready, g)
+            p2p.mark("bwd: row + column pass done")
+            pg.wait(ex.ch_gready, g)
+            add_rows(0, C)
+            add_rows(1, H)
+            pg.signal(ex.ch_gdone, g)
+            pg.signal(ex.ch_gdone2, g)
+            pg.wait(ex.ch_done, ex.seq)                       # forward reuse guard of this exchange
+            ex.done_checked = ex.seq
+            p2p.mark("bwd: grad rows added")
+        else:
+            ev0 = torch.cuda.Event()
+            ev0.record(main)
+            call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, ptr(alpha), ptr(dz), H, D, ptr(dWh_g), 0,
+                 None, None, p, seed, graph.hub_cols().ptr, _stream())
+            pg.signal(ex.ch_gready, g)
+            p2p.mark("bwd: column pass done")
+            ev1 = torch.cuda.Event()
+            ev1.record(main)
+            cs = p2p.copy_stream
+            cs.wait_event(ev1)                                # this rank's own block of d Wh is complete: peers' rows add onto it
+            with torch.cuda.stream(cs):
+                pg.wait(ex.ch_gready, g)
+                add_rows(0, C)
+                pg.signal(ex.ch_gdone, g)
+                p2p.mark("cs: grad rows added")
+                ev_p = torch.cuda.Event()
+                ev_p.record(cs)
+            row_pass()
+            call("msha_spmm_csc", ptr(colptr, I32), ptr(rowidx, I32), ptr(perm, I32), M, None, None, H, D, None, 0,
+                 ptr(dlogit), ptr(ds_g), p, seed, graph.hub_cols().ptr, _stream())
+            pg.signal(ex.ch_gready2, g)
+            p2p.mark("bwd: row pass + score sums done")
+            pg.wait(ex.ch_gready2, g)
+            add_rows(1, H)
+            pg.signal(ex.ch_gdone2, g)
+            pg.wait(ex.ch_done, ex.seq)                       # forward reuse guard of this exchange
+            ex.done_checked = ex.seq
+            p2p.mark("bwd: d s_nbr summed")
+            main.wait_event(ev_p)
+            p2p.mark("bwd: grad rows here")
         # the sums live in this rank's own block of the gradient buffers; hand out copies (the buffers are reused next step)
         dWh = dWh_g[:part.n_local].clone()
         ds_nbr = ds_g[:part.n_local].clone()

@@ -149,12 +149,14 @@ def _emulate(world, N, rows, cols, convs_ref, predictor_ref, x_full, src, dst, l
     return state
 
 
-@pytest.mark.parametrize("world,pipelined", [(2, False), (3, False), (2, "rows"), (3, "rows"), (2, "halo"), (3, "halo")])
+@pytest.mark.parametrize("world,pipelined", [(2, False), (3, False), (2, "rows"), (3, "rows"), (2, "halo"), (3, "halo"),
+                                             (3, "halo-seq")])
 def test_emulated_ranks_p2p_match_full_graph(world, pipelined, monkeypatch):
     """flat: fused exchange kernels; rows: copy-engine pulls of whole blocks under row chunks; halo: only the referenced rows
     (compact column numbering, msha_peer_gather_rows / msha_peer_scatter_add_rows)."""
     monkeypatch.setattr(mp2p, "PIPELINE_MIN_BLOCK_BYTES", 0 if pipelined else 1 << 40)
-    monkeypatch.setattr(mp2p, "HALO", pipelined == "halo")
+    monkeypatch.setattr(mp2p, "HALO", str(pipelined).startswith("halo"))
+    monkeypatch.setattr(mp2p, "PIPELINE_CHUNKS", 1 if pipelined == "halo-seq" else 4)   # 1: sequential halo exchange
     monkeypatch.setattr(mgraph, "SEG_LIMIT", 32)               # hub rows and hub columns on every rank
     N, Fin, H, d, P = 403, 24, 4, 8, 3000
     rows, cols = _power_law_graph(N, 11 + world)

@@ -60,7 +60,7 @@ for construction, tol in (("positive", 1e-4), ("signed", 2e-2)):
     model.zero_grad(set_to_none=True)
     modes = [("nccl+early-rs", None), ("nccl", None)]
     if fabric is not None:
-        modes += [("p2p-flat", (1 << 40, 0)), ("p2p-rows", (0, 0)), ("p2p-halo", (0, 1))]
+        modes += [("p2p-flat", (1 << 40, 0, 4)), ("p2p-rows", (0, 0, 4)), ("p2p-halo", (0, 1, 4)), ("p2p-halo-seq", (0, 1, 1))]
     for overlap, thresholds in modes:
         xl = x_full[part.lo:part.hi].clone().requires_grad_(True)
         if thresholds is None:
@@ -68,7 +68,7 @@ for construction, tol in (("positive", 1e-4), ("signed", 2e-2)):
             out = md.score_pairs(model.predictor, h, src_d[lo:hi], dst_d[lo:hi], part)
         else:
             mp2p.PIPELINE_MIN_BLOCK_BYTES, mp2p.HALO = thresholds[0], bool(thresholds[1])
-            p2p = md.P2P(fabric.group, part)
+            p2p = md.P2P(fabric.group, part, chunks=thresholds[2])
             h = md.gat_encode_p2p(model.convs, xl, pg, part, p2p, score_key="score_h")
             out = md.score_pairs(model.predictor, h, src_d[lo:hi], dst_d[lo:hi], part, p2p=p2p)
         (out * G[lo:hi]).sum().backward()
