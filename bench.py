@@ -973,16 +973,33 @@ def run_flow(args):
     kernels = [{"call": f, "launches_per_step": c // 2, "avg_ms": round(ms / c, 4), "share": round(ms / tot, 4)}
                for f, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])][:10]
     layers = 3                                                                    # 2 heads + out_att applications
+    # SURVEY 8d algorithmic bytes of one step (fp32, int32 indices): the inter-scale attention of H = 2 heads fwd+bwd with its
+    # three transposed passes, the node terms of both sides, BatchNorm (7 passes over (N + M, C)), the dense elu(u @ v.T) score
+    # matrix and log-softmax (8 passes over (N, H*M) / (N, M)), the degenerate out_att layer (a-1); the intra scales of the
+    # full model add the batch rows' group lists
+    Hh, dd, Fin = 2, 64, 128
+    Cc = Hh * dd
+    alg_bytes = (E * ((16 + 24 * Hh + 12 * Cc) + 3 * (8 + 4 * Hh + 4 * Cc)) + (N + M) * (12 * Fin + 20 * Cc) + 7 * (N + M) * Cc * 4
+                 + 8 * N * Hh * M * 4 + N * (12 * Hh * M + 8 * M) + 8 * E)
+    if full:
+        alg_bytes += 2 * B * (N // 291 + N // 25) * 4 * dd * Hh
+    hbm_peak, _, peak_src = load_peaks()
     out = {"metric": "gat_fwd_bwd_layer_edges_per_sec", "value": E * layers / (ms_dev / 1e3), "unit": "edges/s", "n_gpus": 1,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{args.workload}: 2015-shaped flow graph N={N}, M={M}, nnz={E} ({src.size} records), "
                                   f"{'Ours' if full else 'ablation3'}(in=128,out=64,H=2,p=0.5), batch {B}, nll_loss, Adam "
                                   "(train.py:206-232)",
+                      "dropout": 0.5,
                       "l2_policy": "graph and parameters (~50 MB) are L2-resident by nature of the workload; launch/latency bound"},
            "e2e": {"value": E * layers / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": 2 * B * 8, "d2h_bytes_per_step": 4},
-           "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "kernels": kernels, "loss": loss_host, **graph_info}
+           "gpu_launches": int(launches), "clocks": clocks,
+           "roofline": {"bound": "hbm", "kernel": "whole step (~60 kernels on a graph that fits the L2; launch / latency bound)",
+                        "achieved": alg_bytes / (ms_dev / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (ms_dev / 1e3) / 1e9 / hbm_peak, "traffic": None,
+                        "note": "algorithmic bytes of the step (SURVEY 8d a-3 / a-1 models) / device step time; " + peak_src},
+           "kernels": kernels, "loss": loss_host, **graph_info}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = flow_cpu_baseline(src, dst, N, M, B, reps=2)
     print(json.dumps(out))

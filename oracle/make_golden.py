@@ -86,6 +86,26 @@ def case_gat(save):
     save("gat", d)
 
 
+def case_gat_h8(save):
+    """BASELINE.json configs[1]: GAT(n_features=32, n_classes=32, n_heads=8) -- the head count and widths train.py:199 /
+    LLP.py:290-295 use (the `gat` case above has 2 heads of width 8)."""
+    GATm = ref_import.import_module("GAT")
+    gen = torch.Generator().manual_seed(112)
+    N, M, H = 67, 32, 8
+    gdp = {str(i): float(v) for i, v in enumerate(torch.rand(N, generator=gen))}
+    torch.manual_seed(12)
+    model = GATm.GAT(n_features=M, n_classes=M, n_heads=H, dropout=0.0, gdp=gdp, N=N)
+    adj = _rand_adj(N, M, 0.08, gen, iso_rows=(5, 40))
+    model.train()
+    out = model(adj)
+    G = torch.randn(N, M, generator=gen)
+    grads = _grads(out, G, list(model.parameters()))
+    d = dict(adj=_np(adj), G=_np(G), out=_np(out), gdp=np.array(list(gdp.values()), dtype=np.float64), **_state(model))
+    for (name, _), g in zip(model.named_parameters(), grads):
+        d["g." + name] = _np(g)
+    save("gat_h8", d)
+
+
 def _msha_inputs(gen, N, M, Fin, iso_rows=(3,)):
     S = torch.rand(N, Fin, generator=gen)
     R = torch.rand(M, Fin, generator=gen)
@@ -450,7 +470,7 @@ def main():
 
     torch.set_num_threads(1)
     for fn in (case_gal, case_gat, case_ours_layers, case_ours_record, case_msha_models, case_hgane,
-               case_linkpred, case_gcn, case_generic_gat, case_dataset, case_llp, case_baselines):
+               case_linkpred, case_gcn, case_generic_gat, case_dataset, case_llp, case_baselines, case_gat_h8):
         fn(save)
 
 

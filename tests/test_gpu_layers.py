@@ -54,12 +54,14 @@ def test_graph_attention_layer_golden():
         layer(x, torch.ones(37, 9, device=DEV))          # adj.shape must equal (N, out_features)
 
 
-@pytest.mark.parametrize("via", ["dense", "edge_index", "graph"])
-def test_gat_model_golden(via):
-    g = load_golden("gat")
+@pytest.mark.parametrize("via,name,H", [("dense", "gat", 2), ("edge_index", "gat", 2), ("graph", "gat", 2),
+                                        ("dense", "gat_h8", 8), ("graph", "gat_h8", 8)])
+def test_gat_model_golden(via, name, H):
+    """gat_h8: BASELINE.json configs[1]'s GAT(32, 32, 8 heads) -- golden from the unmodified GAT.py."""
+    g = load_golden(name)
     N, M = g["adj"].shape
     gdp = {str(i): float(v) for i, v in enumerate(g["gdp"])}
-    model = _load(mg.GAT(M, M, 2, 0.0, gdp, N), params_of(g))
+    model = _load(mg.GAT(M, M, H, 0.0, gdp, N), params_of(g))
     model.train()
     adj = _t(g["adj"])
     if via == "edge_index":
@@ -73,7 +75,7 @@ def test_gat_model_golden(via):
     assert rel_err(_np(out), g["out"]) < TOL
     (out * _t(g["G"])).sum().backward()
     named = dict(model.named_parameters())
-    _check_grads(named, g, ["features", "attention_0.W", "attention_1.W", "out_att.W"])
+    _check_grads(named, g, ["features", "out_att.W"] + [f"attention_{i}.W" for i in range(H)])
     out2 = model(model.features, adj)                    # LLP.py:163 signature
     assert rel_err(_np(out2), g["out"]) < TOL
 
@@ -249,6 +251,36 @@ def test_gat_conv_vs_oracle(N, Fin, H, d, density, concat, seg_limit, monkeypatc
     leaves = [torch.tensor(a, dtype=torch.float64, requires_grad=True)
               for a in (x, _np(conv.W), _np(conv.a_nbr), _np(conv.a_self))]
     ref = O.gat_layer(*leaves, rowptr, col, H, concat=concat)
+    (ref * torch.tensor(G, dtype=torch.float64)).sum().backward()
+    assert rel_err(_np(out), ref.detach().numpy()) < TOL
+    for got, lf, name in zip((xg.grad, conv.W.grad, conv.a_nbr.grad, conv.a_self.grad), leaves, "x W a_nbr a_self".split()):
+        assert rel_err(_np(got), lf.grad.numpy()) < TOL, name
+
+
+def test_gat_conv_hub_row_at_the_production_segment_length(monkeypatch):
+    """The segment length the large graphs run with (1 024, graph.SEG_LIMIT_MAX): one row and one column with 2 600 entries
+    (3 segments each, the last one ragged), the cfg-3/4 layer shape (H = 8, d' = 32, C = 256), against the fp64 oracle
+    (Ablation.py:262-274 arithmetic) -- output, input and parameter gradients."""
+    monkeypatch.setattr(mg.graph, "SEG_LIMIT", 1024)
+    rng = np.random.default_rng(1024)
+    N, Fin, H, d = 2600, 32, 8, 32
+    adj = (rng.random((N, N)) < 0.004).astype(np.float32)
+    adj[np.arange(N), np.arange(N)] = 1
+    adj[17, :] = 1                                        # hub row: 2 600 neighbours
+    adj[:, 99] = 1                                        # hub column: referenced by every row
+    x = rng.random((N, Fin)).astype(np.float32)
+    torch.manual_seed(7)
+    conv = mg.GATConv(Fin, d, heads=H, concat=True).to(DEV)
+    xg = _t(x, grad=True)
+    graph = mg.Graph.from_dense(_t(adj))
+    assert graph.hub_rows().struct.seg_limit == 1024 and graph.hub_rows().n_segs == 3 and graph.hub_cols().n_segs == 3
+    out = conv(xg, graph)
+    G = rng.standard_normal(out.shape).astype(np.float32)
+    (out * _t(G)).sum().backward()
+    rowptr, col, _ = O.csr_from_dense(adj)
+    leaves = [torch.tensor(a, dtype=torch.float64, requires_grad=True)
+              for a in (x, _np(conv.W), _np(conv.a_nbr), _np(conv.a_self))]
+    ref = O.gat_layer(*leaves, rowptr, col, H)
     (ref * torch.tensor(G, dtype=torch.float64)).sum().backward()
     assert rel_err(_np(out), ref.detach().numpy()) < TOL
     for got, lf, name in zip((xg.grad, conv.W.grad, conv.a_nbr.grad, conv.a_self.grad), leaves, "x W a_nbr a_self".split()):

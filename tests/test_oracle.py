@@ -96,15 +96,16 @@ def test_graph_attention_layer():
     assert np.max(np.abs(g["ga"])) < 1e-5 and np.max(np.abs(ga.numpy())) < 1e-12
 
 
-def test_gat_model():
-    g = load_golden("gat")
+@pytest.mark.parametrize("name,H", [("gat", 2), ("gat_h8", 8)])
+def test_gat_model(name, H):
+    g = load_golden(name)
     p = params_of(g)
     rowptr, col, _ = O.csr_from_dense(g["adj"])
     leaves = {k: _leaf(v) for k, v in p.items()}
-    heads = [(leaves[f"attention_{i}.W"], leaves[f"attention_{i}.a"]) for i in range(2)]
+    heads = [(leaves[f"attention_{i}.W"], leaves[f"attention_{i}.a"]) for i in range(H)]
     out = O.gat_model(leaves["features"], heads, (leaves["out_att.W"], leaves["out_att.a"]), rowptr, col)
     assert rel_err(out.detach().numpy(), g["out"]) < TOL
-    names = ["features", "attention_0.W", "attention_1.W", "out_att.W"]
+    names = ["features", "out_att.W"] + [f"attention_{i}.W" for i in range(H)]
     grads = _grad(out, g["G"], [leaves[n] for n in names])
     for n, gr in zip(names, grads):
         assert rel_err(gr.numpy(), g["g." + n]) < 5e-5, n
@@ -394,7 +395,7 @@ def test_committed_goldens_regenerate_bit_for_bit(tmp_path, monkeypatch):
     monkeypatch.setattr(mgold, "OUT", str(tmp_path))
     mgold.main()
     names = sorted(f for f in os.listdir(committed) if f.endswith(".npz"))
-    assert names == sorted(os.listdir(tmp_path)) and len(names) == 26
+    assert names == sorted(os.listdir(tmp_path)) and len(names) == 27
     for f in names:
         with np.load(os.path.join(committed, f)) as a, np.load(os.path.join(tmp_path, f)) as b:
             assert set(a.files) == set(b.files), f
