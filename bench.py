@@ -399,7 +399,9 @@ def run_job(args, wl_name, steps, warmup, full=True):
     torch.manual_seed(100 + rank)
     x = torch.nn.Parameter(torch.rand(n_loc, wl["feat"], device=dev) * 0.1)      # learnable node features (GAT.py:42)
     params = list(model.parameters())
-    opt = torch.optim.Adam(params + [x], lr=1e-3, weight_decay=5e-4, fused=True)   # train.py:207
+    # single GPU, small step: the whole step (sampler, forward, loss, backward, Adam) is replayed as one CUDA graph
+    use_graph = world == 1 and not strong and not args.no_cuda_graph and not args.unfused_loss
+    opt = torch.optim.Adam(params + [x], lr=1e-3, weight_decay=5e-4, fused=True, capturable=use_graph)   # train.py:207
     P = 2 * n_pos
     labels = torch.cat([torch.ones(n_pos, dtype=torch.int64, device=dev), torch.zeros(n_pos, dtype=torch.int64, device=dev)])
     lib = mg._lib.lib()
@@ -435,6 +437,21 @@ def run_job(args, wl_name, steps, warmup, full=True):
             dist.barrier()
         torch.cuda.synchronize()
 
+    graph_info = {"cuda_graph": False}
+    run_step = step                                      # (it, pos) -> loss
+
+    def capture():
+        """-> (callable like `step`, library launches per step) replaying the step as one CUDA graph; None when capture fails."""
+        try:
+            l0_ = lib.msha_launch_count()
+            cap = mg.CapturedStep(lambda pos: step(4242, pos), [pos_dev], warmup=warmup)
+            per = (lib.msha_launch_count() - l0_) // (warmup + 1)
+            return (lambda it, pos: cap(pos)), int(per)
+        except Exception as e:      # noqa: BLE001
+            torch.cuda.synchronize()
+            graph_info["cuda_graph_error"] = repr(e)[:300]
+            return None
+
     def timed(n, first_it, feed=None):
         """n steps between two CUDA events on the launching stream, barrier + synchronize on both sides -> ms / step."""
         barrier()
@@ -443,13 +460,20 @@ def run_job(args, wl_name, steps, warmup, full=True):
         e0.record()
         last = None
         for it in range(n):
-            last = feed(it) if feed is not None else step(first_it + it, pos_dev)
+            last = feed(it) if feed is not None else run_step(first_it + it, pos_dev)
         e1.record()
         barrier()
         return e0.elapsed_time(e1) / n, lib.msha_launch_count() - l0, last
 
-    for it in range(warmup):
-        step(it, pos_dev)
+    launches_per_step = None
+    if use_graph:
+        got = capture()
+        if got is not None:
+            run_step, launches_per_step = got
+            graph_info = {"cuda_graph": True, "launches_in_graph": launches_per_step}
+    if not graph_info["cuda_graph"]:
+        for it in range(warmup):
+            step(it, pos_dev)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -477,7 +501,7 @@ def run_job(args, wl_name, steps, warmup, full=True):
             torch.cuda.current_stream().wait_event(ready[b])
             if i + 1 < total[0]:
                 prefetch(i + 1)
-            loss_ = step(seed0 + i, bufs[b])
+            loss_ = run_step(seed0 + i, bufs[b])
             consumed[b].record()
             return float(loss_.item())
         return run
@@ -497,10 +521,17 @@ def run_job(args, wl_name, steps, warmup, full=True):
     variant = None
     if full and not args.contraction_free and not args.unfused_loss:
         mg.functional.SPARSE_NLL_BWD = True
-        for it in range(3):
-            step(30_000 + it, pos_dev)
+        keep_run = run_step
+        got = capture() if graph_info["cuda_graph"] else None
+        if got is not None:
+            run_step = got[0]
+        else:
+            run_step = step
+            for it in range(3):
+                step(30_000 + it, pos_dev)
         ms_var, _, _ = timed(steps, 30_003)
         mg.functional.SPARSE_NLL_BWD = False
+        run_step = keep_run
         variant = ms_var
     t = torch.tensor([ms_dev, ms_e2e, variant if variant is not None else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -608,7 +639,8 @@ def run_job(args, wl_name, steps, warmup, full=True):
         "e2e": {"value": total_edges / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(pos_host.numel() * 8), "d2h_bytes_per_step": 4,
                 "input_pipeline": "pinned batch of step i+1 copied on a second stream while step i computes; loss.item() every step"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches_per_step * steps if graph_info["cuda_graph"] else launches),
+        **graph_info,
         "clocks": clocks,
         "roofline": roofline,
         "gat_layer_roofline": gat_roofline,
@@ -1349,7 +1381,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true",
-                    help="flow / flow-ours / yearly: launch every kernel from the host instead of replaying one captured CUDA graph")
+                    help="ddi (1 GPU) / flow / flow-ours / yearly: launch every kernel from the host instead of replaying one "
+                         "captured CUDA graph")
     ap.add_argument("--contraction-free", action="store_true",
                     help="headline step with the contraction-free scorer backward (exploits the one-hot d scores of the nll "
                          "read-out); default: the general tensor-core backward, the contraction-free step reported beside it")

@@ -247,7 +247,8 @@ int msha_score_mlp_nll_bwd_sparse(const uint32_t* order, const int64_t* target, 
 int msha_score_nll_label_order(const int64_t* target, const int64_t* src, int64_t P, int64_t Hd, int64_t n_src,
                                uint64_t* keys, uint64_t* keys_tmp, uint32_t* order, uint32_t* order_tmp, void* ws,
                                size_t ws_bytes, void* stream);
-/* builder-defined sampler (the reference's --ns_rate flags are dead code, LLP.py:26-29) */
+/* builder-defined sampler (the reference's --ns_rate flags are dead code, LLP.py:26-29); like the dropout draws its Philox key
+ * folds in the device-side epoch (msha_dropout_epoch_*), so a replayed CUDA graph samples fresh pairs */
 int msha_negative_sample(uint64_t seed, int64_t P, int64_t n_src, int64_t n_dst, int64_t* src, int64_t* dst,
                          void* stream);
 int msha_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* keep, void* stream);

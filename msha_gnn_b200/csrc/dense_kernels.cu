@@ -727,6 +727,7 @@ __global__ void negative_sample_kernel(uint64_t seed, int64_t P, uint32_t n_src,
     // one thread per Philox block = 2 pairs
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b * 2 >= P) return;
+    seed = drop_seed_eff(seed);        // folds in the device-side epoch: a replayed CUDA graph draws fresh negatives (epoch 0: unchanged)
     Philox4 r = philox4x32_10((uint32_t)b, (uint32_t)((uint64_t)b >> 32), 1u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
     src[2 * b] = (int64_t)(((uint64_t)r.x * n_src) >> 32);
     dst[2 * b] = (int64_t)(((uint64_t)r.y * n_dst) >> 32);
