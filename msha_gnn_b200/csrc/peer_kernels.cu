@@ -471,13 +471,14 @@ MSHA_API int msha_peer_allreduce_f64(double* out, const uint64_t* src_tab, int64
 //   list_beg/list_end  range of `lists` (row ids inside the peer's block) handled by this launch, per peer
 //   local_off          row of this rank's compact buffer where entry list_first[q] of peer q's segment lives
 // ---------------------------------------------------------------------------------------------
+template <typename VecT>
 __global__ void __launch_bounds__(PULL_THREADS)
-peer_gather_rows_kernel(float4* __restrict__ dst, const uint64_t* __restrict__ src_tab, int world, int rank,
+peer_gather_rows_kernel(VecT* __restrict__ dst, const uint64_t* __restrict__ src_tab, int world, int rank,
                         const int32_t* __restrict__ lists, const int64_t* __restrict__ list_beg,
                         const int64_t* __restrict__ list_end, const int64_t* __restrict__ list_first,
                         const int64_t* __restrict__ local_off, int row_vec) {
     const int q = (rank + 1 + blockIdx.y) % world;
-    const float4* __restrict__ src = reinterpret_cast<const float4*>(src_tab[q]);
+    const VecT* __restrict__ src = reinterpret_cast<const VecT*>(src_tab[q]);
     const int64_t b = list_beg[q], e = list_end[q];
     const int64_t total = (e - b) * row_vec;
     const int64_t base = local_off[q] - list_first[q];
@@ -489,20 +490,24 @@ peer_gather_rows_kernel(float4* __restrict__ dst, const uint64_t* __restrict__ s
     }
 }
 
+__device__ __forceinline__ void vec_atomic_add(float4* p, float4 x) { atomicAdd(p, x); }
+__device__ __forceinline__ void vec_atomic_add(float2* p, float2 x) { atomicAdd(p, x); }
+__device__ __forceinline__ void vec_atomic_add(float* p, float x) { atomicAdd(p, x); }
+
+template <typename VecT>
 __global__ void __launch_bounds__(PULL_THREADS)
-peer_scatter_add_rows_kernel(float* __restrict__ dst, const uint64_t* __restrict__ src_tab, int world, int rank,
+peer_scatter_add_rows_kernel(VecT* __restrict__ dst, const uint64_t* __restrict__ src_tab, int world, int rank,
                              const int32_t* __restrict__ lists, const int64_t* __restrict__ list_ptr,
                              const int64_t* __restrict__ remote_off, int row_vec) {
     const int q = (rank + 1 + blockIdx.y) % world;
-    const float4* __restrict__ src = reinterpret_cast<const float4*>(src_tab[q]) + remote_off[q] * row_vec;
+    const VecT* __restrict__ src = reinterpret_cast<const VecT*>(src_tab[q]) + remote_off[q] * row_vec;
     const int64_t b = list_ptr[q], e = list_ptr[q + 1];
     const int64_t total = (e - b) * row_vec;
     const int64_t stride = (int64_t)gridDim.x * PULL_THREADS;
     for (int64_t i = (int64_t)blockIdx.x * PULL_THREADS + threadIdx.x; i < total; i += stride) {
         const int64_t k = i / row_vec;
         const int v = (int)(i % row_vec);
-        const float4 x = src[k * row_vec + v];
-        atomicAdd(reinterpret_cast<float4*>(dst) + (int64_t)lists[b + k] * row_vec + v, x);     // rows of different peers collide
+        vec_atomic_add(dst + (int64_t)lists[b + k] * row_vec + v, src[k * row_vec + v]);     // rows of different peers collide
     }
 }
 
@@ -520,12 +525,20 @@ MSHA_API int msha_peer_gather_rows(float* dst, const uint64_t* src_tab, int worl
                                    const int64_t* local_off, int64_t max_rows_per_peer, int64_t C, int max_ctas,
                                    void* stream) {
     MSHA_REQUIRE(dst && src_tab && lists && list_beg && list_end && list_first && local_off, "peer_gather_rows: null argument");
-    MSHA_REQUIRE(C > 0 && C % 4 == 0 && ((uintptr_t)dst & 15) == 0, "peer_gather_rows: rows must be whole 128-bit vectors");
+    MSHA_REQUIRE(C > 0 && ((uintptr_t)dst & 15) == 0, "peer_gather_rows: bad row width / alignment");
     if (world == 1 || max_rows_per_peer <= 0) return 0;
-    dim3 grid(rows_grid(max_rows_per_peer, (int)(C / 4), world, max_ctas), (unsigned)(world - 1));
-    peer_gather_rows_kernel<<<grid, PULL_THREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(dst), src_tab, world, rank,
-                                                                             lists, list_beg, list_end, list_first, local_off,
-                                                                             (int)(C / 4));
+    const int vw = C % 4 == 0 ? 4 : (C % 2 == 0 ? 2 : 1);           // widest vector that tiles a row (rows stay aligned to it)
+    dim3 grid(rows_grid(max_rows_per_peer, (int)(C / vw), world, max_ctas), (unsigned)(world - 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vw == 4)
+        peer_gather_rows_kernel<float4><<<grid, PULL_THREADS, 0, st>>>(reinterpret_cast<float4*>(dst), src_tab, world, rank, lists,
+                                                                        list_beg, list_end, list_first, local_off, (int)(C / 4));
+    else if (vw == 2)
+        peer_gather_rows_kernel<float2><<<grid, PULL_THREADS, 0, st>>>(reinterpret_cast<float2*>(dst), src_tab, world, rank, lists,
+                                                                        list_beg, list_end, list_first, local_off, (int)(C / 2));
+    else
+        peer_gather_rows_kernel<float><<<grid, PULL_THREADS, 0, st>>>(dst, src_tab, world, rank, lists, list_beg, list_end,
+                                                                       list_first, local_off, (int)C);
     MSHA_LAUNCH_OK();
     return 0;
 }
@@ -537,11 +550,19 @@ MSHA_API int msha_peer_scatter_add_rows(float* dst, const uint64_t* src_tab, int
                                         const int64_t* list_ptr, const int64_t* remote_off, int64_t max_rows_per_peer,
                                         int64_t C, int max_ctas, void* stream) {
     MSHA_REQUIRE(dst && src_tab && lists && list_ptr && remote_off, "peer_scatter_add_rows: null argument");
-    MSHA_REQUIRE(C > 0 && C % 4 == 0 && ((uintptr_t)dst & 15) == 0, "peer_scatter_add_rows: rows must be whole 128-bit vectors");
+    MSHA_REQUIRE(C > 0 && ((uintptr_t)dst & 15) == 0, "peer_scatter_add_rows: bad row width / alignment");
     if (world == 1 || max_rows_per_peer <= 0) return 0;
-    dim3 grid(rows_grid(max_rows_per_peer, (int)(C / 4), world, max_ctas), (unsigned)(world - 1));
-    peer_scatter_add_rows_kernel<<<grid, PULL_THREADS, 0, (cudaStream_t)stream>>>(dst, src_tab, world, rank, lists, list_ptr,
-                                                                                  remote_off, (int)(C / 4));
+    const int vw = C % 4 == 0 ? 4 : (C % 2 == 0 ? 2 : 1);
+    dim3 grid(rows_grid(max_rows_per_peer, (int)(C / vw), world, max_ctas), (unsigned)(world - 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vw == 4)
+        peer_scatter_add_rows_kernel<float4><<<grid, PULL_THREADS, 0, st>>>(reinterpret_cast<float4*>(dst), src_tab, world, rank, lists,
+                                                                             list_ptr, remote_off, (int)(C / 4));
+    else if (vw == 2)
+        peer_scatter_add_rows_kernel<float2><<<grid, PULL_THREADS, 0, st>>>(reinterpret_cast<float2*>(dst), src_tab, world, rank, lists,
+                                                                             list_ptr, remote_off, (int)(C / 2));
+    else
+        peer_scatter_add_rows_kernel<float><<<grid, PULL_THREADS, 0, st>>>(dst, src_tab, world, rank, lists, list_ptr, remote_off, (int)C);
     MSHA_LAUNCH_OK();
     return 0;
 }

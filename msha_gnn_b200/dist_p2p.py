@@ -632,6 +632,7 @@ class HaloPlan:
                 beg[q], end[q] = need_ptr[q] + b, need_ptr[q] + e
             self.chunk_args.append((torch.tensor(beg, **i64), torch.tensor(end, **i64),
                                     max(e_ - b_ for b_, e_ in zip(beg, end))))
+        self.all_args = (torch.tensor(need_ptr[:-1], **i64), torch.tensor(need_ptr[1:], **i64), max(cnt_h + [0]))
         self.list_first = torch.tensor(need_ptr[:-1], **i64)
         self.local_off = torch.tensor(self.hoff, **i64)
         # ---- the owner's view: what every peer takes from this rank's block, and where it sits in the peer's buffer
@@ -667,7 +668,7 @@ class HaloExchange:
             pg.new_channel() for _ in range(6))
         self.seq = self.gcount = self.done_checked = self.gdone_checked = 0
         self.produced = False
-        self.uses_g2 = True
+        self.uses_g2 = len(self.widths) > 1
         self.ev_start = None
         self.s_self = None
 
@@ -826,3 +827,89 @@ class _AttentionHalo(torch.autograd.Function):
         dWh = dWh_g[:part.n_local].clone()
         ds_nbr = ds_g[:part.n_local].clone()
         return (dWh, ds_nbr, ds_self) + (None,) * 9
+
+
+def _halo_gather_all(p2p: P2P, ex: HaloExchange, k=0):
+    """Own block of ``ex.bufs[k]`` is published: fetch every listed row of every peer into the halo segments."""
+    pg, part, plan = p2p.pg, p2p.part, ex.plan
+    beg, end, mx = plan.all_args
+    pg.wait(ex.ch_ready, p2p.chunk_value(ex.seq, p2p.chunks - 1))
+    call("msha_peer_gather_rows", ex.bufs[k].local.data_ptr(), ex.bufs[k].tab.data_ptr(), part.world, part.rank, ptr(plan.need, I32),
+         beg.data_ptr(), end.data_ptr(), plan.list_first.data_ptr(), plan.local_off.data_ptr(), mx, ex.widths[k], p2p.max_ctas,
+         _stream())
+    pg.signal(ex.ch_done, ex.seq)
+
+
+def _halo_add_all(p2p: P2P, ex: HaloExchange, k=0):
+    """``ex.grads[k]`` (compact numbering) is complete on every rank's stream once its flag is seen: add the peers' halo
+    segments onto the listed rows of this rank's own block."""
+    pg, part, plan = p2p.pg, p2p.part, ex.plan
+    ex.gcount += 1
+    g = ex.gcount
+    pg.signal(ex.ch_gready, g)
+    pg.wait(ex.ch_gready, g)
+    call("msha_peer_scatter_add_rows", ex.grads[k].local.data_ptr(), ex.grads[k].tab.data_ptr(), part.world, part.rank,
+         ptr(plan.give, I32), plan.give_ptr.data_ptr(), plan.remote_off.data_ptr(), plan.max_give, ex.widths[k], p2p.max_ctas,
+         _stream())
+    pg.signal(ex.ch_gdone, g)
+
+
+class _HaloGather(torch.autograd.Function):
+    """[n_local, w] -> [n_compact, w]: own rows + the halo rows this rank's edges reference (compact numbering of the
+    plan's graph); backward: the adjoint -- the peers' halo-segment gradients are added onto the owners' rows."""
+
+    @staticmethod
+    def forward(ctx, x, p2p: P2P, ex: HaloExchange):
+        own = _alias_rows(ex.bufs[0].local, 0, p2p.part.n_local)
+        p2p.begin_produce(ex)
+        if x.data_ptr() != own.data_ptr():
+            own.copy_(x)
+        p2p.publish(ex)
+        _halo_gather_all(p2p, ex)
+        ex.produced = False
+        ctx.p2p, ctx.ex = p2p, ex
+        return _alias_rows(ex.bufs[0].local, 0, ex.plan.n_compact)
+
+    @staticmethod
+    def backward(ctx, g):
+        p2p, ex = ctx.p2p, ctx.ex
+        dst = ex.grads[0].local
+        if g.data_ptr() != dst.data_ptr():
+            p2p.ensure_grad_guard(ex)
+            dst.copy_(g)
+        _halo_add_all(p2p, ex)
+        return dst[:p2p.part.n_local].clone(), None, None
+
+
+class _HaloScatterAdd(torch.autograd.Function):
+    """[n_compact, w] per-rank contributions in the compact numbering -> [n_local, w] sums over the ranks of the own rows
+    (the reduce-scatter of ``alpha.T @ h2``, Ours.py:100, restricted to referenced recipients); backward: the halo gather."""
+
+    @staticmethod
+    def forward(ctx, x, p2p: P2P, ex: HaloExchange):
+        dst = ex.grads[0].local
+        if x.data_ptr() != dst.data_ptr():
+            p2p.ensure_grad_guard(ex)
+            dst.copy_(x)
+        _halo_add_all(p2p, ex)
+        ctx.p2p, ctx.ex = p2p, ex
+        return dst[:p2p.part.n_local].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        p2p, ex = ctx.p2p, ctx.ex
+        own = _alias_rows(ex.bufs[0].local, 0, p2p.part.n_local)
+        p2p.begin_produce(ex)
+        own.copy_(g)
+        p2p.publish(ex)
+        _halo_gather_all(p2p, ex)
+        ex.produced = False
+        return _alias_rows(ex.bufs[0].local, 0, ex.plan.n_compact), None, None
+
+
+def halo_gather(p2p: P2P, plan: HaloPlan, x_local, key):
+    return _HaloGather.apply(x_local, p2p, p2p.halo_exchange(key, plan, (x_local.shape[1],)))
+
+
+def halo_scatter_add(p2p: P2P, plan: HaloPlan, x_compact, key):
+    return _HaloScatterAdd.apply(x_compact, p2p, p2p.halo_exchange(key, plan, (x_compact.shape[1],)))

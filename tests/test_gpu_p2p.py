@@ -224,13 +224,14 @@ def test_second_step_reuses_buffers(monkeypatch):
         assert rel_err(res[r][1][1].cpu().numpy(), res[r][0][1].cpu().numpy()) < 1e-6
 
 
-@pytest.mark.parametrize("variant,world", [(3, 2), (1, 2), (1, 3)])
-def test_partitioned_msha_layer_matches_single_gpu(variant, world):
+@pytest.mark.parametrize("variant,world,halo", [(3, 2, True), (1, 2, True), (1, 3, True), (1, 3, False)])
+def test_partitioned_msha_layer_matches_single_gpu(variant, world, halo, monkeypatch):
     """dist_msha.ours_encode on emulated ranks (gather of h1, reduce-scatter of alpha.T @ h2, BN statistics and intra-scale
     group tables all-reduced over peer memory) == layers.msha_heads_forward on one GPU: pair scores elu(u_i . v_j), and the
     gradients of the features and of every layer parameter.  (Ours.py:54-109 / Ablation.py:260-277.)"""
     from msha_gnn_b200 import dist_msha as dm
     from msha_gnn_b200.layers import msha_heads_forward
+    monkeypatch.setattr(mp2p, "HALO", halo)              # halo: only the referenced recipients cross ranks (H = 2: 64-bit rows)
     dev = torch.device(DEV)
     rng = np.random.default_rng(variant * 10 + world)
     N, M, F, d, H, B, P = 301, 53, 16, 8, 2, 40, 500
@@ -267,7 +268,7 @@ def test_partitioned_msha_layer_matches_single_gpu(variant, world):
         ps, pr = md.Partition(N, world, r), md.Partition(M, world, r)
         keep = (rows >= ps.lo) & (rows < ps.hi)
         pgraph = md.partition_graph(torch.from_numpy(rows[keep]).to(dev), torch.from_numpy(cols[keep]).to(dev), ps, col_part=pr)
-        comm = dm.PeerComm({id(ps): mp2p.P2P(fab.groups[r], ps), id(pr): mp2p.P2P(fab.groups[r], pr)})
+        comm = dm.PeerComm({id(ps): mp2p.P2P(fab.groups[r], ps), id(pr): mp2p.P2P(fab.groups[r], pr)}, halo=halo)
         my = copy.deepcopy(layers)
         Sl = S[ps.lo:ps.hi].clone().requires_grad_(True)
         Rl = R[pr.lo:pr.hi].clone().requires_grad_(True)
