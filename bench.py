@@ -389,11 +389,18 @@ def run_job(args, wl_name, steps, warmup, full=True):
     graph.attention_csc()
     use_p2p = world > 1 and args.comm == "p2p"
     p2p = None
+    comm_note = None
     if use_p2p:
         from msha_gnn_b200 import peer
         if _FABRIC[0] is None:
-            _FABRIC[0] = peer.SymmFabric()
-        p2p = mdist.P2P(_FABRIC[0].group, part)
+            try:
+                _FABRIC[0] = peer.SymmFabric()
+            except Exception as e:      # noqa: BLE001  (no peer-mappable memory on this box: say so and use the collectives)
+                _FABRIC[0] = repr(e)[:300]
+        if isinstance(_FABRIC[0], str):
+            use_p2p, comm_note = False, "peer-memory exchange unavailable (" + _FABRIC[0] + "): NCCL collectives used instead"
+        else:
+            p2p = mdist.P2P(_FABRIC[0].group, part)
     torch.manual_seed(42)                                                        # identical parameters on every rank
     model = mg.GATLinkModel(wl["feat"], wl["hidden"], wl["heads"], L, wl["pred_hidden"], dropout=0.0).to(dev)
     torch.manual_seed(100 + rank)
@@ -635,6 +642,7 @@ def run_job(args, wl_name, steps, warmup, full=True):
                        "large blocks (msha_gnn_b200/peer.py, dist.py)" if use_p2p else "as NCCL all_gather / reduce_scatter")
                     + "; pairs data-parallel; parameter gradients all-reduced (NCCL)"),
         "scorer_backward": bwd_kind,
+        **({"comm_note": comm_note} if comm_note else {}),
         "pairs_per_sec": P_global / (ms_dev / 1e3),
         "e2e": {"value": total_edges / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(pos_host.numel() * 8), "d2h_bytes_per_step": 4,

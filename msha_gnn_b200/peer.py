@@ -22,7 +22,7 @@ from . import ops
 from .ops import call
 
 MAX_CHANNELS = 512
-TIMEOUT_NS = int(float(os.environ.get("MSHA_PEER_TIMEOUT_S", "30")) * 1e9)
+TIMEOUT_NS = int(float(os.environ.get("MSHA_PEER_TIMEOUT_S", "60")) * 1e9)
 # blocks up to this many bytes are pulled by one SM kernel (P2P loads, one launch for all peers); larger ones by the
 # copy engines (no SM time, one cudaMemcpyAsync per peer)
 CE_MIN_BYTES = int(os.environ.get("MSHA_PEER_CE_MIN_BYTES", str(4 << 20)))
