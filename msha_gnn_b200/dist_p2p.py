@@ -566,6 +566,44 @@ def _conv_hook(p2p: P2P, nex: Exchange, conv):
 HALO = os.environ.get("MSHA_HALO", "1") != "0"
 
 
+def halo_need(col_padded: torch.Tensor, world: int, rank: int, n_max: int):
+    """Host-side logic of the halo exchange, step 1 (pure index arithmetic; runs on any device): from a rank's column ids in
+    the gathered numbering ``owner * n_max + local`` -> (uniq, inv, owner, remote, cnt, need): the sorted distinct ids, the
+    position of every edge's column in them, their owners, which of them are remote, how many rows of every peer's block the
+    rank references (cnt[rank] = 0), and those rows (ids inside the owner's block, concatenated by owner, ascending)."""
+    uniq, inv = torch.unique(col_padded.long(), return_inverse=True)       # sorted padded ids = sorted by (owner, local row)
+    owner = torch.div(uniq, n_max, rounding_mode="floor")
+    cnt = torch.bincount(owner, minlength=world)
+    cnt[rank] = 0
+    remote = owner != rank
+    need = (uniq[remote] - owner[remote] * n_max).to(I32)
+    return uniq, inv, owner, remote, [int(c) for c in cnt.tolist()], need
+
+
+def halo_offsets(counts, q: int, n_max: int):
+    """Step 2: rank q's compact numbering is [own block (n_max rows) | halo of peer 0 | halo of peer 1 | ...], every segment
+    starting on a multiple of 4 rows.  ``counts[p]`` = rows q takes from p.  -> (segment start per peer, total rows)."""
+    off, o = [], n_max
+    for p_ in range(len(counts)):
+        off.append(o)
+        if p_ != q:
+            o += (counts[p_] + 3) // 4 * 4
+    return off, o
+
+
+def halo_compact_ids(uniq, owner, remote, rank: int, n_max: int, hoff, need_ptr):
+    """Step 3: compact id of every distinct column: own columns keep their local row, the k-th referenced row of peer p sits
+    at ``hoff[p] + k``."""
+    dev = uniq.device
+    comp = torch.empty_like(uniq)
+    comp[~remote] = uniq[~remote] - rank * n_max
+    hoff_t = torch.tensor(hoff, dtype=torch.int64, device=dev)
+    ptr_t = torch.tensor(need_ptr[:-1], dtype=torch.int64, device=dev)
+    ro = owner[remote]
+    comp[remote] = hoff_t[ro] + (torch.arange(int(remote.sum()), device=dev) - ptr_t[ro])
+    return comp
+
+
 class HaloPlan:
     """Per rank and graph: which rows of every peer's block this rank's edges reference (``need``), the compact column
     numbering ``[own block | halo of peer 0 | halo of peer 1 | ...]`` with the graph rebuilt in it, the same lists seen from
@@ -578,30 +616,17 @@ class HaloPlan:
         dev = pgraph.device
         K = p2p.chunks
         rp, col = pgraph.attention_csr()
-        colp = col.long()
-        uniq, inv = torch.unique(colp, return_inverse=True)            # sorted padded ids = sorted by (owner, local row)
-        owner = torch.div(uniq, n_max, rounding_mode="floor")
-        cnt = torch.bincount(owner, minlength=W)
-        cnt[r] = 0
-        cnt_h = [int(c) for c in cnt.tolist()]
+        uniq, inv, owner, remote, cnt_h, need = halo_need(col, W, r, n_max)
         # ---- counts of every rank (symmetric meta buffer), then the lists
         meta = pg.alloc((W, W), torch.int64)
         lists_sym = pg.alloc((part.n_padded,), I32)
-        meta.local[r].copy_(cnt)
-        remote = owner != r
-        need = (uniq[remote] - owner[remote] * n_max).to(I32)          # rows inside the owner's block, concatenated by owner
+        meta.local[r].copy_(torch.tensor(cnt_h, dtype=torch.int64, device=dev))
         lists_sym.local[: need.numel()].copy_(need)
         pg.barrier()
         all_cnt = torch.stack([meta.views[q][q] for q in range(W)]).cpu().tolist()      # all_cnt[q][p]: rank q needs from p
-        pad4 = lambda v: (v + 3) // 4 * 4
 
-        def offsets(counts, q):                                        # halo segment starts of rank q's compact numbering
-            off, o = [], n_max
-            for p_ in range(W):
-                off.append(o)
-                if p_ != q:
-                    o += pad4(counts[p_])
-            return off, o
+        def offsets(counts, q):
+            return halo_offsets(counts, q, n_max)
         self.hoff, n_compact = offsets(all_cnt[r], r)
         self.n_compact = max(offsets(all_cnt[q], q)[1] for q in range(W))      # same buffer shape on every rank
         need_ptr = [0]
@@ -609,12 +634,7 @@ class HaloPlan:
             need_ptr.append(need_ptr[-1] + (cnt_h[q] if q != r else 0))
         self.need, self.need_ptr, self.cnt = need, need_ptr, cnt_h
         # ---- the graph in compact numbering
-        comp = torch.empty_like(uniq)
-        comp[~remote] = uniq[~remote] - r * n_max
-        hoff_t = torch.tensor(self.hoff, dtype=torch.int64, device=dev)
-        ptr_t = torch.tensor(need_ptr[:-1], dtype=torch.int64, device=dev)
-        ro = owner[remote]
-        comp[remote] = hoff_t[ro] + (torch.arange(int(remote.sum()), device=dev) - ptr_t[ro])
+        comp = halo_compact_ids(uniq, owner, remote, r, n_max, self.hoff, need_ptr)
         self.graph = Graph(pgraph.rowptr, comp[inv].to(I32).contiguous(), pgraph.val, pgraph.n_rows, self.n_compact, isolated="zero")
         self.graph.col_padded = col                                    # the gathered-layout ids (bench.py's parity block)
         # ---- chunk boundaries of the pulls: chunk c of peer q = its rows [(n_q c) // K, (n_q (c+1)) // K)

@@ -233,3 +233,69 @@ def test_partitioned_msha_layer_algebra_gloo():
     ret = mp.Manager().dict()
     mp.spawn(_msha_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_halo_numbering_host_logic():
+    """Host-side index arithmetic of the halo exchange (dist_p2p.halo_need / halo_offsets / halo_compact_ids) on simulated
+    ranks, CPU tensors: the compact numbering reproduces the gathered one (forward gather), and the owners' "give" lists --
+    read out of the peers' "need" lists exactly as HaloPlan reads them out of peer memory -- make the scatter-add the adjoint
+    of the gather (the gradient's way back equals a reduce-scatter of the dense gathered gradient)."""
+    from msha_gnn_b200.dist_p2p import halo_need, halo_offsets, halo_compact_ids
+    rng = np.random.default_rng(5)
+    N, W, C = 103, 4, 3
+    parts = [Partition(N, W, r) for r in range(W)]
+    n_max = parts[0].n_max
+    feat = torch.tensor(rng.standard_normal((N, C)))
+    gathered = torch.zeros(parts[0].n_padded, C, dtype=torch.float64)                 # the whole-block gathered layout
+    gathered[parts[0].to_padded(torch.arange(N))] = feat
+    cols = [torch.from_numpy(rng.choice(N, size=rng.integers(5, 60), replace=True)) for _ in range(W)]   # each rank's edge columns
+    plans = []
+    for r in range(W):
+        colp = parts[r].to_padded(cols[r])
+        uniq, inv, owner, remote, cnt, need = halo_need(colp, W, r, n_max)
+        need_ptr = [0]
+        for q in range(W):
+            need_ptr.append(need_ptr[-1] + (cnt[q] if q != r else 0))
+        plans.append(dict(colp=colp, uniq=uniq, inv=inv, owner=owner, remote=remote, cnt=cnt, need=need, need_ptr=need_ptr))
+    all_cnt = [p["cnt"] for p in plans]
+    n_compact = max(halo_offsets(all_cnt[q], q, n_max)[1] for q in range(W))
+    grads, comps = [], []
+    for r, p in enumerate(plans):
+        hoff, _ = halo_offsets(all_cnt[r], r, n_max)
+        comp = halo_compact_ids(p["uniq"], p["owner"], p["remote"], r, n_max, hoff, p["need_ptr"])[p["inv"]]
+        comps.append(comp)
+        assert int(comp.max()) < n_compact and all(h % 4 == 0 for h in hoff)
+        # forward: own block + the listed rows of every peer's own block, packed at hoff[q] (msha_peer_gather_rows)
+        buf = torch.full((n_compact, C), float("nan"), dtype=torch.float64)
+        buf[: parts[r].n_local] = feat[parts[r].lo:parts[r].hi]
+        for q in range(W):
+            if q != r:
+                rows = p["need"][p["need_ptr"][q]:p["need_ptr"][q + 1]].long()
+                assert torch.all(rows[1:] > rows[:-1])                                   # ascending, distinct
+                buf[hoff[q]:hoff[q] + rows.numel()] = feat[parts[q].lo + rows]
+        assert torch.equal(buf[comp], gathered[p["colp"]])                               # same rows as the whole-block gather
+        g = torch.zeros(n_compact, C, dtype=torch.float64)                               # a gradient in the compact numbering
+        g.index_add_(0, comp, torch.tensor(rng.standard_normal((comp.numel(), C))))
+        grads.append(g)
+    # backward: owner r adds, for every peer q, q's halo segment for r onto the rows q listed (msha_peer_scatter_add_rows)
+    for r in range(W):
+        own = grads[r][: parts[r].n_local].clone()
+        for q in range(W):
+            if q == r:
+                continue
+            n_q = all_cnt[q][r]
+            start = sum(all_cnt[q][p_] for p_ in range(r) if p_ != q)                    # HaloPlan's read of peer q's list buffer
+            give = plans[q]["need"][start:start + n_q].long()
+            off = halo_offsets(all_cnt[q], q, n_max)[0][r]
+            own.index_add_(0, give, grads[q][off:off + n_q])
+        dense = torch.zeros(parts[0].n_padded, C, dtype=torch.float64)                    # reduce-scatter of the dense gathered gradients
+        for q in range(W):
+            dq = torch.zeros_like(dense)
+            # scatter q's compact gradient back to the gathered numbering through its (compact id -> padded id) map
+            pad_of = torch.zeros(n_compact, dtype=torch.int64)
+            pad_of[comps[q]] = plans[q]["colp"]
+            used = torch.unique(comps[q])
+            dq.index_add_(0, pad_of[used], grads[q][used])
+            dense += dq
+        want = dense[r * n_max: r * n_max + parts[r].n_local]
+        assert torch.allclose(own, want, atol=1e-12)
