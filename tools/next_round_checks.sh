@@ -1,16 +1,14 @@
 #!/bin/bash
-# One gpurun call that settles what round 1 left pending:
-#   * the whole GPU suite on the final code
-#   * the default step with the pair order by label (default) and by (label, src) (MSHA_NLL_ORDER=src), with the per-step trace
-#     of the device-timed loop (host enqueue ms, GPU ms, allocator reserve, GC) -- the src order becomes the default if its
-#     trace shows no allocator growth inside the timed loop and dev ms/step is ~4.05
-#   usage:  gpurun --timeout 300 -- 'bash tools/next_round_checks.sh'
+# Measurements round 2 left open (DESIGN.md sections 7 / 8); each line is one gpurun call on an 8-GPU box:
+#   * the partitioned MSHA layer with the halo exchange at the named cfg-5 shape (built, parity-tested, measured at 2 GPUs only)
+#   * the R-MAT strong-scaling step with a phase trace on the final (sequential halo) code
+#   usage:  gpurun --gpus 8 --timeout 900 -- 'bash tools/next_round_checks.sh'
 set -u
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/next_gpu_tests.log
-for order in label src; do
-    MSHA_BENCH_TRACE=1 MSHA_NLL_ORDER=$order python bench.py --no-cpu-baseline --steps 20 \
-        > gpurun_out/next_bench_$order.json 2> gpurun_out/next_bench_$order.trace
-    tail -1 gpurun_out/next_bench_$order.json | python tools/bench_summary.py "order=$order"
-    grep "dev loop trace" gpurun_out/next_bench_$order.trace | cut -c1-700
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29530"
+for halo in 0 1; do
+    MSHA_MSHA_HALO=$halo $T bench.py --gpus 8 --workload ours --steps 5 > gpurun_out/next_ours_n8_halo$halo.json 2> gpurun_out/next_ours_n8_halo$halo.err
+    python tools/bench_summary.py "ours n8 halo=$halo" < gpurun_out/next_ours_n8_halo$halo.json
 done
+bash tools/rmat_n.sh 8 next_trace MSHA_P2P_TRACE=1
+grep "p2p trace rank 0" gpurun_out/rmat_next_trace.err | cut -c1-2000
