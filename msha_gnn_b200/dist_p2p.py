@@ -479,8 +479,6 @@ def gat_encode_p2p(convs, x_local, pgraph: Graph, part, p2p: P2P, training=True,
     pgraph.hub_rows()
     pgraph.hub_cols()
     convs = list(convs)
-    pg = p2p.pg
-    K = p2p.chunks
     chained = None                                        # exchange whose own blocks the previous layer's hook produced
     def layer_exchange(l_, conv_):
         H_, C_ = conv_.heads, conv_.heads * conv_.out_features

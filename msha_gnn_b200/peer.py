@@ -46,7 +46,6 @@ class PeerTensor:
         self.local = views[rank]
         self.addr = [int(v.data_ptr()) for v in views]
         self.tab = torch.tensor(self.addr, dtype=torch.int64, device=self.local.device)      # device table for kernels
-        self._keep = None
 
 
 class PeerGroup:
