@@ -635,6 +635,12 @@ class HaloPlan:
         comp = halo_compact_ids(uniq, owner, remote, r, n_max, self.hoff, need_ptr)
         self.graph = Graph(pgraph.rowptr, comp[inv].to(I32).contiguous(), pgraph.val, pgraph.n_rows, self.n_compact, isolated="zero")
         self.graph.col_padded = col                                    # the gathered-layout ids (bench.py's parity block)
+        # the host-synchronising one-off builds of the compact graph happen here, not lazily in the first backward pass: a
+        # backward node whose host thread blocks behind kernels that wait for a peer's flag stalls that rank, and ranks
+        # emulated in ONE process share autograd's device thread -- the peer's signalling nodes would then never be enqueued
+        self.graph.attention_csc()
+        self.graph.hub_rows()
+        self.graph.hub_cols()
         # ---- chunk boundaries of the pulls: chunk c of peer q = its rows [(n_q c) // K, (n_q (c+1)) // K)
         i64 = dict(dtype=torch.int64, device=dev)
         need_l = need.long()

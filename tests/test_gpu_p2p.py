@@ -132,6 +132,8 @@ def _emulate(world, N, rows, cols, convs_ref, predictor_ref, x_full, src, dst, l
     fab = peer.LocalFabric(world, dev)
     P = src.numel()
     state = [None] * world
+    import threading
+    together = threading.Barrier(world)
 
     def rank_step(r):
         part = md.Partition(N, world, r)
@@ -143,6 +145,7 @@ def _emulate(world, N, rows, cols, convs_ref, predictor_ref, x_full, src, dst, l
         st["h"] = md.gat_encode_p2p(st["convs"], st["x"], pgraph, part, st["p2p"], score_key="score_h")
         st["loss"] = md.score_pairs(st["pred"], st["h"], src[lo:hi], dst[lo:hi], part, target=labels[lo:hi],
                                     global_pairs=P, p2p=st["p2p"])
+        together.wait(timeout=60)       # the ranks' backward passes share autograd's one device thread: enter it together
         st["loss"].backward()
         state[r] = st
     _run_ranks(fab, rank_step)
