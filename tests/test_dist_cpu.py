@@ -299,3 +299,30 @@ def test_halo_numbering_host_logic():
             dense += dq
         want = dense[r * n_max: r * n_max + parts[r].n_local]
         assert torch.allclose(own, want, atol=1e-12)
+
+
+def test_backward_passes_of_the_peer_path_never_synchronise_the_host():
+    """Source check.  A backward node that blocks its host thread (device-to-host read, pageable upload, lazily built CSC /
+    hub table) does so behind kernels that wait for a peer's flag; ranks emulated in one process share autograd's device
+    thread, so the peer's signalling node is then never enqueued (profiles/r02_gpu_tests_last_run.txt).  Every
+    ``backward`` of dist_p2p / dist_msha therefore works on tables that exist already: HaloPlan / gat_encode_p2p build them."""
+    import ast
+    import inspect
+    from msha_gnn_b200 import dist_p2p, dist_msha
+    blocking = {"item", "tolist", "cpu", "synchronize", "nonzero", "unique", "numpy"}
+    seen = 0
+    for mod in (dist_p2p, dist_msha):
+        tree = ast.parse(inspect.getsource(mod))
+        for cls in [n for n in ast.walk(tree) if isinstance(n, ast.ClassDef)]:
+            for fn in [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "backward"]:
+                seen += 1
+                for node in ast.walk(fn):
+                    if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute):
+                        assert node.func.attr not in blocking, (mod.__name__, cls.name, node.func.attr, node.lineno)
+                        assert not (node.func.attr in ("tensor", "as_tensor") and getattr(node.func.value, "id", "") == "torch"), \
+                            (mod.__name__, cls.name, "host list -> device upload", node.lineno)
+    assert seen >= 6
+    # ... and the halo plan builds the compact graph's derived tables itself
+    src = inspect.getsource(dist_p2p.HaloPlan.__init__)
+    for built in ("attention_csc()", "hub_rows()", "hub_cols()"):
+        assert "self.graph." + built in src
